@@ -1,0 +1,191 @@
+"""TEST INFRASTRUCTURE ONLY - records golden vectors from the LIVE reference.
+
+Run in the build container (the only place /root/reference exists):
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/gen_golden.py
+
+Imports the unmodified reference through ``oracle/ref_harness.py``, runs
+closed-loop ``MPPI.forward`` solves on CPU for each case below and writes
+``tests/golden/<case>.npz`` holding the inputs (state, injected noise =
+``solver._action_noises``, reference path) and outputs (per-sample costs via a
+recording wrapper around ``cost_func``, lambda, action_seq, state_seq, top
+samples). It also writes the env fixtures (occupancy grids bit-packed, centre
+line) that tests and bench.py need where the reference is absent.
+
+Versions recorded in every file: torch / scipy / numpy of this container.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import scipy
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_harness as rh  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+VERSIONS = json.dumps({"torch": torch.__version__, "scipy": scipy.__version__, "numpy": np.__version__})
+
+
+class CostRecorder:
+    """Wraps a reference cost callable and keeps every per-call cost vector, so
+    the per-sample total the reference forms at src/pi_mpc/mppi.py:333-336 can
+    be rebuilt without touching the reference."""
+
+    def __init__(self, fn):
+        self.fn, self.calls = fn, []
+
+    def __call__(self, state, action, info):
+        c = self.fn(state, action, info)
+        self.calls.append(c.detach().clone())
+        return c
+
+    def take_total(self, horizon: int) -> torch.Tensor:
+        calls, self.calls = self.calls[: horizon + 1], self.calls[horizon + 1:]
+        stage = torch.stack(calls[:horizon], dim=1)
+        return torch.sum(stage, dim=1) + calls[horizon]
+
+
+def run_case(name, solver, recorder, horizon, state0, advance, n_solves, pre_solve=None, extra_cfg=None, top_n=8):
+    rec = {k: [] for k in ("state", "noise", "costs", "lam", "lam_next", "action_seq", "state_seq", "top_traj",
+                           "top_w", "refpath")}
+    state = state0.clone()
+    for s in range(n_solves):
+        if pre_solve is not None:
+            rec["refpath"].append(pre_solve(state).numpy().copy())
+        lam_before = solver._lambda
+        a, ss = solver.forward(state=state.clone())
+        rec["state"].append(state.numpy().copy())
+        rec["noise"].append(solver._action_noises.numpy().copy())
+        rec["costs"].append(recorder.take_total(horizon).numpy().copy())
+        mode = getattr(solver, "_auto_lambda", None)
+        # lambda the weights were formed with: MPO updates after the weights (mppi.py:376 vs :398)
+        rec["lam"].append(float(lam_before) if mode in (None, "MPO") else float(solver._lambda))
+        rec["lam_next"].append(float(solver._lambda))
+        rec["action_seq"].append(a.detach().numpy().copy())
+        rec["state_seq"].append(ss.detach().numpy().copy())
+        tt, tw = solver.get_top_samples(top_n)
+        rec["top_traj"].append(tt.detach().numpy().copy())
+        rec["top_w"].append(tw.detach().numpy().copy())
+        state = advance(state, a.detach())
+    out = {k: np.stack(v) for k, v in rec.items() if len(v)}
+    out["cfg"] = np.array(json.dumps(extra_cfg or {}))
+    out["versions"] = np.array(VERSIONS)
+    path = os.path.join(OUT, f"{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: {os.path.getsize(path) / 1e3:.0f} kB, lam={rec['lam']}")
+
+
+def closure_case(name, example, fn_names, cfg, state0, n_solves=3):
+    ns = rh.load_reference()
+    dyn, cost = rh.extract_closures(example, fn_names)
+    recorder = CostRecorder(cost)
+    kw = dict(cfg)
+    solver = ns.MPPI(dynamics=dyn, cost_func=recorder, u_min=torch.tensor(kw.pop("u_min")),
+                     u_max=torch.tensor(kw.pop("u_max")), sigmas=torch.tensor(kw.pop("sigmas")), **kw)
+
+    def advance(state, a):
+        return dyn(state.clone().view(1, -1), a[0].view(1, -1)).view(-1)
+
+    run_case(name, solver, recorder, cfg["horizon"], torch.tensor(state0, dtype=torch.float32), advance, n_solves,
+             extra_cfg=dict(cfg, model=example, state0=state0))
+
+
+def nav2d_case(name, cfg, n_solves=3):
+    env, ns = rh.make_navigation2d()
+    recorder = CostRecorder(env.cost_function)
+    kw = dict(cfg)
+    solver = ns.MPPI(dim_state=3, dim_control=2, dynamics=env.dynamics, cost_func=recorder, u_min=env.u_min,
+                     u_max=env.u_max, sigmas=torch.tensor(kw.pop("sigmas")), **kw)
+
+    def advance(state, a):
+        u = torch.clamp(a[0], env.u_min, env.u_max)
+        return env.dynamics(state.view(1, -1), u.view(1, -1)).view(-1)
+
+    run_case(name, solver, recorder, cfg["horizon"], env._robot_state.clone(), advance, n_solves,
+             extra_cfg=dict(cfg, model="navigation2d"))
+
+
+def racing_case(name, cfg, n_solves=3):
+    env, ctl, ns = rh.make_racing()
+    recorder = CostRecorder(ctl.cost_function)
+    kw = dict(cfg)
+    ctl.solver = ns.MPPI(dim_state=4, dim_control=2, dynamics=env.dynamics, cost_func=recorder, u_min=env.u_min,
+                         u_max=env.u_max, sigmas=torch.tensor(kw.pop("sigmas")), **kw)
+
+    def pre_solve(state):  # example/racing.py:73-81
+        ctl.reference_path, ctl.current_path_index = ctl.calc_ref_trajectory(
+            state, env.racing_center_path, ctl.current_path_index, ctl.solver._horizon, DL=0.1,
+            lookahead_distance=3, reference_path_interval=0.85)
+        return ctl.reference_path
+
+    def advance(state, a):  # racing_env.py:142-163 (step = clamp + dynamics)
+        u = torch.clamp(a[0], env.u_min, env.u_max)
+        return env.dynamics(state.view(1, -1), u.view(1, -1)).view(-1)
+
+    run_case(name, ctl.solver, recorder, cfg["horizon"], env._robot_state.clone(), advance, n_solves,
+             pre_solve=pre_solve, extra_cfg=dict(cfg, model="racing"))
+
+
+def env_fixtures():
+    env, ctl, _ = rh.make_racing()
+    om, lm = env._obstacle_map, env._lane_map
+    np.savez_compressed(
+        os.path.join(OUT, "env_racing.npz"),
+        obstacle_bits=np.packbits(om._map_torch.numpy().astype(np.uint8), axis=1),
+        lane_bits=np.packbits(lm._map_torch.numpy().astype(np.uint8), axis=1),
+        shape=np.array(om._map_torch.shape), cell=np.array([om._cell_size, lm._cell_size]),
+        origin=np.array([om._cell_map_origin, lm._cell_map_origin]),
+        lim=np.array(om.x_lim + om.y_lim, dtype=np.float64),
+        center_path=env.racing_center_path.numpy(), start_state=env._robot_state.numpy(),
+        u_min=env.u_min.numpy(), u_max=env.u_max.numpy(), wheelbase=np.array(env.L.item()),
+        v_max=np.array(env.V_MAX.item()),
+        Q=np.array([ctl.Qc, ctl.Ql, ctl.Qv, ctl.Qo, ctl.Qin, ctl.Qdin]), versions=np.array(VERSIONS))
+    env2, _ = rh.make_navigation2d()
+    om2 = env2._obstacle_map
+    np.savez_compressed(
+        os.path.join(OUT, "env_navigation2d.npz"),
+        obstacle_bits=np.packbits(om2._map_torch.numpy().astype(np.uint8), axis=1),
+        shape=np.array(om2._map_torch.shape), cell=np.array([om2._cell_size]),
+        origin=np.array([om2._cell_map_origin]), lim=np.array(om2.x_lim + om2.y_lim, dtype=np.float64),
+        start_state=env2._robot_state.numpy(), goal=env2._goal_pos.numpy(), u_min=env2.u_min.numpy(),
+        u_max=env2.u_max.numpy(), versions=np.array(VERSIONS))
+    print("env fixtures written")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    env_fixtures()
+    # BASELINE.json config 1, verbatim: the reference's own CPU-runnable case
+    closure_case("pendulum_c1", "pendulum", ["dynamics", "cost_function"],
+                 dict(horizon=50, num_samples=1000, dim_state=2, dim_control=1, u_min=[-2.0], u_max=[2.0],
+                      sigmas=[1.0], lambda_=1.0), [3.14, 0.0])
+    closure_case("pendulum_essps", "pendulum", ["dynamics", "cost_function"],
+                 dict(horizon=15, num_samples=1000, dim_state=2, dim_control=1, u_min=[-2.0], u_max=[2.0],
+                      sigmas=[1.0], lambda_="ESSPS"), [2.5, 0.5])  # example/pendulum.py:58-69
+    closure_case("cartpole", "cartpole", ["dynamics", "stage_cost"],
+                 dict(horizon=50, num_samples=512, dim_state=4, dim_control=1, u_min=[-3.0], u_max=[3.0],
+                      sigmas=[1.0], lambda_=0.001), [0.0, 0.0, 0.05, 0.0])
+    closure_case("cartpole_mpo", "cartpole", ["dynamics", "stage_cost"],
+                 dict(horizon=20, num_samples=512, dim_state=4, dim_control=1, u_min=[-3.0], u_max=[3.0],
+                      sigmas=[1.0], lambda_="MPO", use_sg_filter=True), [0.0, 0.1, 0.05, -0.1], n_solves=5)
+    closure_case("mountaincar", "mountaincar", ["dynamics", "cost_func"],
+                 dict(horizon=100, num_samples=384, dim_state=2, dim_control=1, u_min=[-1.0], u_max=[1.0],
+                      sigmas=[1.0], lambda_=0.1), [-0.5, 0.0])
+    nav2d_case("navigation2d_lbps", dict(horizon=60, num_samples=512, sigmas=[0.5, 0.5], lambda_="LBPS"))
+    nav2d_case("navigation2d_essps", dict(horizon=30, num_samples=768, sigmas=[0.5, 0.5], lambda_="ESSPS"))
+    nav2d_case("navigation2d_mpo_expl",
+               dict(horizon=30, num_samples=512, sigmas=[0.5, 0.5], lambda_="MPO", exploration=0.25), n_solves=4)
+    racing_case("racing_sg", dict(horizon=80, num_samples=512, sigmas=[0.5, 0.1], lambda_=1.0, use_sg_filter=True),
+                n_solves=4)
+    racing_case("racing_example", dict(horizon=25, num_samples=1024, sigmas=[0.5, 0.1], lambda_=1.0), n_solves=3)
+
+
+if __name__ == "__main__":
+    main()
