@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py - MPPI solves/sec (control-loop Hz) of the racing kinematic-bicycle
+solve, K=65536 samples, T=80 steps, SG filter on, lambda=1.0 (BASELINE.json
+configs[3], the configuration `metric` is quoted on).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one whole MPPI solve (sample -> clamp -> 80-step rollout of 65536
+samples -> costs -> softmax -> weighted mean -> SG filter -> optimal-trajectory
+rollout) on the closed-loop sequence of states / reference paths recorded once,
+before the timed region, so the timed solves run on inputs resident in HBM.
+N > 1: the K samples are sharded over the ranks (strong scaling: the solve is
+the unit, K is fixed); launch with torch.distributed.run as the contract says.
+
+Prints ONE JSON line (rank 0). See DESIGN.md "measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+K_SAMPLES, HORIZON = 65536, 80
+CFG = dict(model="racing", horizon=HORIZON, num_samples=K_SAMPLES, sigmas=[0.5, 0.1], lambda_=1.0, use_sg_filter=True,
+           sg_window_size=5, sg_poly_order=3, exploration=0.0, seed=42)
+# F_step(racing) = 97 fp32 flop per sample-timestep, 61 per sample for terminal + softmax
+FLOPS_PER_SOLVE = K_SAMPLES * HORIZON * 97 + K_SAMPLES * 61
+MAP_BYTES = 2 * 800 * 25 * 4
+BYTES_PER_SOLVE = 4 * K_SAMPLES + 4 * HORIZON * 2 * 2 + 16 * (HORIZON + 1) + 4 * (HORIZON + 1) * 4 + MAP_BYTES
+H2D_BYTES = 4 * 4 + 16 * (HORIZON + 1)
+D2H_BYTES = 4 * HORIZON * 2 + 4 * (HORIZON + 1) * 4
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+        self.t_mark = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def summary(self, t0, t1):
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows]
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(rows)}
+
+
+def closed_loop_inputs(n_steps: int, device):
+    """Run the engine's own closed loop once (untimed) and keep every step's
+    state [4] and reference path [T+1,4] on the device."""
+    import mppi_playground_b200 as eng
+    from engine_util import build_engine
+    from oracle import fixtures as fx  # env fixture loader only (maps, centre line)
+
+    env = fx.load_env_racing()
+    model, solver = build_engine(CFG, device=device)
+    states = torch.empty(n_steps, 4)
+    refs = torch.empty(n_steps, HORIZON + 1, 4)
+    state, cind = env.start_state.clone(), 0
+    for s in range(n_steps):
+        ref, cind = eng.racing_reference_path(state, env.center_path, cind, HORIZON, v_max=env.v_max)
+        model.reference_path_tensor = ref
+        states[s], refs[s] = state, ref
+        _, seq = solver.forward(state)
+        state = seq[0, 1].cpu()
+    del solver
+    return states, refs
+
+
+def run_b200(args, rank, local_rank, world):
+    import torch.distributed as dist
+
+    import mppi_playground_b200 as eng
+    from engine_util import build_engine
+    from mppi_playground_b200 import _capi
+
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+        pg = dist.group.WORLD
+    n_total = args.warmup + args.steps
+    # distinct inputs per step would be 5000 closed-loop python iterations; cycle through a recorded loop instead
+    n_rec = min(n_total, 256)
+    states_h, refs_h = closed_loop_inputs(n_rec, device) if rank == 0 else (torch.empty(n_rec, 4),
+                                                                           torch.empty(n_rec, HORIZON + 1, 4))
+    states_d, refs_d = states_h.to(device), refs_h.to(device)
+    if world > 1:
+        dist.broadcast(states_d, 0)
+        dist.broadcast(refs_d, 0)
+        states_h, refs_h = states_d.cpu(), refs_d.cpu()
+
+    model, solver = build_engine(CFG, device=device, process_group=pg) if world > 1 else build_engine(CFG, device=device)
+    model.reference_path_tensor = refs_d[0]
+    lib, h = solver._lib, solver._h
+    solver._bind_maps(required=True)
+    action = torch.empty(HORIZON, 2, device=device)
+    seq = torch.empty(HORIZON + 1, 4, device=device)
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
+    stream = torch.cuda.current_stream(device)
+    sp = stream.cuda_stream
+
+    def solve(i):
+        j = i % n_rec
+        if world == 1:
+            _capi.check(lib.mppi_solve(h, states_d[j].data_ptr(), refs_d[j].data_ptr(), None, action.data_ptr(),
+                                       seq.data_ptr(), sp))
+        else:
+            model.reference_path_tensor = refs_d[j]
+            solver.forward(states_d[j])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for i in range(args.warmup):
+        solve(i)
+        flush.zero_()
+    # ---- timed region: K solves, L2 flushed between them, each bracketed by CUDA events on the launch stream
+    solver.kernel_timing(True)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        ev[i][0].record(stream)
+        solve(args.warmup + i)
+        ev[i][1].record(stream)
+        flush.zero_()
+    barrier()
+    t1 = time.perf_counter()
+    per_step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(per_step_ms)], device=device, dtype=torch.float64)
+    kern_ms, kern_n = solver.kernel_time_ms()
+    solver.kernel_timing(False)
+    launches = solver.launch_info()["launches_last_solve"] * args.steps
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = total_ms.item() / args.steps
+    # back-to-back (no flush, one bracket) for context
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        solve(args.warmup + i)
+    e1.record(stream)
+    barrier()
+    b2b_ms = e0.elapsed_time(e1) / args.steps
+
+    # ---- end to end through the C ABI with HOST buffers (H2D + solve + D2H + sync every step)
+    e2e = None
+    if world == 1:
+        a_h = np.empty((HORIZON, 2), np.float32)
+        s_h = np.empty((HORIZON + 1, 4), np.float32)
+        st_np, rf_np = states_h.numpy(), refs_h.numpy()
+        n_e2e = min(args.steps, 2000)
+        for i in range(min(args.warmup, 20)):
+            _capi.check(lib.mppi_solve_host(h, st_np[i % n_rec].ctypes.data, rf_np[i % n_rec].ctypes.data,
+                                            a_h.ctypes.data, s_h.ctypes.data))
+        torch.cuda.synchronize(device)
+        spent = 0.0
+        for i in range(n_e2e):
+            flush.zero_()
+            torch.cuda.synchronize(device)
+            j = (args.warmup + i) % n_rec
+            c0 = time.perf_counter()
+            _capi.check(lib.mppi_solve_host(h, st_np[j].ctypes.data, rf_np[j].ctypes.data, a_h.ctypes.data,
+                                            s_h.ctypes.data))
+            spent += time.perf_counter() - c0
+        e2e = {"value": n_e2e / spent, "unit": "solves/s", "h2d_bytes_per_step": H2D_BYTES,
+               "d2h_bytes_per_step": D2H_BYTES, "steps": n_e2e,
+               "api": "mppi_solve_host (C ABI, pinned staging, H2D + solve + D2H + stream sync per step)"}
+    else:
+        n_e2e = min(args.steps, 500)
+        spent = torch.zeros(1, dtype=torch.float64, device=device)
+        for i in range(n_e2e):
+            j = (args.warmup + i) % n_rec
+            barrier()
+            c0 = time.perf_counter()
+            model.reference_path_tensor = refs_h[j]  # host tensors: forward() uploads them
+            a, sq = solver.forward(states_h[j])
+            a_host, s_host = a.cpu(), sq.cpu()
+            spent += time.perf_counter() - c0
+        dist.all_reduce(spent, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_e2e / spent.item(), "unit": "solves/s", "h2d_bytes_per_step": H2D_BYTES,
+               "d2h_bytes_per_step": D2H_BYTES, "steps": n_e2e,
+               "api": "MPPI.forward with host tensors in, .cpu() out (sharded solve, NCCL all-gather of partials)"}
+
+    clocks = None
+    if rank == 0:
+        sampler.stop()
+        clocks = sampler.summary(t0, t1)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = time_oracle(n_timed=6, n_warm=1, states=states_h, refs=refs_h, k_samples=K_SAMPLES)
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        info = solver.launch_info()
+        sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12  # TFLOP/s, FMA counted as 2
+        kern_s = kern_ms / 1e3
+        share = world  # each rank runs 1/world of the samples
+        ach = FLOPS_PER_SOLVE / share / kern_s / 1e12 if kern_s > 0 else None
+        hbm_ach = BYTES_PER_SOLVE / kern_s / 1e9 if kern_s > 0 else None
+        line = {
+            "metric": "MPPI solves/sec (control Hz) at K=65536,T=80 racing",
+            "value": 1e3 / ms_per_step, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "racing kinematic-bicycle MPPI solve, K=65536 T=80 ds=4 du=2, SG filter on, "
+                                   "lambda=1.0 (BASELINE.json configs[3])",
+                       "inputs": f"closed loop of {n_rec} recorded (state, reference path) pairs, device resident; "
+                                 "800x800 obstacle + lane occupancy grids, circuit centre line from tests/golden",
+                       "l2": "flushed between timed steps (192 MiB memset outside the per-step CUDA events)",
+                       "ms_per_step_back_to_back_no_flush": b2b_ms,
+                       "parallelism": f"sample-sharded x{world}" if world > 1 else "single GPU, one fused kernel",
+                       "launch": info},
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "roofline": {"bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": (ach / fp32_peak) if ach else None, "traffic": None,
+                         "kernel": "solve_kernel<Racing,false,kFused>", "kernel_ms": kern_ms, "kernel_launches": kern_n,
+                         "algorithmic_flops_per_launch": FLOPS_PER_SOLVE / share,
+                         "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz ({peak_src} MEASURED_PEAKS.json has no "
+                                        "fp32 figure; the path is fp32-issue/latency bound, not HBM or tensor)",
+                         "hbm": {"achieved": hbm_ach, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                                 "frac": (hbm_ach / peaks["hbm_gbs"]) if hbm_ach and peaks.get("hbm_gbs") else None,
+                                 "algorithmic_bytes_per_launch": BYTES_PER_SOLVE, "peak_source": peak_src}},
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def time_oracle(n_timed, n_warm, states, refs, k_samples):
+    """The reference's algorithm on the host cores: oracle/mppi_oracle.py (a torch-CPU
+    restatement pinned bit-exact to the reference) on the same racing workload."""
+    from engine_util import build_oracle
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = dict(CFG, num_samples=k_samples)
+    omodel, oracle = build_oracle(cfg, emulate_dead_work=True)
+    times = []
+    for i in range(n_warm + n_timed):
+        omodel.reference_path = refs[i % len(refs)]
+        c0 = time.perf_counter()
+        oracle.forward(states[i % len(states)])
+        dt = time.perf_counter() - c0
+        if i >= n_warm:
+            times.append(dt)
+    med = statistics.median(times)
+    return {"value": (k_samples / K_SAMPLES) / med, "unit": "solves/s", "cores": torch.get_num_threads(),
+            "kind": "port",
+            "sample": f"{n_timed} solves (median) of {k_samples}/{K_SAMPLES} samples x T={HORIZON}, after {n_warm} "
+                      f"warm-up, torch CPU fp32 with {torch.get_num_threads()} threads; value scaled to the full K",
+            "seconds_per_sample_solve": med}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference is
+    pure Python/torch and does not exist on the GPU box) on the host cores."""
+    if rank != 0:
+        return
+    from oracle import fixtures as fx
+    from oracle import mppi_oracle as mo
+
+    env = fx.load_env_racing()
+    n_rec = 8
+    states, refs = torch.empty(n_rec, 4), torch.empty(n_rec, HORIZON + 1, 4)
+    state, cind = env.start_state.clone(), 0
+    for s in range(n_rec):  # inputs only; advance along the centre line
+        ref, cind = mo.racing_reference_path(state, env.center_path, cind, HORIZON, v_max=env.v_max)
+        states[s], refs[s] = state, ref
+        state = torch.tensor([ref[0, 0], ref[0, 1], ref[0, 2], min(8.0, 1.0 + s)])
+    # Sub-sampling K would flatter the GPU (the CPU path's per-op overhead makes small K slower per
+    # sample), so every timed step is a FULL K=65536 solve and the bound is on how many are run:
+    # as many of the requested steps as fit in ~150 s of CPU time, at least 3.
+    probe = time_oracle(1, 1, states, refs, K_SAMPLES)
+    n_timed = int(max(3, min(args.steps, 150.0 // max(probe["seconds_per_sample_solve"], 1e-3))))
+    n_warm = min(args.warmup, 2)
+    res = time_oracle(n_timed, n_warm, states, refs, K_SAMPLES)
+    res["sample"] += f"; {n_timed} of the requested {args.steps} steps were run to bound the CPU time"
+    value = res["value"]
+    line = {"impl": "reference", "metric": "MPPI solves/sec (control Hz) at K=65536,T=80 racing", "value": value,
+            "unit": "solves/s", "n_gpus": world, "steps": n_timed, "warmup": n_warm,
+            "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "racing kinematic-bicycle MPPI solve, K=65536 T=80 ds=4 du=2, SG filter on, "
+                                   "lambda=1.0 (BASELINE.json configs[3])",
+                       "implementation": "oracle/mppi_oracle.py: op-for-op torch-CPU restatement of "
+                                         "pi_mpc.MPPI.forward, bit-exact to the reference on tests/golden"},
+            "cpu_baseline": {k2: res[k2] for k2 in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank, local_rank, world = dist_env()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch N > 1 with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N "
+                         "--master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
+    run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,208 @@
+/*
+ * mppi_b200.h - C ABI of the B200-native MPPI rollout engine (libmppi_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of kohonda/mppi_playground: a
+ * `pi_mpc.MPPI.forward` solve (reference src/pi_mpc/mppi.py:223-460) plus the
+ * pieces of solver state around it (constructor :24-210, reset :212-221,
+ * get_top_samples :462-487). The reference is pure Python and has no FFI of
+ * its own; these are the entry points a Python shim binds with ctypes (see
+ * INTEGRATION.md and mppi_playground_b200/_capi.py). Plain pointers and
+ * sizes only - no torch types cross this boundary.
+ *
+ * Conventions
+ *   - every function returns MPPI_OK (0) or a negative MppiStatus; the text of
+ *     the last error of the calling thread is mppi_last_error();
+ *   - "d_" pointers are device pointers on the handle's device, "h_" pointers
+ *     are host pointers; all arrays are fp32, row-major, dense;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ *     stream); calls are asynchronous on that stream unless stated;
+ *   - one handle is driven by one host thread at a time (the reference is not
+ *     re-entrant either: global torch RNG, src/pi_mpc/mppi.py:93);
+ *   - there is no CPU fallback: without a usable sm_100 device mppi_create
+ *     fails with MPPI_ERR_CUDA.
+ */
+#ifndef MPPI_B200_H_
+#define MPPI_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPPI_ABI_VERSION 1
+#define MPPI_MAX_DIM_CONTROL 4
+#define MPPI_MAX_DIM_STATE 8
+#define MPPI_MAX_SG_WINDOW 33
+#define MPPI_MAX_MODEL_PARAMS 32
+
+typedef enum MppiStatus {
+  MPPI_OK = 0,
+  MPPI_ERR_INVALID = -1, /* bad argument / config (the reference's AssertionError / ValueError cases) */
+  MPPI_ERR_CUDA = -2,    /* CUDA runtime error, text in mppi_last_error() */
+  MPPI_ERR_STATE = -3,   /* call sequence error (e.g. top samples before any solve) */
+  MPPI_ERR_UNSUPPORTED = -4
+} MppiStatus;
+
+/* Built-in env models compiled as __device__ functions. */
+typedef enum MppiModel {
+  MPPI_MODEL_PENDULUM = 0,     /* example/pendulum.py:17-47 */
+  MPPI_MODEL_CARTPOLE = 1,     /* example/cartpole.py:17-81 */
+  MPPI_MODEL_MOUNTAINCAR = 2,  /* example/mountaincar.py:17-55 */
+  MPPI_MODEL_NAVIGATION2D = 3, /* src/envs/navigation_2d.py:218-279 */
+  MPPI_MODEL_RACING = 4        /* src/envs/racing_env.py:327-372 + example/racing.py:110-159 */
+} MppiModel;
+
+/* lambda_ argument of the constructor (src/pi_mpc/mppi.py:183-210). */
+typedef enum MppiLambdaMode {
+  MPPI_LAMBDA_FIXED = 0,
+  MPPI_LAMBDA_MPO = 1,
+  MPPI_LAMBDA_LBPS = 2,
+  MPPI_LAMBDA_ESSPS = 3
+} MppiLambdaMode;
+
+/* Layout of MppiConfig.model_params (floats), per model.
+ *   PENDULUM / CARTPOLE / MOUNTAINCAR: none (the reference hard-codes them).
+ *   NAVIGATION2D (12): v_min v_max w_min w_max  goal_x goal_y  x_lo x_hi y_lo y_hi  dt  obstacle_weight
+ *   RACING (17):       a_min a_max s_min s_max  wheelbase v_max  x_lo x_hi y_lo y_hi  dt  Qc Ql Qv Qo Qin Qdin
+ */
+#define MPPI_NAV2D_NUM_PARAMS 12
+#define MPPI_RACING_NUM_PARAMS 17
+
+/* Mirrors the keyword arguments of MPPI.__init__ (src/pi_mpc/mppi.py:24-47). */
+typedef struct MppiConfig {
+  int32_t abi_version; /* MPPI_ABI_VERSION */
+  int32_t model;       /* MppiModel */
+  int32_t horizon;     /* T */
+  int32_t num_samples; /* K rolled by THIS handle (the shard size when sharded) */
+  int32_t dim_state;
+  int32_t dim_control;
+  float u_min[MPPI_MAX_DIM_CONTROL];
+  float u_max[MPPI_MAX_DIM_CONTROL];
+  float sigmas[MPPI_MAX_DIM_CONTROL];
+  int32_t lambda_mode; /* MppiLambdaMode */
+  double lambda_;      /* used when lambda_mode == FIXED */
+  double lbps_delta;
+  double essps_target_ess; /* <= 0: default total_samples / 10 (mppi.py:185-187) */
+  double lambda_min;
+  double lambda_max;
+  double exploration; /* fraction of zero-mean samples (mppi.py:266) */
+  int32_t use_sg_filter;
+  int32_t sg_window_size;
+  int32_t sg_poly_order;
+  int32_t sg_coeffs_given; /* 1: use sg_coeffs as given (e.g. torch's fp32 pinv), 0: engine solves them */
+  float sg_coeffs[MPPI_MAX_SG_WINDOW];
+  uint64_t seed;
+  int32_t device; /* CUDA device ordinal */
+  /* sample sharding: this handle owns global sample ids
+   * [sample_offset, sample_offset + num_samples) out of total_samples.
+   * Single GPU: sample_offset = 0, total_samples = num_samples (or 0). */
+  int64_t sample_offset;
+  int64_t total_samples;
+  int32_t num_model_params;
+  float model_params[MPPI_MAX_MODEL_PARAMS];
+  int32_t block_size; /* 0: engine picks */
+  int32_t flags;      /* reserved, 0 */
+} MppiConfig;
+
+typedef struct MppiHandle MppiHandle;
+
+/* ---- lifetime ---------------------------------------------------------------- */
+/* MPPI.__init__ (mppi.py:24-210): validates the config, allocates device state
+ * (warm start [T,du], SG history [T-1,du], costs [K], partial buffers). */
+int mppi_create(const MppiConfig* cfg, MppiHandle** out);
+void mppi_destroy(MppiHandle* h);
+/* MPPI.reset (mppi.py:212-221): zero the warm start and the SG history. */
+int mppi_reset(MppiHandle* h, void* stream);
+const char* mppi_last_error(void);
+int mppi_abi_version(void);
+
+/* ---- model data ---------------------------------------------------------------- */
+/* Replace the model parameter block (cost weights can change between solves:
+ * example/racing.py:41-46 are plain attributes). n must match the model. */
+int mppi_set_model_params(MppiHandle* h, const float* params, int32_t n);
+/* Occupancy grid for slot 0 (obstacle map; NAVIGATION2D and RACING) or slot 1
+ * (lane map; RACING). `grid` is the reference's [W,H] fp32 0/1 map, x on the
+ * slow axis (src/envs/obstacle_map_2d.py:195), on the device if on_device != 0.
+ * It is bit-packed once into the layout the kernels stage into shared memory.
+ * Synchronous. */
+int mppi_set_map(MppiHandle* h, int32_t slot, const float* grid, int32_t on_device, int32_t width, int32_t height,
+                 float cell_size, float origin_x, float origin_y);
+
+/* ---- one solve (MPPI.forward, mppi.py:223-460) ----------------------------------- */
+/* d_state [ds]; d_refpath [T+1,4] (RACING only, else NULL: example/racing.py:73-81);
+ * d_noise NULL for the in-kernel Philox sampler, or [K,T,du] = sigma*eps as
+ * MultivariateNormal.rsample returns it (parity mode, mppi.py:261-263).
+ * Outputs: d_action_seq [T,du], d_state_seq [T+1,ds] (the reference returns
+ * the latter as [1,T+1,ds]). Asynchronous on `stream`. */
+int mppi_solve(MppiHandle* h, const float* d_state, const float* d_refpath, const float* d_noise,
+               float* d_action_seq, float* d_state_seq, void* stream);
+/* Same solve with HOST buffers: pinned staging, H2D of state/refpath, the
+ * solve, D2H of both outputs, and a stream synchronize before returning. */
+int mppi_solve_host(MppiHandle* h, const float* h_state, const float* h_refpath, float* h_action_seq,
+                    float* h_state_seq);
+
+/* ---- sample-sharded solve (one handle per GPU, K split across ranks) ------------- */
+/* Stage 1: roll this shard. Fixed-lambda / MPO modes also reduce the shard to
+ * its partial (see mppi_partial_floats). LBPS / ESSPS stop after the costs. */
+int mppi_shard_rollout(MppiHandle* h, const float* d_state, const float* d_refpath, const float* d_noise,
+                       void* stream);
+/* Stage 2 (LBPS / ESSPS only): d_costs_all [total_samples] = all shards' costs
+ * gathered by the caller; runs the lambda search (identical on every rank)
+ * and reduces this shard to its partial. */
+int mppi_shard_lambda(MppiHandle* h, const float* d_costs_all, void* stream);
+/* Stage 3: d_partials [n_shards, mppi_partial_floats()] gathered by the
+ * caller; combines them and finishes the solve (SG filter, optimal-trajectory
+ * rollout, state carry). Every rank computes identical outputs. */
+int mppi_shard_finish(MppiHandle* h, const float* d_partials, int32_t n_shards, const float* d_state,
+                      float* d_action_seq, float* d_state_seq, void* stream);
+int32_t mppi_partial_floats(const MppiHandle* h);
+/* Device buffers owned by the handle, valid until mppi_destroy. */
+int mppi_costs_ptr(MppiHandle* h, const float** d_costs);     /* [num_samples] of the last solve */
+int mppi_partial_ptr(MppiHandle* h, const float** d_partial); /* [mppi_partial_floats()] */
+
+/* ---- inspection ------------------------------------------------------------------ */
+/* softmax(-costs/lambda) of the last solve (mppi.py:376), d_weights [num_samples]. */
+int mppi_weights(MppiHandle* h, float* d_weights, void* stream);
+/* get_top_samples (mppi.py:462-487): the n highest-weight samples of the last
+ * solve, weight-descending. Trajectories are not stored during the solve;
+ * they are re-rolled from the sampler key (or from d_noise, which must still
+ * be valid, in parity mode). d_traj [n,T+1,ds], d_w [n]. */
+int mppi_top_samples(MppiHandle* h, int32_t n, float* d_traj, float* d_w, void* stream);
+/* _states_prediction (mppi.py:508-524): roll n action sequences d_actions [n,T,du]
+ * from d_state; d_traj [n,T+1,ds]. Used by get_samples_from_posterior (mppi.py:489-506). */
+int mppi_rollout_actions(MppiHandle* h, const float* d_state, const float* d_actions, int32_t n, float* d_traj,
+                         void* stream);
+/* lambda the last solve's weights used, and the one the next solve will use
+ * (they differ in MPO mode, mppi.py:376 vs :398). Synchronises `stream`. */
+int mppi_get_lambda(MppiHandle* h, double* lambda_used, double* lambda_next, void* stream);
+/* Warm start [T,du] and SG history [T-1,du] (the solver's whole carried state
+ * besides MPO's rho/Adam moments; mppi.py:157,163,452-458). */
+int mppi_get_carry(MppiHandle* h, float* d_prev_action_seq, float* d_history, void* stream);
+int mppi_set_carry(MppiHandle* h, const float* d_prev_action_seq, const float* d_history, void* stream);
+/* Device pointer of the live warm start buffer [T,du] (read-only for callers). */
+int mppi_prev_action_ptr(MppiHandle* h, const float** d_prev_action_seq);
+/* Number of kernels the last mppi_solve / mppi_solve_host launched. */
+int32_t mppi_last_launch_count(const MppiHandle* h);
+/* Launch geometry picked for the rollout kernel. */
+int mppi_launch_info(const MppiHandle* h, int32_t* grid, int32_t* block, int32_t* smem_bytes);
+/* Time the dominant (rollout) kernel of subsequent solves with CUDA events on
+ * the launching stream: enable with 1, read back the mean/launch count with
+ * mppi_kernel_time_ms (which synchronises the events). */
+int mppi_kernel_timing(MppiHandle* h, int32_t enable);
+int mppi_kernel_time_ms(MppiHandle* h, double* mean_ms, int32_t* launches);
+
+/* Philox4x32-10 known-answer hook for tests: out[4] = block(counter, key). Host code. */
+void mppi_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);
+/* Index the NEXT solve will key its sampler with (== number of solves so far). */
+uint64_t mppi_solve_index(const MppiHandle* h);
+/* sigma*eps the in-kernel sampler draws for solve `solve_index`, in the
+ * reference's [K,T,du] layout (what MultivariateNormal.rsample returns,
+ * mppi.py:261-263). Lets a test feed the engine's own noise to the oracle. */
+int mppi_sample_noise(MppiHandle* h, uint64_t solve_index, float* d_noise_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPPI_B200_H_ */

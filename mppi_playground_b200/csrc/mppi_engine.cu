@@ -1,0 +1,816 @@
+// mppi_engine.cu - host side of libmppi_b200.so: handle management, launch
+// geometry, and the C ABI declared in include/mppi_b200.h.
+//
+// Built for sm_100a only:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false ...
+// (-fmad=false: see mppi_models.cuh - the reference never contracts a*b+c).
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cub/device/device_radix_sort.cuh>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/mppi_b200.h"
+#include "mppi_kernels.cuh"
+
+using namespace mppi;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) return fail(MPPI_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e));    \
+  } while (0)
+
+constexpr int kNumSMs = 148;
+constexpr unsigned kMaxSmem = 227 * 1024;
+
+struct ModelInfo {
+  int ds, du, maps, n_params;
+  bool refpath;
+};
+ModelInfo model_info(int model) {
+  switch (model) {
+    case MPPI_MODEL_PENDULUM: return {Pendulum::DS, Pendulum::DU, 0, 0, false};
+    case MPPI_MODEL_CARTPOLE: return {Cartpole::DS, Cartpole::DU, 0, 0, false};
+    case MPPI_MODEL_MOUNTAINCAR: return {MountainCar::DS, MountainCar::DU, 0, 0, false};
+    case MPPI_MODEL_NAVIGATION2D: return {Navigation2D::DS, Navigation2D::DU, 1, MPPI_NAV2D_NUM_PARAMS, false};
+    case MPPI_MODEL_RACING: return {Racing::DS, Racing::DU, 2, MPPI_RACING_NUM_PARAMS, true};
+    default: return {0, 0, 0, 0, false};
+  }
+}
+
+// Savitzky-Golay coefficients = first row of pinv(vander(-h..h, order+1))
+// (mppi.py:568-596) via the normal equations in fp64, rounded to fp32.
+bool savgol_coeffs(int window, int order, float* out) {
+  const int h = (window - 1) / 2, n = order + 1;
+  std::vector<double> G(n * n, 0.0), inv(n * n, 0.0);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      double s = 0;
+      for (int x = -h; x <= h; ++x) s += pow((double)x, i) * pow((double)x, j);
+      G[i * n + j] = s;
+    }
+  // invert G by Gauss-Jordan with partial pivoting
+  for (int i = 0; i < n; ++i) inv[i * n + i] = 1.0;
+  for (int c = 0; c < n; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < n; ++r)
+      if (fabs(G[r * n + c]) > fabs(G[piv * n + c])) piv = r;
+    if (fabs(G[piv * n + c]) < 1e-300) return false;
+    for (int j = 0; j < n; ++j) {
+      std::swap(G[c * n + j], G[piv * n + j]);
+      std::swap(inv[c * n + j], inv[piv * n + j]);
+    }
+    double d = G[c * n + c];
+    for (int j = 0; j < n; ++j) {
+      G[c * n + j] /= d;
+      inv[c * n + j] /= d;
+    }
+    for (int r = 0; r < n; ++r)
+      if (r != c) {
+        double f = G[r * n + c];
+        for (int j = 0; j < n; ++j) {
+          G[r * n + j] -= f * G[c * n + j];
+          inv[r * n + j] -= f * inv[c * n + j];
+        }
+      }
+  }
+  // pinv(A)[0, m] = sum_j inv[0][j] * x_m^j
+  for (int m = 0; m < window; ++m) {
+    double s = 0;
+    for (int j = 0; j < n; ++j) s += inv[j] * pow((double)(m - h), j);
+    out[m] = (float)s;
+  }
+  return true;
+}
+
+}  // namespace
+
+struct MppiHandle {
+  MppiConfig cfg{};
+  ModelInfo mi{};
+  int device = 0;
+  int E = 0, E_pad = 0, P = 0;
+  int block = 0, grid = 0;
+  unsigned smem = 0;
+  SolveParams base{};  // everything that does not change between solves
+  // device buffers
+  float* d_prev_action = nullptr;
+  float* d_history = nullptr;
+  float* d_nominal_snapshot = nullptr;
+  float* d_state_snapshot = nullptr;
+  DeviceScalars* d_sc = nullptr;
+  float* d_costs = nullptr;
+  float* d_block_partials = nullptr;
+  float* d_rank_partial = nullptr;
+  unsigned int* d_counter = nullptr;
+  uint32_t* d_map[2] = {nullptr, nullptr};
+  bool map_set[2] = {false, false};
+  // host-call staging (mppi_solve_host)
+  float* h_pinned = nullptr;  // state | refpath | action_seq | state_seq
+  float* d_stage = nullptr;
+  cudaStream_t own_stream = nullptr;
+  // top samples
+  int* d_idx_in = nullptr;
+  int* d_idx_out = nullptr;
+  float* d_keys_out = nullptr;
+  void* d_sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
+  // bookkeeping
+  uint64_t solve_count = 0;  // index of the NEXT solve
+  bool solved = false;
+  const float* last_noise = nullptr;
+  int last_launches = 0;
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+};
+
+namespace {
+
+size_t pad16(size_t bytes) { return (bytes + 15) / 16 * 16; }
+
+// Launch geometry for the rollout kernel. The path is latency bound at the
+// sizes MPPI runs (K/32 warps spread over 592 schedulers), so the model is:
+// time ~ waves * w / ipc(w) with w = max warps on one scheduler.
+int pick_block(const MppiHandle* h, int n_maps, const unsigned* map_bytes, unsigned pa_bytes) {
+  const int K = h->cfg.num_samples;
+  int best = 0;
+  double best_t = 1e300;
+  const int cands[] = {512, 256, 128, 64};
+  for (int bs : cands) {
+    SmemLayout L = make_layout(n_maps, map_bytes, h->cfg.horizon, h->E_pad, pa_bytes, h->mi.refpath, bs / 32);
+    if (L.total > kMaxSmem) continue;
+    long long blocks = ((long long)K + bs - 1) / bs;
+    int per_sm = std::min<long long>({2048 / bs, (long long)(kMaxSmem / L.total), 65536 / (128LL * bs)});
+    if (per_sm < 1) per_sm = 1;
+    long long conc = (long long)kNumSMs * per_sm;
+    long long waves = (blocks + conc - 1) / conc;
+    long long res_blocks = std::min<long long>(per_sm, (blocks + kNumSMs - 1) / kNumSMs);
+    double w = std::max(1.0, ceil(res_blocks * (bs / 32) / 4.0));
+    double ipc = std::min(0.9, 0.28 * pow(w, 0.7));
+    double t = waves * w / ipc;
+    if (t < best_t * 0.999 || best == 0) {
+      best_t = t;
+      best = bs;
+    }
+  }
+  return best;
+}
+
+template <class M>
+int launch_solve(MppiHandle* h, const SolveParams& p, int mode, bool inject, cudaStream_t st) {
+  void (*k)(SolveParams) = nullptr;
+#define PICK(MODE)                                                     \
+  k = inject ? (void (*)(SolveParams))solve_kernel<M, true, MODE>      \
+             : (void (*)(SolveParams))solve_kernel<M, false, MODE>
+  if (mode == kFused)
+    PICK(kFused);
+  else if (mode == kCosts)
+    PICK(kCosts);
+  else
+    PICK(kReduce);
+#undef PICK
+  CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->timing && mode != kReduce) {
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaEventRecord(e0, st));
+  }
+  k<<<h->grid, h->block, h->smem, st>>>(p);
+  if (e0) {
+    CUDA_TRY(cudaEventRecord(e1, st));
+    h->events.emplace_back(e0, e1);
+  }
+  CUDA_TRY(cudaGetLastError());
+  h->last_launches++;
+  return MPPI_OK;
+}
+
+int dispatch_solve(MppiHandle* h, const SolveParams& p, int mode, bool inject, cudaStream_t st) {
+  switch (h->cfg.model) {
+    case MPPI_MODEL_PENDULUM: return launch_solve<Pendulum>(h, p, mode, inject, st);
+    case MPPI_MODEL_CARTPOLE: return launch_solve<Cartpole>(h, p, mode, inject, st);
+    case MPPI_MODEL_MOUNTAINCAR: return launch_solve<MountainCar>(h, p, mode, inject, st);
+    case MPPI_MODEL_NAVIGATION2D: return launch_solve<Navigation2D>(h, p, mode, inject, st);
+    case MPPI_MODEL_RACING: return launch_solve<Racing>(h, p, mode, inject, st);
+  }
+  return fail(MPPI_ERR_INVALID, "unknown model %d", h->cfg.model);
+}
+
+template <class M>
+int launch_finish(MppiHandle* h, const SolveParams& p, const float* parts, int n, cudaStream_t st) {
+  unsigned sm = finish_scratch_bytes(h->E_pad);
+  finish_kernel<M><<<1, 256, sm, st>>>(p, parts, n);
+  CUDA_TRY(cudaGetLastError());
+  h->last_launches++;
+  return MPPI_OK;
+}
+
+int dispatch_finish(MppiHandle* h, const SolveParams& p, const float* parts, int n, cudaStream_t st) {
+  switch (h->cfg.model) {
+    case MPPI_MODEL_PENDULUM: return launch_finish<Pendulum>(h, p, parts, n, st);
+    case MPPI_MODEL_CARTPOLE: return launch_finish<Cartpole>(h, p, parts, n, st);
+    case MPPI_MODEL_MOUNTAINCAR: return launch_finish<MountainCar>(h, p, parts, n, st);
+    case MPPI_MODEL_NAVIGATION2D: return launch_finish<Navigation2D>(h, p, parts, n, st);
+    case MPPI_MODEL_RACING: return launch_finish<Racing>(h, p, parts, n, st);
+  }
+  return fail(MPPI_ERR_INVALID, "unknown model %d", h->cfg.model);
+}
+
+int launch_search(MppiHandle* h, const float* costs, long long n, cudaStream_t st) {
+  SearchParams q{};
+  q.costs = costs;
+  q.n = n;
+  q.mode = h->cfg.lambda_mode;
+  q.lambda_min = h->cfg.lambda_min;
+  q.lambda_max = h->cfg.lambda_max;
+  q.lbps_delta = h->cfg.lbps_delta;
+  q.essps_target = h->cfg.essps_target_ess;
+  q.sc = h->d_sc;
+  lambda_search_kernel<<<1, 1024, 0, st>>>(q);
+  CUDA_TRY(cudaGetLastError());
+  h->last_launches++;
+  return MPPI_OK;
+}
+
+int check_ready(MppiHandle* h) {
+  if (!h) return fail(MPPI_ERR_INVALID, "null handle");
+  for (int i = 0; i < h->mi.maps; ++i)
+    if (!h->map_set[i]) return fail(MPPI_ERR_STATE, "occupancy map slot %d has not been set (mppi_set_map)", i);
+  return MPPI_OK;
+}
+
+// Per-solve parameter block: base + this call's pointers + sampler counter.
+int make_params(MppiHandle* h, const float* d_state, const float* d_refpath, const float* d_noise, float* d_action,
+                float* d_state_seq, int n_shards, SolveParams* out) {
+  if (!d_state) return fail(MPPI_ERR_INVALID, "state is null");
+  if (h->mi.refpath && !d_refpath) return fail(MPPI_ERR_INVALID, "this model needs a reference path [T+1,4]");
+  SolveParams p = h->base;
+  p.state = d_state;
+  p.refpath = d_refpath;
+  p.ref_bulk_ok = d_refpath && (((uintptr_t)d_refpath & 15) == 0);
+  p.noise = d_noise;
+  p.action_out = d_action;
+  p.state_seq_out = d_state_seq;
+  p.key.solve_lo = (uint32_t)h->solve_count;
+  p.key.solve_hi = (uint32_t)(h->solve_count >> 32);
+  p.n_shards = n_shards;
+  *out = p;
+  return MPPI_OK;
+}
+
+template <class M>
+int launch_reroll(MppiHandle* h, const SolveParams& p, int n, float* traj, float* w, cudaStream_t st) {
+  if (p.noise)
+    reroll_kernel<M, true><<<(n + 127) / 128, 128, 0, st>>>(p, h->d_idx_out, n, traj, w);
+  else
+    reroll_kernel<M, false><<<(n + 127) / 128, 128, 0, st>>>(p, h->d_idx_out, n, traj, w);
+  CUDA_TRY(cudaGetLastError());
+  return MPPI_OK;
+}
+
+template <class M>
+int launch_rollout_actions(MppiHandle* h, const SolveParams& p, const float* actions, int n, float* traj,
+                           cudaStream_t st) {
+  rollout_actions_kernel<M><<<(n + 127) / 128, 128, 0, st>>>(p, actions, n, traj);
+  CUDA_TRY(cudaGetLastError());
+  return MPPI_OK;
+}
+
+void refresh_launch_geometry(MppiHandle* h) {
+  unsigned mb[2] = {h->base.map_bytes[0], h->base.map_bytes[1]};
+  int bs = h->cfg.block_size > 0 ? h->cfg.block_size : pick_block(h, h->mi.maps, mb, h->base.prev_action_bytes);
+  h->block = bs;
+  h->grid = (h->cfg.num_samples + bs - 1) / bs;
+  h->smem = make_layout(h->mi.maps, mb, h->cfg.horizon, h->E_pad, h->base.prev_action_bytes, h->mi.refpath, bs / 32)
+                .total;
+}
+
+}  // namespace
+
+// ================================ C ABI ========================================
+extern "C" {
+
+const char* mppi_last_error(void) { return g_last_error.c_str(); }
+int mppi_abi_version(void) { return MPPI_ABI_VERSION; }
+
+void mppi_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]) {
+  Philox::block(counter[0], counter[1], counter[2], counter[3], key[0], key[1], out);
+}
+
+int mppi_create(const MppiConfig* cfg, MppiHandle** out) {
+  if (!cfg || !out) return fail(MPPI_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != MPPI_ABI_VERSION)
+    return fail(MPPI_ERR_INVALID, "abi_version %d != %d", cfg->abi_version, MPPI_ABI_VERSION);
+  ModelInfo mi = model_info(cfg->model);
+  if (mi.ds == 0) return fail(MPPI_ERR_INVALID, "unknown model %d", cfg->model);
+  if (cfg->dim_state != mi.ds || cfg->dim_control != mi.du)
+    return fail(MPPI_ERR_INVALID, "model %d has dim_state=%d dim_control=%d, got %d/%d", cfg->model, mi.ds, mi.du,
+                cfg->dim_state, cfg->dim_control);
+  if (cfg->horizon < 1 || cfg->num_samples < 1) return fail(MPPI_ERR_INVALID, "horizon and num_samples must be >= 1");
+  if ((long long)cfg->horizon * mi.du > 4096) return fail(MPPI_ERR_UNSUPPORTED, "horizon * dim_control > 4096");
+  if (cfg->lambda_mode < MPPI_LAMBDA_FIXED || cfg->lambda_mode > MPPI_LAMBDA_ESSPS)
+    return fail(MPPI_ERR_INVALID, "lambda_ must be 'MPO', 'LBPS', 'ESSPS', or a float value.");
+  if (cfg->lambda_mode == MPPI_LAMBDA_FIXED && !(cfg->lambda_ > 0.0))
+    return fail(MPPI_ERR_INVALID, "lambda_ must be positive");
+  if (cfg->num_model_params != mi.n_params)
+    return fail(MPPI_ERR_INVALID, "model %d takes %d parameters, got %d", cfg->model, mi.n_params,
+                cfg->num_model_params);
+  if (cfg->use_sg_filter) {
+    if (cfg->sg_window_size % 2 == 0 || cfg->sg_window_size <= cfg->sg_poly_order)
+      return fail(MPPI_ERR_INVALID, "window_size must be odd and greater than poly_order.");  // mppi.py:580-581
+    if (cfg->sg_window_size > MPPI_MAX_SG_WINDOW) return fail(MPPI_ERR_UNSUPPORTED, "sg_window_size > %d", MPPI_MAX_SG_WINDOW);
+    if (2 * cfg->horizon - 1 < cfg->sg_window_size / 2)
+      return fail(MPPI_ERR_INVALID, "horizon too short for the Savitzky-Golay window");
+  }
+  if (cfg->block_size != 0 && (cfg->block_size < 64 || cfg->block_size > 512 || cfg->block_size % 32))
+    return fail(MPPI_ERR_INVALID, "block_size must be 0 or a multiple of 32 in [64, 512]");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(MPPI_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(MPPI_ERR_INVALID, "device %d out of range", cfg->device);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10)
+    return fail(MPPI_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device,
+                prop.major, prop.minor);
+  CUDA_TRY(cudaSetDevice(cfg->device));
+
+  MppiHandle* h = new (std::nothrow) MppiHandle();
+  if (!h) return fail(MPPI_ERR_INVALID, "out of host memory");
+  h->cfg = *cfg;
+  h->mi = mi;
+  h->device = cfg->device;
+  if (h->cfg.total_samples <= 0) {
+    h->cfg.total_samples = cfg->num_samples;
+    h->cfg.sample_offset = 0;
+  }
+  if (h->cfg.essps_target_ess <= 0.0) h->cfg.essps_target_ess = (double)h->cfg.total_samples / 10.0;  // mppi.py:185-187
+  const int T = cfg->horizon, DU = mi.du, DS = mi.ds, K = cfg->num_samples;
+  h->E = T * DU;
+  h->E_pad = (h->E + 31) / 32 * 32;
+  h->P = kPartialHeader + h->E_pad;
+
+  auto cleanup = [&](int rc) {
+    mppi_destroy(h);
+    return rc;
+  };
+#define ALLOC(ptr, bytes)                                                                                   \
+  do {                                                                                                      \
+    cudaError_t _e = cudaMalloc((void**)&(ptr), pad16(bytes) ? pad16(bytes) : 16);                         \
+    if (_e != cudaSuccess) return cleanup(fail(MPPI_ERR_CUDA, "cudaMalloc(%zu): %s", (size_t)(bytes),      \
+                                               cudaGetErrorString(_e)));                                    \
+    cudaMemset((ptr), 0, pad16(bytes) ? pad16(bytes) : 16);                                                 \
+  } while (0)
+  ALLOC(h->d_prev_action, (size_t)h->E_pad * 4);
+  ALLOC(h->d_history, (size_t)std::max(1, (T - 1) * DU) * 4);
+  ALLOC(h->d_nominal_snapshot, (size_t)h->E_pad * 4);
+  ALLOC(h->d_state_snapshot, 64);
+  ALLOC(h->d_sc, sizeof(DeviceScalars));
+  ALLOC(h->d_costs, (size_t)K * 4);
+  ALLOC(h->d_rank_partial, (size_t)h->P * 4);
+  ALLOC(h->d_counter, 16);
+  // staging for mppi_solve_host: state | refpath | action | state_seq
+  size_t stage_floats = 8 + (size_t)(T + 1) * 4 + (size_t)h->E_pad + (size_t)(T + 1) * DS + 8;
+  ALLOC(h->d_stage, stage_floats * 4);
+  if (cudaMallocHost((void**)&h->h_pinned, stage_floats * 4) != cudaSuccess)
+    return cleanup(fail(MPPI_ERR_CUDA, "cudaMallocHost failed"));
+  if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+    return cleanup(fail(MPPI_ERR_CUDA, "cudaStreamCreate failed"));
+
+  DeviceScalars sc{};
+  sc.lambda = (cfg->lambda_mode == MPPI_LAMBDA_FIXED) ? cfg->lambda_ : 1.0;  // MPO starts at 1.0 (mppi.py:193)
+  sc.lambda_used = sc.lambda;
+  sc.rho = 0.0f;  // log(1.0)
+  if (cudaMemcpy(h->d_sc, &sc, sizeof sc, cudaMemcpyHostToDevice) != cudaSuccess)
+    return cleanup(fail(MPPI_ERR_CUDA, "cudaMemcpy(scalars) failed"));
+
+  SolveParams& b = h->base;
+  b.K = K;
+  b.T = T;
+  b.k_offset = h->cfg.sample_offset;
+  // threshold = int(num_samples * (1 - exploration)) on the GLOBAL sample count (mppi.py:266)
+  b.explore_threshold = (long long)((double)h->cfg.total_samples * (1.0 - cfg->exploration));
+  for (int d = 0; d < DU; ++d) {
+    b.u_min[d] = cfg->u_min[d];
+    b.u_max[d] = cfg->u_max[d];
+    b.sigma[d] = cfg->sigmas[d];
+  }
+  for (int i = 0; i < mi.n_params; ++i) b.mp.v[i] = cfg->model_params[i];
+  b.prev_action = h->d_prev_action;
+  b.prev_action_bytes = (unsigned)pad16((size_t)h->E_pad * 4);
+  b.history = h->d_history;
+  b.nominal_snapshot = h->d_nominal_snapshot;
+  b.state_snapshot = h->d_state_snapshot;
+  b.sc = h->d_sc;
+  b.costs = h->d_costs;
+  b.rank_partial = h->d_rank_partial;
+  b.counter = h->d_counter;
+  b.key.seed_lo = (uint32_t)cfg->seed;
+  b.key.seed_hi = (uint32_t)(cfg->seed >> 32);
+  b.lambda_mode = cfg->lambda_mode;
+  b.mpo_epsilon = 0.1f;  // mppi.py:194
+  b.use_sg = cfg->use_sg_filter ? 1 : 0;
+  b.sg_window = cfg->sg_window_size;
+  if (cfg->use_sg_filter) {
+    if (cfg->sg_coeffs_given) {
+      for (int i = 0; i < cfg->sg_window_size; ++i) b.sg_coeffs[i] = cfg->sg_coeffs[i];
+    } else if (!savgol_coeffs(cfg->sg_window_size, cfg->sg_poly_order, b.sg_coeffs)) {
+      return cleanup(fail(MPPI_ERR_INVALID, "singular Savitzky-Golay system"));
+    }
+  }
+  b.E = h->E;
+  b.E_pad = h->E_pad;
+  b.P = h->P;
+  refresh_launch_geometry(h);
+  if (h->smem > kMaxSmem) return cleanup(fail(MPPI_ERR_UNSUPPORTED, "shared memory budget exceeded (%u B)", h->smem));
+  // block partials: sized for the smallest block the engine may pick later (maps change smem)
+  ALLOC(h->d_block_partials, (size_t)((K + 63) / 64) * h->P * 4);
+  b.block_partials = h->d_block_partials;
+#undef ALLOC
+  *out = h;
+  return MPPI_OK;
+}
+
+void mppi_destroy(MppiHandle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (auto& ev : h->events) {
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  cudaFree(h->d_prev_action);
+  cudaFree(h->d_history);
+  cudaFree(h->d_nominal_snapshot);
+  cudaFree(h->d_state_snapshot);
+  cudaFree(h->d_sc);
+  cudaFree(h->d_costs);
+  cudaFree(h->d_block_partials);
+  cudaFree(h->d_rank_partial);
+  cudaFree(h->d_counter);
+  cudaFree(h->d_map[0]);
+  cudaFree(h->d_map[1]);
+  cudaFree(h->d_stage);
+  cudaFree(h->d_idx_in);
+  cudaFree(h->d_idx_out);
+  cudaFree(h->d_keys_out);
+  cudaFree(h->d_sort_tmp);
+  if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+int mppi_reset(MppiHandle* h, void* stream) {
+  if (!h) return fail(MPPI_ERR_INVALID, "null handle");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemsetAsync(h->d_prev_action, 0, (size_t)h->E_pad * 4, st));
+  CUDA_TRY(cudaMemsetAsync(h->d_history, 0, (size_t)std::max(1, (h->cfg.horizon - 1) * h->mi.du) * 4, st));
+  return MPPI_OK;
+}
+
+int mppi_set_model_params(MppiHandle* h, const float* params, int32_t n) {
+  if (!h || (!params && n > 0)) return fail(MPPI_ERR_INVALID, "null argument");
+  if (n != h->mi.n_params) return fail(MPPI_ERR_INVALID, "model takes %d parameters, got %d", h->mi.n_params, n);
+  for (int i = 0; i < n; ++i) h->base.mp.v[i] = params[i];
+  return MPPI_OK;
+}
+
+int mppi_set_map(MppiHandle* h, int32_t slot, const float* grid, int32_t on_device, int32_t W, int32_t H,
+                 float cell, float ox, float oy) {
+  if (!h || !grid) return fail(MPPI_ERR_INVALID, "null argument");
+  if (slot < 0 || slot >= h->mi.maps) return fail(MPPI_ERR_INVALID, "model has %d map slots, got slot %d", h->mi.maps, slot);
+  if (W < 1 || H < 1 || !(cell > 0.0f)) return fail(MPPI_ERR_INVALID, "bad map geometry");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int words = (H + 31) / 32;
+  const size_t bytes = pad16((size_t)W * words * 4);
+  const float* d_grid = grid;
+  float* tmp = nullptr;
+  if (!on_device) {
+    CUDA_TRY(cudaMalloc((void**)&tmp, (size_t)W * H * 4));
+    cudaError_t e = cudaMemcpy(tmp, grid, (size_t)W * H * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      cudaFree(tmp);
+      return fail(MPPI_ERR_CUDA, "map upload: %s", cudaGetErrorString(e));
+    }
+    d_grid = tmp;
+  }
+  cudaFree(h->d_map[slot]);
+  h->d_map[slot] = nullptr;
+  cudaError_t e = cudaMalloc((void**)&h->d_map[slot], bytes);
+  if (e == cudaSuccess) e = cudaMemset(h->d_map[slot], 0, bytes);
+  if (e == cudaSuccess) {
+    int n = W * words;
+    pack_map_kernel<<<(n + 255) / 256, 256>>>(d_grid, W, H, words, h->d_map[slot]);
+    e = cudaDeviceSynchronize();
+  }
+  cudaFree(tmp);
+  if (e != cudaSuccess) return fail(MPPI_ERR_CUDA, "map pack: %s", cudaGetErrorString(e));
+  SolveParams& b = h->base;
+  b.map_bits[slot] = h->d_map[slot];
+  b.map_W[slot] = W;
+  b.map_H[slot] = H;
+  b.map_words[slot] = words;
+  b.map_bytes[slot] = (unsigned)bytes;
+  b.map_cell[slot] = cell;
+  b.map_ox[slot] = ox;
+  b.map_oy[slot] = oy;
+  h->map_set[slot] = true;
+  refresh_launch_geometry(h);
+  if (h->smem > kMaxSmem)
+    return fail(MPPI_ERR_UNSUPPORTED, "occupancy maps need %u B of shared memory (> %u)", h->smem, kMaxSmem);
+  return MPPI_OK;
+}
+
+static int solve_impl(MppiHandle* h, const float* d_state, const float* d_refpath, const float* d_noise,
+                      float* d_action, float* d_state_seq, cudaStream_t st) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!d_action || !d_state_seq) return fail(MPPI_ERR_INVALID, "output pointer is null");
+  CUDA_TRY(cudaSetDevice(h->device));
+  SolveParams p;
+  rc = make_params(h, d_state, d_refpath, d_noise, d_action, d_state_seq, 1, &p);
+  if (rc) return rc;
+  h->last_launches = 0;
+  const bool inject = d_noise != nullptr;
+  if (h->cfg.lambda_mode == MPPI_LAMBDA_LBPS || h->cfg.lambda_mode == MPPI_LAMBDA_ESSPS) {
+    if ((rc = dispatch_solve(h, p, kCosts, inject, st))) return rc;
+    if ((rc = launch_search(h, h->d_costs, h->cfg.num_samples, st))) return rc;
+    if ((rc = dispatch_solve(h, p, kReduce, inject, st))) return rc;
+  } else {
+    if ((rc = dispatch_solve(h, p, kFused, inject, st))) return rc;
+  }
+  h->last_noise = d_noise;
+  h->solve_count++;
+  h->solved = true;
+  return MPPI_OK;
+}
+
+int mppi_solve(MppiHandle* h, const float* d_state, const float* d_refpath, const float* d_noise,
+               float* d_action_seq, float* d_state_seq, void* stream) {
+  if (!h) return fail(MPPI_ERR_INVALID, "null handle");
+  return solve_impl(h, d_state, d_refpath, d_noise, d_action_seq, d_state_seq, (cudaStream_t)stream);
+}
+
+int mppi_solve_host(MppiHandle* h, const float* h_state, const float* h_refpath, float* h_action_seq,
+                    float* h_state_seq) {
+  if (!h || !h_state || !h_action_seq || !h_state_seq) return fail(MPPI_ERR_INVALID, "null argument");
+  if (h->mi.refpath && !h_refpath) return fail(MPPI_ERR_INVALID, "this model needs a reference path [T+1,4]");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int T = h->cfg.horizon, DS = h->mi.ds;
+  const size_t n_state = 8, n_ref = (size_t)(T + 1) * 4, n_act = (size_t)h->E_pad, n_seq = (size_t)(T + 1) * DS;
+  float* hp = h->h_pinned;
+  memcpy(hp, h_state, DS * 4);
+  size_t in_floats = n_state;
+  if (h->mi.refpath) {
+    memcpy(hp + n_state, h_refpath, n_ref * 4);
+    in_floats += n_ref;
+  }
+  cudaStream_t st = h->own_stream;
+  CUDA_TRY(cudaMemcpyAsync(h->d_stage, hp, in_floats * 4, cudaMemcpyHostToDevice, st));
+  float* d_act = h->d_stage + n_state + n_ref;
+  float* d_seq = d_act + n_act;
+  int rc = solve_impl(h, h->d_stage, h->mi.refpath ? h->d_stage + n_state : nullptr, nullptr, d_act, d_seq, st);
+  if (rc) return rc;
+  float* hout = hp + n_state + n_ref;
+  CUDA_TRY(cudaMemcpyAsync(hout, d_act, (n_act + n_seq) * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  memcpy(h_action_seq, hout, (size_t)h->E * 4);
+  memcpy(h_state_seq, hout + n_act, n_seq * 4);
+  return MPPI_OK;
+}
+
+// ---- sharded solve ---------------------------------------------------------------------------
+int mppi_shard_rollout(MppiHandle* h, const float* d_state, const float* d_refpath, const float* d_noise,
+                       void* stream) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  SolveParams p;
+  // outputs are written by mppi_shard_finish; n_shards = 2 only means "stop at the shard partial"
+  rc = make_params(h, d_state, d_refpath, d_noise, nullptr, nullptr, 2, &p);
+  if (rc) return rc;
+  h->last_launches = 0;
+  const bool lam_search = h->cfg.lambda_mode == MPPI_LAMBDA_LBPS || h->cfg.lambda_mode == MPPI_LAMBDA_ESSPS;
+  rc = dispatch_solve(h, p, lam_search ? kCosts : kFused, d_noise != nullptr, (cudaStream_t)stream);
+  if (rc) return rc;
+  h->last_noise = d_noise;
+  return MPPI_OK;
+}
+
+int mppi_shard_lambda(MppiHandle* h, const float* d_costs_all, void* stream) {
+  if (!h || !d_costs_all) return fail(MPPI_ERR_INVALID, "null argument");
+  if (!(h->cfg.lambda_mode == MPPI_LAMBDA_LBPS || h->cfg.lambda_mode == MPPI_LAMBDA_ESSPS))
+    return fail(MPPI_ERR_STATE, "mppi_shard_lambda is for LBPS / ESSPS handles");
+  CUDA_TRY(cudaSetDevice(h->device));
+  int rc = launch_search(h, d_costs_all, h->cfg.total_samples, (cudaStream_t)stream);
+  if (rc) return rc;
+  SolveParams p;
+  // the reduce pass only touches costs, the warm start and the sampler; state is not read
+  rc = make_params(h, h->d_state_snapshot, h->mi.refpath ? (const float*)h->d_state_snapshot : nullptr, h->last_noise,
+                   nullptr, nullptr, 2, &p);
+  if (rc) return rc;
+  return dispatch_solve(h, p, kReduce, h->last_noise != nullptr, (cudaStream_t)stream);
+}
+
+int mppi_shard_finish(MppiHandle* h, const float* d_partials, int32_t n_shards, const float* d_state,
+                      float* d_action_seq, float* d_state_seq, void* stream) {
+  if (!h || !d_partials || !d_state || !d_action_seq || !d_state_seq || n_shards < 1)
+    return fail(MPPI_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  SolveParams p;
+  int rc = make_params(h, d_state, h->mi.refpath ? d_state : nullptr, nullptr, d_action_seq, d_state_seq, n_shards, &p);
+  if (rc) return rc;
+  rc = dispatch_finish(h, p, d_partials, n_shards, (cudaStream_t)stream);
+  if (rc) return rc;
+  h->solve_count++;
+  h->solved = true;
+  return MPPI_OK;
+}
+
+int32_t mppi_partial_floats(const MppiHandle* h) { return h ? h->P : 0; }
+
+int mppi_costs_ptr(MppiHandle* h, const float** d_costs) {
+  if (!h || !d_costs) return fail(MPPI_ERR_INVALID, "null argument");
+  *d_costs = h->d_costs;
+  return MPPI_OK;
+}
+int mppi_partial_ptr(MppiHandle* h, const float** d_partial) {
+  if (!h || !d_partial) return fail(MPPI_ERR_INVALID, "null argument");
+  *d_partial = h->d_rank_partial;
+  return MPPI_OK;
+}
+int mppi_prev_action_ptr(MppiHandle* h, const float** p) {
+  if (!h || !p) return fail(MPPI_ERR_INVALID, "null argument");
+  *p = h->d_prev_action;
+  return MPPI_OK;
+}
+
+// ---- inspection ----------------------------------------------------------------------------------
+int mppi_weights(MppiHandle* h, float* d_weights, void* stream) {
+  if (!h || !d_weights) return fail(MPPI_ERR_INVALID, "null argument");
+  if (!h->solved) return fail(MPPI_ERR_STATE, "no solve has run yet");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int K = h->cfg.num_samples;
+  weights_kernel<<<(K + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->d_costs, K, h->d_sc, d_weights);
+  CUDA_TRY(cudaGetLastError());
+  return MPPI_OK;
+}
+
+int mppi_top_samples(MppiHandle* h, int32_t n, float* d_traj, float* d_w, void* stream) {
+  if (!h || !d_traj || !d_w) return fail(MPPI_ERR_INVALID, "null argument");
+  const int K = h->cfg.num_samples;
+  if (n < 1 || n > K) return fail(MPPI_ERR_INVALID, "num_samples must be in [1, %d]", K);  // mppi.py:476
+  if (!h->solved) return fail(MPPI_ERR_STATE, "no solve has run yet");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!h->d_idx_in) {
+    CUDA_TRY(cudaMalloc((void**)&h->d_idx_in, (size_t)K * 4));
+    CUDA_TRY(cudaMalloc((void**)&h->d_idx_out, (size_t)K * 4));
+    CUDA_TRY(cudaMalloc((void**)&h->d_keys_out, (size_t)K * 4));
+    iota_kernel<<<(K + 255) / 256, 256, 0, st>>>(h->d_idx_in, K);
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, h->sort_tmp_bytes, h->d_costs, h->d_keys_out, h->d_idx_in,
+                                             h->d_idx_out, K, 0, 32, st));
+    CUDA_TRY(cudaMalloc(&h->d_sort_tmp, h->sort_tmp_bytes));
+  }
+  // highest weight == lowest cost (mppi.py:479-485); ascending radix sort on the fp32 costs
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp, h->sort_tmp_bytes, h->d_costs, h->d_keys_out, h->d_idx_in,
+                                           h->d_idx_out, K, 0, 32, st));
+  SolveParams p = h->base;
+  p.state = h->d_state_snapshot;
+  p.prev_action = h->d_nominal_snapshot;
+  p.noise = h->last_noise;
+  const uint64_t idx = h->solve_count - 1;
+  p.key.solve_lo = (uint32_t)idx;
+  p.key.solve_hi = (uint32_t)(idx >> 32);
+  switch (h->cfg.model) {
+    case MPPI_MODEL_PENDULUM: return launch_reroll<Pendulum>(h, p, n, d_traj, d_w, st);
+    case MPPI_MODEL_CARTPOLE: return launch_reroll<Cartpole>(h, p, n, d_traj, d_w, st);
+    case MPPI_MODEL_MOUNTAINCAR: return launch_reroll<MountainCar>(h, p, n, d_traj, d_w, st);
+    case MPPI_MODEL_NAVIGATION2D: return launch_reroll<Navigation2D>(h, p, n, d_traj, d_w, st);
+    case MPPI_MODEL_RACING: return launch_reroll<Racing>(h, p, n, d_traj, d_w, st);
+  }
+  return fail(MPPI_ERR_INVALID, "unknown model");
+}
+
+int mppi_rollout_actions(MppiHandle* h, const float* d_state, const float* d_actions, int32_t n, float* d_traj,
+                         void* stream) {
+  if (!h || !d_state || !d_actions || !d_traj || n < 1) return fail(MPPI_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  SolveParams p = h->base;
+  p.state = d_state;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (h->cfg.model) {
+    case MPPI_MODEL_PENDULUM: return launch_rollout_actions<Pendulum>(h, p, d_actions, n, d_traj, st);
+    case MPPI_MODEL_CARTPOLE: return launch_rollout_actions<Cartpole>(h, p, d_actions, n, d_traj, st);
+    case MPPI_MODEL_MOUNTAINCAR: return launch_rollout_actions<MountainCar>(h, p, d_actions, n, d_traj, st);
+    case MPPI_MODEL_NAVIGATION2D: return launch_rollout_actions<Navigation2D>(h, p, d_actions, n, d_traj, st);
+    case MPPI_MODEL_RACING: return launch_rollout_actions<Racing>(h, p, d_actions, n, d_traj, st);
+  }
+  return fail(MPPI_ERR_INVALID, "unknown model");
+}
+
+int mppi_get_lambda(MppiHandle* h, double* lambda_used, double* lambda_next, void* stream) {
+  if (!h) return fail(MPPI_ERR_INVALID, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  DeviceScalars sc;
+  CUDA_TRY(cudaMemcpyAsync(&sc, h->d_sc, sizeof sc, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  if (lambda_used) *lambda_used = sc.lambda_used;
+  if (lambda_next) *lambda_next = sc.lambda;
+  return MPPI_OK;
+}
+
+int mppi_get_carry(MppiHandle* h, float* d_prev, float* d_hist, void* stream) {
+  if (!h) return fail(MPPI_ERR_INVALID, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d_prev) CUDA_TRY(cudaMemcpyAsync(d_prev, h->d_prev_action, (size_t)h->E * 4, cudaMemcpyDeviceToDevice, st));
+  const size_t hb = (size_t)(h->cfg.horizon - 1) * h->mi.du * 4;
+  if (d_hist && hb) CUDA_TRY(cudaMemcpyAsync(d_hist, h->d_history, hb, cudaMemcpyDeviceToDevice, st));
+  return MPPI_OK;
+}
+
+int mppi_set_carry(MppiHandle* h, const float* d_prev, const float* d_hist, void* stream) {
+  if (!h) return fail(MPPI_ERR_INVALID, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d_prev) CUDA_TRY(cudaMemcpyAsync(h->d_prev_action, d_prev, (size_t)h->E * 4, cudaMemcpyDeviceToDevice, st));
+  const size_t hb = (size_t)(h->cfg.horizon - 1) * h->mi.du * 4;
+  if (d_hist && hb) CUDA_TRY(cudaMemcpyAsync(h->d_history, d_hist, hb, cudaMemcpyDeviceToDevice, st));
+  return MPPI_OK;
+}
+
+int32_t mppi_last_launch_count(const MppiHandle* h) { return h ? h->last_launches : 0; }
+
+int mppi_launch_info(const MppiHandle* h, int32_t* grid, int32_t* block, int32_t* smem_bytes) {
+  if (!h) return fail(MPPI_ERR_INVALID, "null handle");
+  if (grid) *grid = h->grid;
+  if (block) *block = h->block;
+  if (smem_bytes) *smem_bytes = (int32_t)h->smem;
+  return MPPI_OK;
+}
+
+int mppi_kernel_timing(MppiHandle* h, int32_t enable) {
+  if (!h) return fail(MPPI_ERR_INVALID, "null handle");
+  h->timing = enable != 0;
+  return MPPI_OK;
+}
+
+int mppi_kernel_time_ms(MppiHandle* h, double* mean_ms, int32_t* launches) {
+  if (!h) return fail(MPPI_ERR_INVALID, "null handle");
+  double total = 0;
+  int n = 0;
+  for (auto& ev : h->events) {
+    CUDA_TRY(cudaEventSynchronize(ev.second));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, ev.first, ev.second));
+    total += ms;
+    ++n;
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  h->events.clear();
+  if (mean_ms) *mean_ms = n ? total / n : 0.0;
+  if (launches) *launches = n;
+  return MPPI_OK;
+}
+
+uint64_t mppi_solve_index(const MppiHandle* h) { return h ? h->solve_count : 0; }
+
+int mppi_sample_noise(MppiHandle* h, uint64_t solve_index, float* d_noise_out, void* stream) {
+  if (!h || !d_noise_out) return fail(MPPI_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  SolveParams p = h->base;
+  p.key.solve_lo = (uint32_t)solve_index;
+  p.key.solve_hi = (uint32_t)(solve_index >> 32);
+  const int K = h->cfg.num_samples;
+  if (h->mi.du == 1)
+    sample_noise_kernel<1><<<(K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p, d_noise_out);
+  else
+    sample_noise_kernel<2><<<(K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p, d_noise_out);
+  CUDA_TRY(cudaGetLastError());
+  return MPPI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,905 @@
+// mppi_kernels.cuh - the solve kernels of the B200 MPPI engine (sm_100a).
+//
+// One solve (reference src/pi_mpc/mppi.py:255-458) is ONE launch of
+// solve_kernel<Model, kFused> when lambda is known up front (fixed / MPO):
+//
+//   pass 1  per thread = one sample k: T-step rollout with state in registers;
+//           Gaussian perturbation from the counter-based sampler (or injected
+//           noise), clamp, dynamics, stage cost; terminal cost -> costs[k]
+//   block   baseline-subtracted softmax with a block-local baseline
+//           (online-softmax form), exp weights
+//   pass 2  the perturbed controls are regenerated (never stored) and reduced
+//           with a transposed warp reduction into sum_k w_k u_k[t,d]
+//   last    the last block to finish combines the per-block partials, divides,
+//           applies the Savitzky-Golay stencil, rolls the optimal trajectory,
+//           carries the warm start / history, updates MPO's temperature.
+//
+// LBPS / ESSPS need every cost before lambda exists, so they run the same
+// kernel split in two (kCosts, kReduce) around lambda_search_kernel.
+#pragma once
+#include <math.h>
+
+#include "mppi_models.cuh"
+
+namespace mppi {
+
+enum SolveMode : int { kFused = 0, kCosts = 1, kReduce = 2 };
+enum LambdaMode : int { kLamFixed = 0, kLamMPO = 1, kLamLBPS = 2, kLamESSPS = 3 };
+
+constexpr int kPartialHeader = 8;  // xmax S xmax_tau S_tau Sc_tau cmin cmax pad
+constexpr int kMaxSgWindow = 33;
+
+// Scalars carried on the device between solves.
+struct DeviceScalars {
+  double lambda;       // lambda the NEXT solve's weights use
+  double lambda_used;  // lambda the LAST solve's weights used
+  double S;            // sum_k exp(x_k - xmax) of the last solve
+  float xmax;          // max_k(-c_k / lambda) of the last solve
+  float rho;           // MPO log_temperature
+  double adam_m, adam_v;
+  int adam_step;
+  int search_evals;  // objective evaluations of the last LBPS / ESSPS search
+  float cmin, cmax;
+};
+
+struct SolveParams {
+  int K, T;
+  long long k_offset;           // global id of this shard's first sample
+  long long explore_threshold;  // global ids >= threshold are zero-mean (mppi.py:266)
+  float u_min[4], u_max[4], sigma[4];
+  ModelParams mp;
+  const uint32_t* map_bits[2];
+  int map_W[2], map_H[2], map_words[2];
+  unsigned map_bytes[2];  // padded to 16 B
+  float map_cell[2], map_ox[2], map_oy[2];
+  const float* state;    // [ds]
+  const float* refpath;  // [T+1,4] or null
+  const float* noise;    // [K,T,du] or null
+  int ref_bulk_ok;       // refpath is 16 B aligned -> bulk copy
+  float* prev_action;    // [E] (allocation padded to 16 B)
+  unsigned prev_action_bytes;
+  float* history;  // [(T-1)*du]
+  float* nominal_snapshot;  // [E] warm start the last solve sampled around (for get_top_samples)
+  float* state_snapshot;    // [ds] state of the last solve
+  DeviceScalars* sc;
+  float* costs;           // [K]
+  float* block_partials;  // [grid, P]
+  float* rank_partial;    // [P]
+  unsigned int* counter;
+  float* action_out;     // [T,du]
+  float* state_seq_out;  // [T+1,ds]
+  SamplerKey key;
+  int lambda_mode;
+  float mpo_epsilon;
+  int use_sg, sg_window;
+  float sg_coeffs[kMaxSgWindow];
+  int n_shards;  // 1: finish inside the kernel
+  int E, E_pad, P;
+};
+
+// shared-memory carve-up (host and device agree through this helper)
+struct SmemLayout {
+  unsigned map_off[2];
+  unsigned nominal_off, refraw_off, ref4_off, refv_off, warpacc_off, red_off, misc_off, total;
+};
+
+__host__ __device__ inline unsigned align_up(unsigned x, unsigned a) { return (x + a - 1) / a * a; }
+
+__host__ __device__ inline SmemLayout make_layout(int n_maps, const unsigned* map_bytes, int T, int E_pad,
+                                                   unsigned prev_action_bytes, bool refpath, int n_warps) {
+  SmemLayout L;
+  unsigned o = 16;  // mbarrier
+  for (int i = 0; i < 2; ++i) {
+    L.map_off[i] = o;
+    if (i < n_maps) o += align_up(map_bytes[i], 16);
+  }
+  L.nominal_off = o;
+  o += align_up(prev_action_bytes, 16);
+  L.refraw_off = o;
+  if (refpath) o += (unsigned)(T + 1) * 16;
+  L.ref4_off = o;
+  if (refpath) o += (unsigned)T * 16;
+  L.refv_off = o;
+  if (refpath) o += align_up((unsigned)T * 4, 16);
+  L.warpacc_off = align_up(o, 16);
+  o = L.warpacc_off;
+  {  // per-warp accumulators; the last block reuses the region as finish scratch
+    unsigned acc = (unsigned)n_warps * (unsigned)E_pad * 4;
+    unsigned fin = (unsigned)E_pad * 20 + 256 * 4 + 64;
+    o += align_up(acc > fin ? acc : fin, 16);
+  }
+  L.red_off = o;
+  o += 64 * 8;  // block reduction scratch (doubles)
+  L.misc_off = o;
+  o += 64;
+  L.total = o;
+  return L;
+}
+
+// ---------------------------------------------------------------------------
+// block reductions (deterministic: fixed shuffle tree, then warp 0 in order)
+// ---------------------------------------------------------------------------
+template <class T, class Op>
+__device__ __forceinline__ T block_reduce(T v, Op op, T identity, void* scratch) {
+  T* s = reinterpret_cast<T*>(scratch);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(kFullMask, v, o));
+  __syncthreads();  // scratch may still be read from a previous reduction
+  if (lane == 0) s[warp] = v;
+  __syncthreads();
+  T r = (lane < nw) ? s[lane] : identity;
+  if (nw > 32) {  // not reachable: blockDim <= 1024
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) r = op(r, __shfl_xor_sync(kFullMask, r, o));
+  return r;  // every thread holds the result
+}
+struct OpMax {
+  __device__ float operator()(float a, float b) const { return fmaxf(a, b); }
+};
+struct OpMin {
+  __device__ float operator()(float a, float b) const { return fminf(a, b); }
+};
+struct OpAddF {
+  __device__ float operator()(float a, float b) const { return a + b; }
+};
+struct OpAddD {
+  __device__ double operator()(double a, double b) const { return a + b; }
+};
+
+// ---------------------------------------------------------------------------
+// sampling of one chunk (4 normals) -> controls of the timesteps it covers
+// ---------------------------------------------------------------------------
+template <int DU>
+struct Chunking {
+  static_assert(DU == 1 || DU == 2, "built-in models have 1 or 2 controls");
+  static constexpr int kStepsPerChunk = 4 / DU;
+};
+
+// clamp(mean + sigma * eps) for entry e = t * DU + d (mppi.py:266-275)
+template <int DU>
+__device__ __forceinline__ float perturbed_entry(const SolveParams& p, const float* nominal, bool zero_mean, int t,
+                                                 int d, float eps_scaled) {
+  float m = zero_mean ? 0.0f : nominal[t * DU + d];
+  return clampf(m + eps_scaled, p.u_min[d], p.u_max[d]);
+}
+
+// ---------------------------------------------------------------------------
+// finish: combine partials -> optimal sequence -> SG filter -> trajectory, carry
+// ---------------------------------------------------------------------------
+struct Combined {
+  float xmax, xmax_tau, cmin, cmax;
+  double S, S_tau, Sc_tau;
+};
+
+// Combine n partials (stride P) into `out` + N[E] (shared, doubles).
+// Deterministic: fixed traversal order, independent of which block runs it.
+__device__ inline void combine_partials(const float* __restrict__ parts, int n, int P, int E, Combined* out,
+                                        double* N, float* scale_buf /*[256]*/, void* red) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  float xm = -INFINITY, xmt = -INFINITY, cmin = INFINITY, cmax = -INFINITY;
+  for (int b = tid; b < n; b += nt) {
+    const float* q = parts + (size_t)b * P;
+    xm = fmaxf(xm, q[0]);
+    xmt = fmaxf(xmt, q[2]);
+    cmin = fminf(cmin, q[5]);
+    cmax = fmaxf(cmax, q[6]);
+  }
+  xm = block_reduce(xm, OpMax(), -INFINITY, red);
+  xmt = block_reduce(xmt, OpMax(), -INFINITY, red);
+  cmin = block_reduce(cmin, OpMin(), INFINITY, red);
+  cmax = block_reduce(cmax, OpMax(), -INFINITY, red);
+  double S = 0.0, St = 0.0, Sct = 0.0;
+  for (int b = tid; b < n; b += nt) {
+    const float* q = parts + (size_t)b * P;
+    S += (double)q[1] * (double)expf(q[0] - xm);
+    if (xmt > -INFINITY) {
+      double sc = (double)expf(q[2] - xmt);
+      St += (double)q[3] * sc;
+      Sct += (double)q[4] * sc;
+    }
+  }
+  S = block_reduce(S, OpAddD(), 0.0, red);
+  St = block_reduce(St, OpAddD(), 0.0, red);
+  Sct = block_reduce(Sct, OpAddD(), 0.0, red);
+  // weighted-sum numerators: thread e owns entry e, walks the partials in order
+  for (int e = tid; e < E; e += nt) N[e] = 0.0;
+  for (int b0 = 0; b0 < n; b0 += 256) {
+    int nb = min(256, n - b0);
+    __syncthreads();
+    if (tid < nb) scale_buf[tid] = expf(parts[(size_t)(b0 + tid) * P] - xm);
+    __syncthreads();
+    for (int e = tid; e < E; e += nt) {
+      double a = N[e];
+      for (int b = 0; b < nb; ++b)
+        a += (double)parts[(size_t)(b0 + b) * P + kPartialHeader + e] * (double)scale_buf[b];
+      N[e] = a;
+    }
+  }
+  if (tid == 0) {
+    out->xmax = xm;
+    out->xmax_tau = xmt;
+    out->cmin = cmin;
+    out->cmax = cmax;
+    out->S = S;
+    out->S_tau = St;
+    out->Sc_tau = Sct;
+  }
+  __syncthreads();
+}
+
+// MPO temperature update (mppi.py:387-398) in the closed form that reproduces
+// torch's fp32 autograd, see oracle/mppi_oracle.py:mpo_gradient_device_form.
+__device__ inline void mpo_update(const SolveParams& p, const Combined& c) {
+  DeviceScalars* sc = p.sc;
+  float rho = sc->rho;
+  float tau = (rho > 20.0f) ? rho : log1pf(expf(rho));  // softplus, torch threshold 20
+  float lse32 = __fadd_rn((float)log(c.S_tau), c.xmax_tau);
+  double term1 = (double)__fadd_rn(p.mpo_epsilon, lse32);
+  double term2 = exp((double)c.xmax_tau - (double)lse32) * c.Sc_tau / (double)tau;
+  double g = (term1 + term2) / (1.0 + exp(-(double)rho));
+  int step = sc->adam_step + 1;
+  double m = sc->adam_m + (g - sc->adam_m) * (1.0 - 0.9);
+  double v = 0.999 * sc->adam_v + (1.0 - 0.999) * g * g;
+  double bc1 = 1.0 - pow(0.9, (double)step), bc2 = 1.0 - pow(0.999, (double)step);
+  float nrho = (float)((double)rho - (0.2 / bc1) * m / (sqrt(v) / sqrt(bc2) + 1e-8));
+  sc->adam_step = step;
+  sc->adam_m = m;
+  sc->adam_v = v;
+  sc->rho = nrho;
+  sc->lambda = (double)expf(nrho);  // torch.exp(log_temperature).item()
+}
+
+// Everything after the weighted sum (mppi.py:381-458). Runs in ONE block.
+// smem: opt[E], y[(2T-1)*du] floats supplied by the caller.
+template <class M>
+__device__ inline void finish_solve(const SolveParams& p, const typename M::Ctx& ctx, const Combined& c,
+                                    const double* N, float* opt, float* ybuf) {
+  constexpr int DS = M::DS, DU = M::DU;
+  const int tid = threadIdx.x, nt = blockDim.x, T = p.T, E = p.E;
+  const int H = (T - 1) * DU;
+  for (int e = tid; e < E; e += nt) {
+    float r = (float)(N[e] / c.S);  // sum_k softmax_k * u_k  (mppi.py:381-384)
+    opt[e] = r;
+    ybuf[H + e] = r;
+  }
+  for (int i = tid; i < H; i += nt) ybuf[i] = p.history[i];
+  __syncthreads();
+  if (p.use_sg) {  // mppi.py:423-443, 598-620
+    const int W = p.sg_window, pad = W / 2, n = 2 * T - 1;
+    for (int e = tid; e < E; e += nt) {
+      int t = e / DU, d = e - t * DU;
+      int o = (T - 1) + t;  // position in the prolonged sequence
+      float acc = 0.0f;
+      for (int j = 0; j < W; ++j) {
+        int q = o + j;  // index into the padded signal
+        int i = (q < pad) ? (pad - 1 - q) : ((q < pad + n) ? (q - pad) : (n - 1 - (q - pad - n)));
+        acc = acc + p.sg_coeffs[j] * ybuf[i * DU + d];
+      }
+      opt[e] = acc;
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < E; e += nt) {
+    float a = opt[e];
+    p.action_out[e] = a;
+    p.nominal_snapshot[e] = p.prev_action[e];
+    p.prev_action[e] = a;  // warm start, no time shift (mppi.py:452)
+  }
+  for (int i = tid; i < H; i += nt)  // history = cat(history[1:], opt[0]) (mppi.py:455-458)
+    p.history[i] = (i < H - DU) ? ybuf[i + DU] : opt[i - (H - DU)];
+  if (tid == 0) {  // optimal-trajectory rollout (mppi.py:448-449, 508-524)
+    float s[DS], seen[DS], u[DU];
+#pragma unroll
+    for (int i = 0; i < DS; ++i) {
+      s[i] = p.state[i];
+      p.state_snapshot[i] = s[i];
+    }
+    for (int t = 0; t < T; ++t) {
+#pragma unroll
+      for (int d = 0; d < DU; ++d) u[d] = opt[t * DU + d];
+      M::step(ctx, s, u, seen);
+#pragma unroll
+      for (int i = 0; i < DS; ++i) p.state_seq_out[t * DS + i] = seen[i];
+    }
+#pragma unroll
+    for (int i = 0; i < DS; ++i) p.state_seq_out[T * DS + i] = s[i];
+  }
+  if (tid == 32 % nt) {
+    DeviceScalars* sc = p.sc;
+    sc->lambda_used = sc->lambda;
+    sc->S = c.S;
+    sc->xmax = c.xmax;
+    sc->cmin = c.cmin;
+    sc->cmax = c.cmax;
+    if (p.lambda_mode == kLamMPO) mpo_update(p, c);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// the solve kernel
+// ---------------------------------------------------------------------------
+template <class M, bool kInject>
+__device__ __forceinline__ float rollout_cost(const SolveParams& p, const typename M::Ctx& ctx, const float* nominal,
+                                              bool zero_mean, uint32_t k_lo, uint32_t k_hi, long long k_local) {
+  constexpr int DS = M::DS, DU = M::DU, SPC = Chunking<DU>::kStepsPerChunk;
+  const int T = p.T;
+  float s[DS], seen[DS];
+#pragma unroll
+  for (int i = 0; i < DS; ++i) s[i] = __ldg(p.state + i);
+  float u[DU], up[DU], upp[DU];
+#pragma unroll
+  for (int d = 0; d < DU; ++d) up[d] = upp[d] = 0.0f;
+  float total = 0.0f;
+  const float* nz = kInject ? (p.noise + (size_t)k_local * T * DU) : nullptr;
+  for (int t0 = 0, chunk = 0; t0 < T; t0 += SPC, ++chunk) {
+    float z[4];
+    if (!kInject) normal4(p.key, k_lo, k_hi, (uint32_t)chunk, z);
+#pragma unroll
+    for (int j = 0; j < SPC; ++j) {
+      const int t = t0 + j;
+      if (t < T) {
+#pragma unroll
+        for (int d = 0; d < DU; ++d) {
+          float eps = kInject ? nz[t * DU + d] : p.sigma[d] * z[j * DU + d];
+          u[d] = perturbed_entry<DU>(p, nominal, zero_mean, t, d, eps);
+        }
+        float pu[DU];  // info["prev_action"]: U[:, max(t-1, 0)]  (mppi.py:299-304)
+#pragma unroll
+        for (int d = 0; d < DU; ++d) pu[d] = (t == 0) ? u[d] : up[d];
+        M::step(ctx, s, u, seen);                      // S[:, t+1] = dynamics(S[:, t], U[:, t])   (mppi.py:282-286)
+        total = total + M::cost(ctx, seen, u, pu, t);  // stage cost on the stored S[:, t]        (mppi.py:307-311)
+#pragma unroll
+        for (int d = 0; d < DU; ++d) {
+          upp[d] = up[d];
+          up[d] = u[d];
+        }
+      }
+    }
+  }
+  // terminal: state S[:, T], zero action, stale t = T-1 and prev_action = U[:, T-2] (mppi.py:318-328)
+  float zero[DU], pa[DU];
+#pragma unroll
+  for (int d = 0; d < DU; ++d) {
+    zero[d] = 0.0f;
+    pa[d] = (T >= 2) ? upp[d] : up[d];
+  }
+  return total + M::cost(ctx, s, zero, pa, T - 1);  // mppi.py:333-336
+}
+
+template <class M, bool kInject, int kMode>
+__global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ SolveParams p) {
+  constexpr int DU = M::DU;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
+  const SmemLayout L =
+      make_layout(M::kMaps, p.map_bytes, p.T, p.E_pad, p.prev_action_bytes, M::kRefPath, n_warps);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  float* nominal = reinterpret_cast<float*>(smem + L.nominal_off);
+  float* warp_acc = reinterpret_cast<float*>(smem + L.warpacc_off);
+  void* red = smem + L.red_off;
+  int* misc = reinterpret_cast<int*>(smem + L.misc_off);
+
+  // ---- stage the block's read-only inputs into shared memory (TMA bulk copies)
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    unsigned bytes = p.prev_action_bytes;
+    if (kMode != kReduce) {
+      for (int i = 0; i < M::kMaps; ++i) bytes += p.map_bytes[i];
+      if (M::kRefPath && p.ref_bulk_ok) bytes += (unsigned)(p.T + 1) * 16;
+    }
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(nominal, p.prev_action, p.prev_action_bytes, bar);
+    if (kMode != kReduce) {
+      for (int i = 0; i < M::kMaps; ++i) bulk_g2s(smem + L.map_off[i], p.map_bits[i], p.map_bytes[i], bar);
+      if (M::kRefPath && p.ref_bulk_ok) bulk_g2s(smem + L.refraw_off, p.refpath, (unsigned)(p.T + 1) * 16, bar);
+    }
+  }
+  if (M::kRefPath && kMode != kReduce && !p.ref_bulk_ok) {
+    float* raw = reinterpret_cast<float*>(smem + L.refraw_off);
+    for (int i = tid; i < (p.T + 1) * 4; i += blockDim.x) raw[i] = p.refpath[i];
+  }
+  mbar_wait(bar, 0);
+  __syncthreads();
+
+  typename M::Ctx ctx;
+  if constexpr (M::kMaps >= 1) {
+    MapView mv[2];
+    for (int i = 0; i < M::kMaps; ++i)
+      mv[i] = MapView{reinterpret_cast<const uint32_t*>(smem + L.map_off[i]), p.map_W[i], p.map_H[i], p.map_words[i],
+                      p.map_cell[i], p.map_ox[i], p.map_oy[i]};
+    if constexpr (M::kMaps == 1) {
+      ctx.map = mv[0];
+    } else {
+      ctx.obstacle = mv[0];
+      ctx.lane = mv[1];
+    }
+    ctx.p = &p.mp;
+  }
+  if constexpr (M::kRefPath) {
+    // per-stage reference row: (x, y, sin yaw, cos yaw), v_target (racing.py:127-143)
+    float4* ref4 = reinterpret_cast<float4*>(smem + L.ref4_off);
+    float* refv = reinterpret_cast<float*>(smem + L.refv_off);
+    if (kMode != kReduce) {
+      const float* raw = reinterpret_cast<const float*>(smem + L.refraw_off);
+      for (int t = tid; t < p.T; t += blockDim.x) {
+        float sy, cy;
+        sincosf(raw[t * 4 + 2], &sy, &cy);
+        ref4[t] = make_float4(raw[t * 4 + 0], raw[t * 4 + 1], sy, cy);
+        refv[t] = raw[t * 4 + 3];
+      }
+      __syncthreads();
+    }
+    ctx.ref = ref4;
+    ctx.ref_v = refv;
+  }
+
+  const long long k_local = (long long)blockIdx.x * blockDim.x + tid;
+  const bool active = k_local < p.K;
+  const long long k_global = p.k_offset + k_local;
+  const uint32_t k_lo = (uint32_t)k_global, k_hi = (uint32_t)((unsigned long long)k_global >> 32);
+  const bool zero_mean = k_global >= p.explore_threshold;
+
+  // ---- pass 1: rollout + cost -------------------------------------------------
+  float cost = INFINITY;
+  if (kMode == kReduce) {
+    if (active) cost = p.costs[k_local];
+  } else if (active) {
+    cost = rollout_cost<M, kInject>(p, ctx, nominal, zero_mean, k_lo, k_hi, k_local);
+    p.costs[k_local] = cost;
+  }
+  if (kMode == kCosts) return;
+
+  // ---- block-local softmax baseline (mppi.py:376; online-softmax form) -----------
+  const float lam = (float)p.sc->lambda;
+  const float x = active ? (-cost) / lam : -INFINITY;
+  const float xmax_b = block_reduce(x, OpMax(), -INFINITY, red);
+  const float w = active ? expf(x - xmax_b) : 0.0f;
+  const float S_b = block_reduce(w, OpAddF(), 0.0f, red);
+  const float cmin_b = block_reduce(active ? cost : INFINITY, OpMin(), INFINITY, red);
+  const float cmax_b = block_reduce(active ? cost : -INFINITY, OpMax(), -INFINITY, red);
+  float xmt_b = -INFINITY, St_b = 0.0f, Sct_b = 0.0f;
+  if (p.lambda_mode == kLamMPO) {  // second softmax at tau = softplus(rho) for the MPO step
+    const float rho = p.sc->rho;
+    const float tau = (rho > 20.0f) ? rho : log1pf(expf(rho));
+    const float xt = active ? (-cost) / tau : -INFINITY;
+    xmt_b = block_reduce(xt, OpMax(), -INFINITY, red);
+    const float et = active ? expf(xt - xmt_b) : 0.0f;
+    St_b = block_reduce(et, OpAddF(), 0.0f, red);
+    Sct_b = block_reduce(active ? et * cost : 0.0f, OpAddF(), 0.0f, red);
+  }
+
+  // ---- pass 2: regenerate the perturbed controls, reduce sum_k w_k u_k -------------
+  const int n_groups = p.E_pad / 32;
+  float* my_acc = warp_acc + (size_t)warp * p.E_pad;
+  if (__any_sync(kFullMask, w != 0.0f)) {  // exact: a zero weight contributes exactly nothing
+    const float* nz = kInject && active ? (p.noise + (size_t)k_local * p.T * DU) : nullptr;
+    for (int g = 0; g < n_groups; ++g) {
+      float v[32];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float z[4];
+        const int e0 = g * 32 + c * 4;
+        if (!kInject && e0 < p.E) normal4(p.key, k_lo, k_hi, (uint32_t)(g * 8 + c), z);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int e = e0 + j;
+          float val = 0.0f;
+          if (e < p.E && active) {
+            const int t = e / DU, d = e - t * DU;
+            float eps = kInject ? nz[e] : p.sigma[d] * z[j];
+            val = w * perturbed_entry<DU>(p, nominal, zero_mean, t, d, eps);
+          }
+          v[c * 4 + j] = val;
+        }
+      }
+      float r = warp_transpose_sum(v, lane);
+      my_acc[g * 32 + lane] = r;
+    }
+  } else {
+    for (int e = lane; e < p.E_pad; e += 32) my_acc[e] = 0.0f;
+  }
+  __syncthreads();
+  float* part = p.block_partials + (size_t)blockIdx.x * p.P;
+  for (int e = tid; e < p.E; e += blockDim.x) {
+    float a = 0.0f;
+    for (int wv = 0; wv < n_warps; ++wv) a += warp_acc[(size_t)wv * p.E_pad + e];
+    part[kPartialHeader + e] = a;
+  }
+  if (tid == 0) {
+    part[0] = xmax_b;
+    part[1] = S_b;
+    part[2] = xmt_b;
+    part[3] = St_b;
+    part[4] = Sct_b;
+    part[5] = cmin_b;
+    part[6] = cmax_b;
+    part[7] = 0.0f;
+  }
+
+  // ---- last block: combine and finish ------------------------------------------------
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    unsigned ticket = atomicAdd(p.counter, 1u);
+    misc[0] = (ticket == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!misc[0]) return;
+  __threadfence();
+  // reuse the per-warp accumulators as scratch: N[E] doubles, opt[E], y[(2T-1)*du], scales[256]
+  // (n_warps * E_pad * 4 bytes are available; the host sizes it for this, see engine)
+  double* Nbuf = reinterpret_cast<double*>(smem + L.warpacc_off);
+  float* opt = reinterpret_cast<float*>(Nbuf + p.E_pad);
+  float* ybuf = opt + p.E_pad;
+  float* scale_buf = ybuf + 2 * p.E_pad;
+  Combined* comb = reinterpret_cast<Combined*>(scale_buf + 256);
+  combine_partials(p.block_partials, (int)gridDim.x, p.P, p.E, comb, Nbuf, scale_buf, red);
+  if (p.n_shards == 1) {
+    finish_solve<M>(p, ctx, *comb, Nbuf, opt, ybuf);
+  } else {
+    for (int e = tid; e < p.E; e += blockDim.x) p.rank_partial[kPartialHeader + e] = (float)Nbuf[e];
+    if (tid == 0) {
+      float* q = p.rank_partial;
+      q[0] = comb->xmax;
+      q[1] = (float)comb->S;
+      q[2] = comb->xmax_tau;
+      q[3] = (float)comb->S_tau;
+      q[4] = (float)comb->Sc_tau;
+      q[5] = comb->cmin;
+      q[6] = comb->cmax;
+      q[7] = 0.0f;
+    }
+  }
+  if (tid == 0) *p.counter = 0u;
+}
+
+// Stage 3 of a sharded solve: combine the gathered shard partials and finish.
+template <class M>
+__global__ void __launch_bounds__(256, 1) finish_kernel(const __grid_constant__ SolveParams p, const float* parts,
+                                                         int n) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  double* Nbuf = reinterpret_cast<double*>(smem);
+  float* opt = reinterpret_cast<float*>(Nbuf + p.E_pad);
+  float* ybuf = opt + p.E_pad;
+  float* scale_buf = ybuf + 2 * p.E_pad;
+  Combined* comb = reinterpret_cast<Combined*>(scale_buf + 256);
+  void* red = reinterpret_cast<unsigned char*>(comb) + 64;
+  typename M::Ctx ctx{};
+  if constexpr (M::kMaps >= 1) ctx.p = &p.mp;
+  combine_partials(parts, n, p.P, p.E, comb, Nbuf, scale_buf, red);
+  finish_solve<M>(p, ctx, *comb, Nbuf, opt, ybuf);
+}
+
+__host__ __device__ inline unsigned finish_scratch_bytes(int E_pad) {
+  return (unsigned)E_pad * 8 + (unsigned)E_pad * 4 * 3 + 256 * 4 + 64 + 64 * 8;
+}
+
+// ---------------------------------------------------------------------------
+// LBPS / ESSPS: lambda search on costs[K] (mppi.py:341-370, 526-566). One block;
+// the control flow of scipy's bounded Brent / brentq runs redundantly in every
+// thread in fp64, each objective evaluation is a block-wide reduction.
+// ---------------------------------------------------------------------------
+struct SearchStats {
+  double S, S2, Sc;
+};
+
+__device__ inline SearchStats softmax_stats(const float* __restrict__ costs, long long n, double lambda, float cmin,
+                                            void* red) {
+  // w = softmax(-c / lambda) in fp32 like the reference; sums kept in fp64
+  const float lam = (float)lambda;
+  const float xmax = (-cmin) / lam;
+  double S = 0.0, S2 = 0.0, Sc = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    float c = costs[i];
+    float e = expf((-c) / lam - xmax);
+    S += (double)e;
+    S2 += (double)e * (double)e;
+    Sc += (double)e * (double)c;
+  }
+  SearchStats r;
+  r.S = block_reduce(S, OpAddD(), 0.0, red);
+  r.S2 = block_reduce(S2, OpAddD(), 0.0, red);
+  r.Sc = block_reduce(Sc, OpAddD(), 0.0, red);
+  return r;
+}
+
+struct SearchParams {
+  const float* costs;
+  long long n;
+  int mode;  // kLamLBPS / kLamESSPS
+  double lambda_min, lambda_max, lbps_delta, essps_target;
+  DeviceScalars* sc;
+};
+
+__device__ inline double dsign(double x) { return (x > 0.0) - (x < 0.0); }
+
+__global__ void __launch_bounds__(1024, 1) lambda_search_kernel(const SearchParams q) {
+  __shared__ double red[64];
+  float cmin = INFINITY, cmax = -INFINITY;
+  for (long long i = threadIdx.x; i < q.n; i += blockDim.x) {
+    float c = q.costs[i];
+    cmin = fminf(cmin, c);
+    cmax = fmaxf(cmax, c);
+  }
+  cmin = block_reduce(cmin, OpMin(), INFINITY, red);
+  cmax = block_reduce(cmax, OpMax(), -INFINITY, red);
+  int evals = 0;
+  double result;
+  if (q.mode == kLamLBPS) {
+    // J(lambda) = sum w c + (cmax - cmin) * sqrt((1-delta)/delta) / sqrt(ESS)   (mppi.py:534-557)
+    const double range = (double)(float)(cmax - cmin);
+    const double pen = sqrt((1.0 - q.lbps_delta) / q.lbps_delta);
+    auto J = [&](double lam) {
+      SearchStats s = softmax_stats(q.costs, q.n, lam, cmin, red);
+      ++evals;
+      double ess = 1.0 / (double)(float)(s.S2 / (s.S * s.S));
+      double expected = (double)(float)(s.Sc / s.S);
+      return expected + range * pen / sqrt(ess);
+    };
+    // scipy.optimize minimize_scalar(method="bounded"), xatol = 1e-5, maxiter = 500
+    const double sqrt_eps = sqrt(2.2e-16), golden_mean = 0.5 * (3.0 - sqrt(5.0)), xatol = 1e-5;
+    double a = q.lambda_min, b = q.lambda_max;
+    double fulc = a + golden_mean * (b - a), nfc = fulc, xf = fulc, rat = 0.0, e = 0.0, x = xf;
+    double fx = J(x);
+    int num = 1;
+    double ffulc = fx, fnfc = fx;
+    double xm = 0.5 * (a + b), tol1 = sqrt_eps * fabs(xf) + xatol / 3.0, tol2 = 2.0 * tol1;
+    while (fabs(xf - xm) > (tol2 - 0.5 * (b - a))) {
+      bool golden = true;
+      if (fabs(e) > tol1) {
+        golden = false;
+        double r = (xf - nfc) * (fx - ffulc);
+        double qq = (xf - fulc) * (fx - fnfc);
+        double pp = (xf - fulc) * qq - (xf - nfc) * r;
+        qq = 2.0 * (qq - r);
+        if (qq > 0.0) pp = -pp;
+        qq = fabs(qq);
+        r = e;
+        e = rat;
+        if (fabs(pp) < fabs(0.5 * qq * r) && pp > qq * (a - xf) && pp < qq * (b - xf)) {
+          rat = (pp + 0.0) / qq;
+          x = xf + rat;
+          if ((x - a) < tol2 || (b - x) < tol2) {
+            double si = dsign(xm - xf) + ((xm - xf) == 0.0 ? 1.0 : 0.0);
+            rat = tol1 * si;
+          }
+        } else {
+          golden = true;
+        }
+      }
+      if (golden) {
+        e = (xf >= xm) ? (a - xf) : (b - xf);
+        rat = golden_mean * e;
+      }
+      double si = dsign(rat) + (rat == 0.0 ? 1.0 : 0.0);
+      x = xf + si * fmax(fabs(rat), tol1);
+      double fu = J(x);
+      ++num;
+      if (fu <= fx) {
+        if (x >= xf)
+          a = xf;
+        else
+          b = xf;
+        fulc = nfc;
+        ffulc = fnfc;
+        nfc = xf;
+        fnfc = fx;
+        xf = x;
+        fx = fu;
+      } else {
+        if (x < xf)
+          a = x;
+        else
+          b = x;
+        if (fu <= fnfc || nfc == xf) {
+          fulc = nfc;
+          ffulc = fnfc;
+          nfc = x;
+          fnfc = fu;
+        } else if (fu <= ffulc || fulc == xf || fulc == nfc) {
+          fulc = x;
+          ffulc = fu;
+        }
+      }
+      xm = 0.5 * (a + b);
+      tol1 = sqrt_eps * fabs(xf) + xatol / 3.0;
+      tol2 = 2.0 * tol1;
+      if (num >= 500) break;
+    }
+    result = xf;
+  } else {
+    // ESS(lambda) = 1 / sum w^2  (mppi.py:526-532); root of ESS - target (mppi.py:351-370)
+    auto F = [&](double lam) {
+      SearchStats s = softmax_stats(q.costs, q.n, lam, cmin, red);
+      ++evals;
+      return 1.0 / (double)(float)(s.S2 / (s.S * s.S)) - q.essps_target;
+    };
+    double f_lo = F(q.lambda_min), f_hi = F(q.lambda_max);
+    if (f_lo >= 0.0) {  // target <= ess_at_min
+      result = q.lambda_min;
+    } else if (f_hi <= 0.0) {  // target >= ess_at_max
+      result = q.lambda_max;
+    } else {
+      // scipy.optimize.brentq, xtol = 2e-12, rtol = 4 eps, maxiter = 100
+      const double xtol = 2e-12, rtol = 8.881784197001252e-16;
+      double xpre = q.lambda_min, xcur = q.lambda_max, fpre = F(xpre), fcur = F(xcur);
+      double xblk = 0.0, fblk = 0.0, spre = 0.0, scur = 0.0;
+      result = xcur;
+      bool done = false;
+      if (fpre == 0.0) {
+        result = xpre;
+        done = true;
+      } else if (fcur == 0.0) {
+        result = xcur;
+        done = true;
+      }
+      for (int it = 0; it < 100 && !done; ++it) {
+        if (fpre != 0.0 && fcur != 0.0 && ((fpre < 0.0) != (fcur < 0.0))) {
+          xblk = xpre;
+          fblk = fpre;
+          spre = scur = xcur - xpre;
+        }
+        if (fabs(fblk) < fabs(fcur)) {
+          xpre = xcur;
+          xcur = xblk;
+          xblk = xpre;
+          fpre = fcur;
+          fcur = fblk;
+          fblk = fpre;
+        }
+        double delta = (xtol + rtol * fabs(xcur)) / 2.0;
+        double sbis = (xblk - xcur) / 2.0;
+        if (fcur == 0.0 || fabs(sbis) < delta) {
+          result = xcur;
+          done = true;
+          break;
+        }
+        if (fabs(spre) > delta && fabs(fcur) < fabs(fpre)) {
+          double stry;
+          if (xpre == xblk) {
+            stry = -fcur * (xcur - xpre) / (fcur - fpre);
+          } else {
+            double dpre = (fpre - fcur) / (xpre - xcur);
+            double dblk = (fblk - fcur) / (xblk - xcur);
+            stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre));
+          }
+          if (2.0 * fabs(stry) < fmin(fabs(spre), 3.0 * fabs(sbis) - delta)) {
+            spre = scur;
+            scur = stry;
+          } else {
+            spre = sbis;
+            scur = sbis;
+          }
+        } else {
+          spre = sbis;
+          scur = sbis;
+        }
+        xpre = xcur;
+        fpre = fcur;
+        if (fabs(scur) > delta)
+          xcur += scur;
+        else
+          xcur += (sbis > 0.0 ? delta : -delta);
+        fcur = F(xcur);
+        result = xcur;
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    q.sc->lambda = result;
+    q.sc->search_evals = evals;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// small utility kernels
+// ---------------------------------------------------------------------------
+__global__ void weights_kernel(const float* __restrict__ costs, int K, const DeviceScalars* sc,
+                               float* __restrict__ out) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const float lam = (float)sc->lambda_used;
+  out[k] = expf((-costs[k]) / lam - sc->xmax) / (float)sc->S;
+}
+
+__global__ void iota_kernel(int* out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i;
+}
+
+__global__ void pack_map_kernel(const float* __restrict__ grid, int W, int H, int words, uint32_t* __restrict__ bits) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= W * words) return;
+  int ix = idx / words, wj = idx - ix * words;
+  uint32_t v = 0;
+  for (int b = 0; b < 32; ++b) {
+    int iy = wj * 32 + b;
+    if (iy < H && grid[(size_t)ix * H + iy] != 0.0f) v |= (1u << b);
+  }
+  bits[idx] = v;
+}
+
+// sigma * eps of the in-kernel sampler in the reference's [K,T,du] layout
+// (what MultivariateNormal.rsample returns, mppi.py:261-263) - tests only.
+template <int DU>
+__global__ void sample_noise_kernel(SolveParams p, float* __restrict__ out) {
+  long long k_local = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k_local >= p.K) return;
+  long long kg = p.k_offset + k_local;
+  uint32_t k_lo = (uint32_t)kg, k_hi = (uint32_t)((unsigned long long)kg >> 32);
+  for (int c = 0; c * 4 < p.E; ++c) {
+    float z[4];
+    normal4(p.key, k_lo, k_hi, (uint32_t)c, z);
+    for (int j = 0; j < 4; ++j) {
+      int e = c * 4 + j;
+      if (e < p.E) out[(size_t)k_local * p.E + e] = p.sigma[e % DU] * z[j];
+    }
+  }
+}
+
+// get_top_samples (mppi.py:462-487): re-roll the selected samples, storing states.
+template <class M, bool kInject>
+__global__ void reroll_kernel(SolveParams p, const int* __restrict__ order, int n, float* __restrict__ traj,
+                              float* __restrict__ wout) {
+  constexpr int DS = M::DS, DU = M::DU, SPC = Chunking<DU>::kStepsPerChunk;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long k_local = order[i];
+  const long long kg = p.k_offset + k_local;
+  const uint32_t k_lo = (uint32_t)kg, k_hi = (uint32_t)((unsigned long long)kg >> 32);
+  const bool zero_mean = kg >= p.explore_threshold;
+  typename M::Ctx ctx{};
+  if constexpr (M::kMaps >= 1) ctx.p = &p.mp;
+  float s[DS], seen[DS], u[DU];
+  for (int d = 0; d < DS; ++d) s[d] = p.state[d];
+  float* out = traj + (size_t)i * (p.T + 1) * DS;
+  const float* nz = kInject ? (p.noise + (size_t)k_local * p.T * DU) : nullptr;
+  for (int t0 = 0, chunk = 0; t0 < p.T; t0 += SPC, ++chunk) {
+    float z[4];
+    if (!kInject) normal4(p.key, k_lo, k_hi, (uint32_t)chunk, z);
+    for (int j = 0; j < SPC; ++j) {
+      int t = t0 + j;
+      if (t >= p.T) break;
+      for (int d = 0; d < DU; ++d) {
+        float eps = kInject ? nz[t * DU + d] : p.sigma[d] * z[j * DU + d];
+        // the warm start the solve used is gone (carried state was overwritten);
+        // p.prev_action here points at a snapshot taken before the solve
+        u[d] = perturbed_entry<DU>(p, p.prev_action, zero_mean, t, d, eps);
+      }
+      M::step(ctx, s, u, seen);
+      for (int d = 0; d < DS; ++d) out[t * DS + d] = seen[d];
+    }
+  }
+  for (int d = 0; d < DS; ++d) out[p.T * DS + d] = s[d];
+  const float lam = (float)p.sc->lambda_used;
+  wout[i] = expf((-p.costs[k_local]) / lam - p.sc->xmax) / (float)p.sc->S;
+}
+
+// _states_prediction (mppi.py:508-524): roll n given action sequences [n,T,du].
+template <class M>
+__global__ void rollout_actions_kernel(SolveParams p, const float* __restrict__ actions, int n,
+                                       float* __restrict__ traj) {
+  constexpr int DS = M::DS, DU = M::DU;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  typename M::Ctx ctx{};
+  if constexpr (M::kMaps >= 1) ctx.p = &p.mp;
+  float s[DS], seen[DS], u[DU];
+  for (int d = 0; d < DS; ++d) s[d] = p.state[d];
+  float* out = traj + (size_t)i * (p.T + 1) * DS;
+  const float* a = actions + (size_t)i * p.T * DU;
+  for (int t = 0; t < p.T; ++t) {
+    for (int d = 0; d < DU; ++d) u[d] = a[t * DU + d];
+    M::step(ctx, s, u, seen);
+    for (int d = 0; d < DS; ++d) out[t * DS + d] = seen[d];
+  }
+  for (int d = 0; d < DS; ++d) out[p.T * DS + d] = s[d];
+}
+
+}  // namespace mppi

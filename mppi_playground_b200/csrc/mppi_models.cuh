@@ -1,0 +1,205 @@
+// mppi_models.cuh - the reference's env models as __device__ functions.
+//
+// Each model restates, operation for operation, the fp32 ATen sequence of the
+// reference callable it replaces (file:line cited per model; paths relative to
+// the reference root). The translation unit is compiled with -fmad=false: the
+// reference never fuses a multiply into an add (every ATen op is its own
+// kernel), and the occupancy costs are discontinuous in the rolled-out
+// position, so contraction is off here on purpose. Division is IEEE (`/`),
+// rounding to cells is half-to-even (torch.round), sin/cos/tan are the
+// precise CUDA libm versions.
+//
+// Interface (all static, state lives in registers of one thread):
+//   step(ctx, s, u, seen)  s <- dynamics(s, u); `seen` = what the solver's
+//                          stored S[:, t] holds when the cost loop reads it
+//                          (== the input state, except MountainCar, whose
+//                          dynamics writes through its input views).
+//   cost(ctx, s, u, pu, t) stage cost with info = {prev_action: pu, t}.
+#pragma once
+#include "mppi_device.cuh"
+
+namespace mppi {
+
+// Occupancy grid, bit-packed: bit (iy & 31) of word [ix * words + (iy >> 5)].
+struct MapView {
+  const uint32_t* bits;
+  int W, H, words;
+  float cell, ox, oy;
+};
+
+// src/envs/obstacle_map_2d.py:168-200 == src/envs/lane_map_2d.py:90-122.
+__device__ __forceinline__ float map_lookup(const MapView& m, float x, float y) {
+  int ix = __float2int_rn(x / m.cell + m.ox);  // :179-180 true division, round half-even, to integer
+  int iy = __float2int_rn(y / m.cell + m.oy);
+  bool oob = (ix < 0) | (ix >= m.W) | (iy < 0) | (iy >= m.H);  // :183-190
+  ix = min(max(ix, 0), m.W - 1);                                // :191-192
+  iy = min(max(iy, 0), m.H - 1);
+  uint32_t w = m.bits[ix * m.words + (iy >> 5)];  // :195
+  float occ = (float)((w >> (iy & 31)) & 1u);
+  return oob ? 1.0f : occ;  // :198
+}
+
+struct ModelParams {
+  float v[32];
+};
+
+// ---------------------------------------------------------------------------
+struct Pendulum {  // example/pendulum.py:17-47
+  static constexpr int DS = 2, DU = 1, kMaps = 0;
+  static constexpr bool kRefPath = false;
+  struct Ctx {};
+  __device__ static __forceinline__ void step(const Ctx&, float (&s)[DS], const float (&u)[DU], float (&seen)[DS]) {
+    seen[0] = s[0];
+    seen[1] = s[1];
+    const float pi = 3.14159274101257324f;
+    float tq = clampf(u[0], -2.0f, 2.0f);                       // :26-27
+    float acc = (-15.0f * sinf(s[0] + pi) + 3.0f * tq) * 0.05f;  // :28-35
+    float nthd = s[1] + acc;
+    s[0] = s[0] + nthd * 0.05f;       // :36 (unclamped rate)
+    s[1] = clampf(nthd, -8.0f, 8.0f);  // :37
+  }
+  __device__ static __forceinline__ float cost(const Ctx&, const float (&s)[DS], const float (&)[DU],
+                                               const float (&)[DU], int) {
+    float a = wrap_angle(s[0]);
+    return a * a + 0.1f * (s[1] * s[1]);  // :42-47
+  }
+};
+
+// ---------------------------------------------------------------------------
+struct Cartpole {  // example/cartpole.py:17-81
+  static constexpr int DS = 4, DU = 1, kMaps = 0;
+  static constexpr bool kRefPath = false;
+  struct Ctx {};
+  __device__ static __forceinline__ void step(const Ctx&, float (&s)[DS], const float (&u)[DU], float (&seen)[DS]) {
+#pragma unroll
+    for (int i = 0; i < DS; ++i) seen[i] = s[i];
+    const float total_mass = 1.1f, pml = 0.05f;                              // :30-34
+    float force = (u[0] >= 0.0f) ? 10.0f : ((u[0] < 0.0f) ? -10.0f : 0.0f);  // :41-44 bang-bang
+    float st, ct;
+    sincosf(s[2], &st, &ct);
+    float temp = (force + pml * (s[3] * s[3]) * st) / total_mass;                                    // :49
+    float thacc = (9.8f * st - ct * temp) / (0.5f * (1.33333337306976318f - 0.1f * (ct * ct) / total_mass));  // :50-52
+    float xacc = temp - pml * thacc * ct / total_mass;                                               // :53
+    float nx = s[0] + 0.02f * s[1];  // :55-58
+    float nxd = s[1] + 0.02f * xacc;
+    float nth = s[2] + 0.02f * s[3];
+    float nthd = s[3] + 0.02f * thacc;
+    s[0] = clampf(nx, -2.4f, 2.4f);                                  // :60-65
+    s[2] = clampf(nth, -0.20943951606750488f, 0.20943951606750488f);  // float(12*2*pi/360)
+    s[1] = nxd;
+    s[3] = nthd;
+  }
+  __device__ static __forceinline__ float cost(const Ctx&, const float (&s)[DS], const float (&)[DU],
+                                               const float (&)[DU], int) {
+    float a = wrap_angle(s[2]);
+    return a * a + 0.1f * (s[3] * s[3]) + 0.1f * (s[0] * s[0]);  // :71-81
+  }
+};
+
+// ---------------------------------------------------------------------------
+struct MountainCar {  // example/mountaincar.py:17-55
+  static constexpr int DS = 2, DU = 1, kMaps = 0;
+  static constexpr bool kRefPath = false;
+  struct Ctx {};
+  __device__ static __forceinline__ void step(const Ctx&, float (&s)[DS], const float (&u)[DU], float (&seen)[DS]) {
+    float force = clampf(u[0], -1.0f, 1.0f);                          // :32
+    float v_raw = s[1] + (force * 0.0015f - 0.0025f * cosf(3.0f * s[0]));  // :34  `velocity +=` (in place)
+    float v = clampf(v_raw, -0.07f, 0.07f);                            // :35
+    float p_raw = s[0] + v;                                            // :36  `position +=` (in place)
+    seen[0] = p_raw;  // the in-place writes land in the solver's S[:, t]
+    seen[1] = v_raw;
+    s[0] = clampf(p_raw, -1.2f, 0.6f);  // :37
+    s[1] = v;
+  }
+  __device__ static __forceinline__ float cost(const Ctx&, const float (&s)[DS], const float (&)[DU],
+                                               const float (&)[DU], int) {
+    float d = 0.45f - s[0];
+    return d * d;  // :45-55
+  }
+};
+
+// ---------------------------------------------------------------------------
+struct Navigation2D {  // src/envs/navigation_2d.py:218-279
+  static constexpr int DS = 3, DU = 2, kMaps = 1;
+  static constexpr bool kRefPath = false;
+  struct Ctx {
+    MapView map;
+    const ModelParams* p;  // v_min v_max w_min w_max goal_x goal_y x_lo x_hi y_lo y_hi dt w_obst
+  };
+  __device__ static __forceinline__ void step(const Ctx& c, float (&s)[DS], const float (&u)[DU], float (&seen)[DS]) {
+    const float* p = c.p->v;
+#pragma unroll
+    for (int i = 0; i < DS; ++i) seen[i] = s[i];
+    float v = clampf(u[0], p[0], p[1]);  // :235-236
+    float w = clampf(u[1], p[2], p[3]);
+    float th = wrap_angle(s[2]);  // :237
+    float st, ct;
+    sincosf(th, &st, &ct);
+    float nx = s[0] + v * ct * p[10];  // :239-241
+    float ny = s[1] + v * st * p[10];
+    float nth = wrap_angle(th + w * p[10]);
+    s[0] = clampf(nx, p[6], p[7]);  // :244-251
+    s[1] = clampf(ny, p[8], p[9]);
+    s[2] = nth;
+  }
+  __device__ static __forceinline__ float cost(const Ctx& c, const float (&s)[DS], const float (&)[DU],
+                                               const float (&)[DU], int) {
+    const float* p = c.p->v;
+    float dx = s[0] - p[4], dy = s[1] - p[5];
+    float goal = sqrtf(dx * dx + dy * dy);              // :269
+    return goal + p[11] * map_lookup(c.map, s[0], s[1]);  // :271-277
+  }
+};
+
+// ---------------------------------------------------------------------------
+struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
+  static constexpr int DS = 4, DU = 2, kMaps = 2;
+  static constexpr bool kRefPath = true;
+  struct Ctx {
+    MapView obstacle, lane;
+    const ModelParams* p;  // a_min a_max s_min s_max L v_max x_lo x_hi y_lo y_hi dt Qc Ql Qv Qo Qin Qdin
+    const float4* ref;     // per stage t: (x, y, sin yaw, cos yaw) of reference_path[t]
+    const float* ref_v;    // per stage t: target speed reference_path[t, 3]
+  };
+  __device__ static __forceinline__ void step(const Ctx& c, float (&s)[DS], const float (&u)[DU], float (&seen)[DS]) {
+    const float* p = c.p->v;
+#pragma unroll
+    for (int i = 0; i < DS; ++i) seen[i] = s[i];
+    float accel = clampf(u[0], p[0], p[1]);  // :345-346
+    float steer = clampf(u[1], p[2], p[3]);
+    float th = wrap_angle(s[2]);  // :347
+    float st, ct;
+    sincosf(th, &st, &ct);
+    float dx = s[3] * ct;  // :349-352
+    float dy = s[3] * st;
+    float dth = s[3] * tanf(steer) / p[4];
+    float nx = s[0] + dx * p[10];  // :354-357
+    float ny = s[1] + dy * p[10];
+    float nth = wrap_angle(th + dth * p[10]);
+    float nv = s[3] + accel * p[10];
+    s[0] = clampf(nx, p[6], p[7]);  // :360-368
+    s[1] = clampf(ny, p[8], p[9]);
+    s[2] = nth;
+    s[3] = clampf(nv, -p[5], p[5]);
+  }
+  __device__ static __forceinline__ float cost(const Ctx& c, const float (&s)[DS], const float (&u)[DU],
+                                               const float (&pu)[DU], int t) {
+    const float* p = c.p->v;
+    const float4 r = c.ref[t];
+    float sx = s[0] - r.x, sy = s[1] - r.y;
+    float ec = r.z * sx - r.w * sy;                         // racing.py:127-131
+    float el = (-r.w) * sx - r.z * sy;                      // :132-136
+    float path = p[11] * (ec * ec) + p[12] * (el * el);     // :138
+    float dv = s[3] - c.ref_v[t];
+    float vel = p[13] * (dv * dv);                           // :141-143
+    float occ = map_lookup(c.obstacle, s[0], s[1]);          // :146-150
+    occ = occ + map_lookup(c.lane, s[0], s[1]);
+    occ = p[14] * occ;                                       // :151
+    float in = p[15] * (u[0] * u[0] + u[1] * u[1]);          // :154
+    float d0 = u[0] - pu[0], d1 = u[1] - pu[1];
+    in = in + p[16] * (d0 * d0 + d1 * d1);                   // :155
+    return path + vel + occ + in;                            // :157
+  }
+};
+
+}  // namespace mppi

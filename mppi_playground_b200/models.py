@@ -1,0 +1,316 @@
+"""Host-side model descriptors and callable -> device-model resolution.
+
+The reference's operator API for the hot path is two Python callables,
+``dynamics(state[K,ds], action[K,du])`` and ``cost_func(state, action, info)``
+(src/pi_mpc/mppi.py:30-31). The engine cannot run Python inside a CUDA kernel,
+so ``resolve`` maps the callables an example passes onto one of the built-in
+``__device__`` models (csrc/mppi_models.cuh):
+
+* bound methods of the reference's env / controller objects are recognised by
+  the class of ``__self__`` (``RacingEnv`` + ``racing_controller``,
+  ``Navigation2DEnv``); their parameters, occupancy grids and the per-solve
+  reference path are read from those live objects, like the reference does;
+* the closures of example/{pendulum,cartpole,mountaincar}.py are all called
+  ``dynamics`` - they are fingerprinted by evaluating them once on a fixed
+  16-row probe batch on the CPU and matching the result against the host
+  formulas below (a few dozen flops at construction, not a solve path);
+* the ``*Model`` descriptor classes of this module resolve to themselves, so
+  the engine is usable without the reference installed;
+* anything else raises ``NotImplementedError``: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _capi
+
+MapSpec = Tuple[torch.Tensor, float, float, float]  # grid[W,H] fp32, cell, origin_x, origin_y
+
+
+class Binding:
+    """What the engine needs to know about one model instance."""
+
+    model_id: int = -1
+    name: str = ""
+    dim_state: int = 0
+    dim_control: int = 0
+
+    def params(self) -> List[float]:
+        return []
+
+    def maps(self) -> List[Optional[MapSpec]]:
+        return []
+
+    def reference_path(self) -> Optional[torch.Tensor]:
+        return None
+
+
+class _Descriptor(Binding):
+    """Base of the stand-alone model descriptors. ``dynamics`` / ``cost_func``
+    exist so that ``MPPI(dynamics=m.dynamics, cost_func=m.cost_func, ...)``
+    reads like the reference's examples; the arithmetic itself runs in the
+    CUDA kernel, never here."""
+
+    def dynamics(self, state, action):  # pragma: no cover - marker only
+        raise NotImplementedError(
+            f"{type(self).__name__}.dynamics is evaluated inside the CUDA rollout kernel; there is no host path")
+
+    def cost_func(self, state, action, info):  # pragma: no cover - marker only
+        raise NotImplementedError(
+            f"{type(self).__name__}.cost_func is evaluated inside the CUDA rollout kernel; there is no host path")
+
+
+class PendulumModel(_Descriptor):
+    """example/pendulum.py:17-47."""
+
+    model_id, name, dim_state, dim_control = _capi.MODEL_PENDULUM, "pendulum", 2, 1
+
+
+class CartpoleModel(_Descriptor):
+    """example/cartpole.py:17-81."""
+
+    model_id, name, dim_state, dim_control = _capi.MODEL_CARTPOLE, "cartpole", 4, 1
+
+
+class MountainCarModel(_Descriptor):
+    """example/mountaincar.py:17-55."""
+
+    model_id, name, dim_state, dim_control = _capi.MODEL_MOUNTAINCAR, "mountaincar", 2, 1
+
+
+class Navigation2DModel(_Descriptor):
+    """src/envs/navigation_2d.py:218-279: unicycle, goal distance + occupancy cost."""
+
+    model_id, name, dim_state, dim_control = _capi.MODEL_NAVIGATION2D, "navigation2d", 3, 2
+
+    def __init__(self, obstacle_grid, cell_size: float, origin: Sequence[float], u_min=(0.0, -1.0),
+                 u_max=(2.0, 1.0), goal=(9.0, 9.0), lim=(-10.0, 10.0, -10.0, 10.0), dt: float = 0.1,
+                 obstacle_weight: float = 10000.0):
+        self.obstacle_grid = torch.as_tensor(obstacle_grid, dtype=torch.float32).contiguous()
+        self.cell_size, self.origin = float(cell_size), (float(origin[0]), float(origin[1]))
+        self.u_min, self.u_max = torch.tensor(u_min, dtype=torch.float32), torch.tensor(u_max, dtype=torch.float32)
+        self.goal, self.lim, self.dt, self.obstacle_weight = tuple(goal), tuple(lim), dt, obstacle_weight
+
+    def params(self):
+        return [self.u_min[0].item(), self.u_max[0].item(), self.u_min[1].item(), self.u_max[1].item(),
+                self.goal[0], self.goal[1], *self.lim, self.dt, self.obstacle_weight]
+
+    def maps(self):
+        return [(self.obstacle_grid, self.cell_size, *self.origin)]
+
+
+class RacingModel(_Descriptor):
+    """Kinematic bicycle (src/envs/racing_env.py:327-372) with the racing
+    controller's cost (example/racing.py:110-159). Set ``reference_path``
+    ([T+1,4]: x, y, yaw, v_target) before every solve (racing.py:73-81)."""
+
+    model_id, name, dim_state, dim_control = _capi.MODEL_RACING, "racing", 4, 2
+
+    def __init__(self, obstacle_grid, lane_grid, cell_size=(0.1, 0.1), origin=((400, 400), (400, 400)),
+                 u_min=(-2.0, -0.25), u_max=(2.0, 0.25), wheelbase: float = 1.0, v_max: float = 8.0,
+                 lim=(-40.0, 40.0, -40.0, 40.0), dt: float = 0.1, Qc=2.0, Ql=3.0, Qv=2.0, Qo=10000.0, Qin=0.01,
+                 Qdin=0.5):
+        self.obstacle_grid = torch.as_tensor(obstacle_grid, dtype=torch.float32).contiguous()
+        self.lane_grid = torch.as_tensor(lane_grid, dtype=torch.float32).contiguous()
+        self.cell_size, self.origin = tuple(cell_size), tuple(tuple(o) for o in origin)
+        self.u_min, self.u_max = torch.tensor(u_min, dtype=torch.float32), torch.tensor(u_max, dtype=torch.float32)
+        self.wheelbase, self.v_max, self.lim, self.dt = wheelbase, v_max, tuple(lim), dt
+        self.Qc, self.Ql, self.Qv, self.Qo, self.Qin, self.Qdin = Qc, Ql, Qv, Qo, Qin, Qdin
+        self.reference_path_tensor: Optional[torch.Tensor] = None
+
+    def params(self):
+        return [self.u_min[0].item(), self.u_max[0].item(), self.u_min[1].item(), self.u_max[1].item(),
+                self.wheelbase, self.v_max, *self.lim, self.dt, self.Qc, self.Ql, self.Qv, self.Qo, self.Qin,
+                self.Qdin]
+
+    def maps(self):
+        return [(self.obstacle_grid, float(self.cell_size[0]), float(self.origin[0][0]), float(self.origin[0][1])),
+                (self.lane_grid, float(self.cell_size[1]), float(self.origin[1][0]), float(self.origin[1][1]))]
+
+    def reference_path(self):
+        return self.reference_path_tensor
+
+
+def racing_reference_path(state: torch.Tensor, path: torch.Tensor, cind: int, horizon: int, v_max: float = 8.0,
+                          DL: float = 0.1, lookahead_distance: float = 3.0,
+                          reference_path_interval: float = 0.85) -> Tuple[torch.Tensor, int]:
+    """Look-ahead reference for the racing cost, the job of
+    ``racing_controller.calc_ref_trajectory`` (example/racing.py:161-218):
+    nearest centre-line point (never behind ``cind``), then one row every
+    ``reference_path_interval`` metres starting ``lookahead_distance`` ahead.
+    Vectorised on whatever device ``path`` lives on; returns ([T+1,4], index)."""
+    d2 = (path[:, 0] - state[0].to(path.device)) ** 2 + (path[:, 1] - state[1].to(path.device)) ** 2
+    ind = max(int(cind), int(torch.argmin(d2).item()))
+    n = path.shape[0]
+    # the reference accumulates `travel += interval` in fp64 and rounds half-to-even per row;
+    # the running sum is kept (81 scalar adds) so that x.5 cases land on the same index
+    travel, dinds = float(lookahead_distance), []
+    for _ in range(horizon + 1):
+        travel += reference_path_interval
+        dinds.append(int(round(travel / DL)))
+    dind = torch.tensor(dinds, dtype=torch.long)
+    idx = ind + dind
+    beyond = idx >= n
+    xref = torch.zeros(horizon + 1, 4, dtype=path.dtype, device=path.device)
+    xref[:, :3] = path[idx.clamp(max=n - 1).to(path.device)]
+    xref[:, 3] = 0.0 if bool(beyond.any()) else v_max
+    return xref, ind
+
+
+# ---- bindings onto the reference's live objects -----------------------------------------
+
+
+def _lim4(obstacle_map) -> List[float]:
+    return [float(obstacle_map.x_lim[0]), float(obstacle_map.x_lim[1]), float(obstacle_map.y_lim[0]),
+            float(obstacle_map.y_lim[1])]
+
+
+def _map_spec(m) -> MapSpec:
+    """(grid, cell, ox, oy) of a reference ObstacleMap / LaneMap
+    (src/envs/obstacle_map_2d.py:76-89,164-166; lane_map_2d.py:55-61,84-88)."""
+    if getattr(m, "_map_torch", None) is None:
+        raise ValueError("cost map has no torch grid yet (ObstacleMap.convert_to_torch() not called)")
+    return (m._map_torch, float(m._cell_size), float(m._cell_map_origin[0]), float(m._cell_map_origin[1]))
+
+
+class _ReferenceRacing(Binding):
+    model_id, name, dim_state, dim_control = _capi.MODEL_RACING, "racing", 4, 2
+
+    def __init__(self, env, controller):
+        self.env, self.ctl = env, controller
+
+    def params(self):
+        e, c = self.env, self.ctl
+        return [float(e.u_min[0]), float(e.u_max[0]), float(e.u_min[1]), float(e.u_max[1]), float(e.L),
+                float(e.V_MAX), *_lim4(e._obstacle_map), 0.1,  # delta_t default, racing_env.py:328
+                float(c.Qc), float(c.Ql), float(c.Qv), float(c.Qo), float(c.Qin), float(c.Qdin)]
+
+    def maps(self):
+        c = self.ctl
+        if c.obstacle_map is None or c.lane_map is None:  # example/racing.py:83-90 raises the same way
+            raise ValueError("reference path, obstacle map, and lane map must be set before calling solve method.")
+        return [_map_spec(c.obstacle_map), _map_spec(c.lane_map)]
+
+    def map_identity(self):
+        return (id(self.ctl.obstacle_map), id(self.ctl.lane_map))
+
+    def reference_path(self):
+        return self.ctl.reference_path
+
+
+class _ReferenceNavigation2D(Binding):
+    model_id, name, dim_state, dim_control = _capi.MODEL_NAVIGATION2D, "navigation2d", 3, 2
+
+    def __init__(self, env):
+        self.env = env
+
+    def params(self):
+        e = self.env
+        return [float(e.u_min[0]), float(e.u_max[0]), float(e.u_min[1]), float(e.u_max[1]), float(e._goal_pos[0]),
+                float(e._goal_pos[1]), *_lim4(e._obstacle_map), 0.1, 10000.0]  # navigation_2d.py:219,277
+
+    def maps(self):
+        return [_map_spec(self.env._obstacle_map)]
+
+    def map_identity(self):
+        return (id(self.env._obstacle_map),)
+
+
+# ---- behavioural fingerprints of the example closures -------------------------------------
+
+
+def _wrap(x):
+    return ((x + torch.pi) % (2 * torch.pi)) - torch.pi
+
+
+def _probe_inputs(ds: int, du: int):
+    g = torch.Generator().manual_seed(1234)
+    state = (torch.rand(16, ds, generator=g) - 0.5) * torch.tensor([2.0, 1.0, 0.3, 2.0][:ds])
+    action = (torch.rand(16, du, generator=g) - 0.5) * 5.0
+    return state, action
+
+
+def _pendulum_host(s, a):
+    u = a[:, 0].clamp(-2, 2)
+    thd = s[:, 1] + (-15.0 * torch.sin(s[:, 0] + torch.pi) + 3.0 * u) * 0.05
+    return torch.stack([s[:, 0] + thd * 0.05, thd.clamp(-8, 8)], 1), _wrap(s[:, 0]) ** 2 + 0.1 * s[:, 1] ** 2
+
+
+def _cartpole_host(s, a):
+    x, xd, th, thd = s.unbind(1)
+    force = torch.where(a[:, 0] >= 0, 10.0, -10.0)
+    ct, st = torch.cos(th), torch.sin(th)
+    temp = (force + 0.05 * thd**2 * st) / 1.1
+    thacc = (9.8 * st - ct * temp) / (0.5 * (4.0 / 3.0 - 0.1 * ct**2 / 1.1))
+    xacc = temp - 0.05 * thacc * ct / 1.1
+    lim = 12 * 2 * math.pi / 360
+    nxt = torch.stack([(x + 0.02 * xd).clamp(-2.4, 2.4), xd + 0.02 * xacc, (th + 0.02 * thd).clamp(-lim, lim),
+                       thd + 0.02 * thacc], 1)
+    return nxt, _wrap(th) ** 2 + 0.1 * thd**2 + 0.1 * x**2
+
+
+def _mountaincar_host(s, a):
+    p, v = s[:, 0], s[:, 1]
+    v2 = (v + a[:, 0].clamp(-1, 1) * 0.0015 - 0.0025 * torch.cos(3 * p)).clamp(-0.07, 0.07)
+    return torch.stack([(p + v2).clamp(-1.2, 0.6), v2], 1), (0.45 - p) ** 2
+
+
+_CLOSURE_TWINS = [
+    (PendulumModel, _pendulum_host),
+    (CartpoleModel, _cartpole_host),
+    (MountainCarModel, _mountaincar_host),
+]
+
+
+def _fingerprint(dynamics: Callable, cost_func: Callable, ds: int, du: int) -> Optional[Binding]:
+    state, action = _probe_inputs(ds, du)
+    try:
+        with torch.no_grad():
+            cost = cost_func(state.clone(), action.clone(), {"prev_action": action.clone(), "t": 0,
+                                                            "prev_state": state.clone(),
+                                                            "initial_state": state.clone()})
+            nxt = dynamics(state.clone(), action.clone())  # clones: mountaincar's closure writes through its input
+    except Exception:
+        return None
+    for cls, twin in _CLOSURE_TWINS:
+        if (cls.dim_state, cls.dim_control) != (ds, du):
+            continue
+        want_next, want_cost = twin(state, action)
+        if (tuple(nxt.shape) == tuple(want_next.shape) and torch.allclose(nxt, want_next, rtol=1e-4, atol=1e-5)
+                and torch.allclose(cost.reshape(-1), want_cost, rtol=1e-4, atol=1e-5)):
+            return cls()
+    return None
+
+
+def resolve(dynamics: Callable, cost_func: Callable, dim_state: int, dim_control: int) -> Binding:
+    """Map the two callables of ``MPPI(...)`` onto a built-in device model."""
+    d_self = getattr(dynamics, "__self__", None)
+    c_self = getattr(cost_func, "__self__", None)
+    binding: Optional[Binding] = None
+    if isinstance(d_self, _Descriptor):
+        if c_self is not d_self:
+            raise ValueError("dynamics and cost_func must come from the same model descriptor")
+        binding = d_self
+    elif d_self is not None and type(d_self).__name__ == "RacingEnv":
+        need = ("Qc", "Ql", "Qv", "Qo", "Qin", "Qdin", "reference_path", "obstacle_map", "lane_map")
+        if c_self is None or not all(hasattr(c_self, a) for a in need):
+            raise NotImplementedError("RacingEnv.dynamics is only supported with racing_controller.cost_function")
+        binding = _ReferenceRacing(d_self, c_self)
+    elif d_self is not None and type(d_self).__name__ == "Navigation2DEnv":
+        if c_self is not d_self:
+            raise NotImplementedError("Navigation2DEnv.dynamics is only supported with Navigation2DEnv.cost_function")
+        binding = _ReferenceNavigation2D(d_self)
+    else:
+        binding = _fingerprint(dynamics, cost_func, dim_state, dim_control)
+    if binding is None:
+        raise NotImplementedError(
+            "dynamics/cost_func do not match a built-in device model (pendulum, cartpole, mountaincar, "
+            "navigation2d, racing). mppi_playground_b200 runs the rollout in a CUDA kernel and has no CPU "
+            "fallback for arbitrary Python callables.")
+    if (binding.dim_state, binding.dim_control) != (dim_state, dim_control):
+        raise ValueError(f"model {binding.name} has dim_state={binding.dim_state}, dim_control={binding.dim_control};"
+                         f" got {dim_state}/{dim_control}")
+    return binding

@@ -1,0 +1,458 @@
+"""``MPPI`` - drop-in for ``pi_mpc.mppi.MPPI`` of kohonda/mppi_playground.
+
+Same constructor keywords, defaults, ``forward`` / ``__call__`` / ``reset`` /
+``get_top_samples`` / ``get_samples_from_posterior`` surface and error
+behaviour as the reference class (src/pi_mpc/mppi.py:16-620); the solve itself
+is one launch of the sm_100a rollout kernel in libmppi_b200.so, reached
+through the C ABI in include/mppi_b200.h. torch is used for device memory and
+streams only.
+
+Differences a caller can observe (all documented in DESIGN.md):
+  * no CPU fallback: the reference silently drops to CPU when CUDA is missing
+    (mppi.py:102-105); this class raises instead;
+  * ``dynamics`` / ``cost_func`` must resolve to a built-in device model
+    (``mppi_playground_b200.models.resolve``); ``info`` is accepted and
+    ignored (the built-in costs take what they need from the model object);
+  * the sampler is the engine's counter-based Philox, not torch's global
+    generator, so native-mode noise differs from the reference's draw by
+    draw; ``forward(state, noise=...)`` injects a reference noise tensor;
+  * ``_state_seq_batch`` is not materialised; ``get_top_samples`` re-rolls.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Dict, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _capi, models
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class MPPI(nn.Module):
+    """Model Predictive Path Integral solver (Williams et al., T-RO 2017) on B200."""
+
+    def __init__(
+        self,
+        horizon: int,
+        num_samples: int,
+        dim_state: int,
+        dim_control: int,
+        dynamics: Callable[[torch.Tensor, torch.Tensor], torch.Tensor],
+        cost_func: Callable[[torch.Tensor, torch.Tensor, Dict], torch.Tensor],
+        u_min: torch.Tensor,
+        u_max: torch.Tensor,
+        sigmas: torch.Tensor,
+        lambda_,
+        lbps_delta: float = 0.01,
+        essps_target_ess: Optional[float] = None,
+        lambda_min: float = 0.01,
+        lambda_max: float = 10.0,
+        exploration: float = 0.0,
+        use_sg_filter: bool = False,
+        sg_window_size: int = 5,
+        sg_poly_order: int = 3,
+        device=torch.device("cuda"),
+        dtype=torch.float32,
+        seed: int = 42,
+        *,
+        shard: Optional[Tuple[int, int]] = None,
+        process_group=None,
+        block_size: int = 0,
+    ) -> None:
+        """Arguments up to ``seed`` are the reference's (mppi.py:24-47).
+
+        Keyword-only extensions: ``shard=(rank, world)`` / ``process_group``
+        split the K samples over one process per GPU (``num_samples`` stays the
+        GLOBAL count); ``block_size`` overrides the launch geometry.
+        """
+        super().__init__()
+        u_min, u_max, sigmas = (torch.as_tensor(x) for x in (u_min, u_max, sigmas))
+        assert u_min.shape == (dim_control,)  # mppi.py:96-98
+        assert u_max.shape == (dim_control,)
+        assert sigmas.shape == (dim_control,)
+        if not torch.cuda.is_available():
+            raise RuntimeError("mppi_playground_b200.MPPI needs a CUDA device (B200, sm_100a); there is no CPU "
+                               "fallback - the reference's own pi_mpc.MPPI is the CPU implementation")
+        if dtype != torch.float32:
+            raise NotImplementedError("the device models are fp32, like the reference's default dtype")
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError(f"device={device}: the engine only runs on CUDA devices")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self._device, self._dtype = device, dtype
+        self._lib = _capi.load()
+
+        self._horizon, self._num_samples = int(horizon), int(num_samples)
+        self._dim_state, self._dim_control = int(dim_state), int(dim_control)
+        self._dynamics, self._cost_func = dynamics, cost_func
+        self._u_min = u_min.clone().detach().to(device, dtype)  # mppi.py:115-117
+        self._u_max = u_max.clone().detach().to(device, dtype)
+        self._sigmas = sigmas.clone().detach().to(device, dtype)
+        self._exploration = exploration
+        self._use_sg_filter, self._sg_window_size, self._sg_poly_order = use_sg_filter, sg_window_size, sg_poly_order
+        self._lbps_delta = lbps_delta
+        self._lambda_min, self._lambda_max = lambda_min, lambda_max
+
+        # lambda mode dispatch, mppi.py:183-210
+        if lambda_ == "MPO":
+            self._auto_lambda, mode, lam0 = "MPO", _capi.LAMBDA_MPO, 1.0
+        elif lambda_ == "LBPS":
+            self._auto_lambda, mode, lam0 = "LBPS", _capi.LAMBDA_LBPS, 1.0
+        elif lambda_ == "ESSPS":
+            self._auto_lambda, mode, lam0 = "ESSPS", _capi.LAMBDA_ESSPS, 1.0
+        elif isinstance(lambda_, float):
+            self._auto_lambda, mode, lam0 = None, _capi.LAMBDA_FIXED, lambda_
+        else:
+            raise ValueError("lambda_ must be 'MPO', 'LBPS', 'ESSPS', or a float value.")
+        self._lambda_init = lambda_
+
+        self._binding = models.resolve(dynamics, cost_func, self._dim_state, self._dim_control)
+
+        # sample sharding (one process per GPU)
+        self._pg = process_group
+        if shard is None and process_group is not None:
+            import torch.distributed as dist
+
+            shard = (dist.get_rank(process_group), dist.get_world_size(process_group))
+        self._rank, self._world = shard if shard is not None else (0, 1)
+        lo, hi = shard_bounds(self._num_samples, self._world, self._rank)
+        self._shard_lo, self._local_samples = lo, hi - lo
+        self._essps_target_ess = essps_target_ess if essps_target_ess is not None else num_samples / 10
+
+        cfg = _capi.MppiConfig()
+        cfg.abi_version = _capi.ABI_VERSION
+        cfg.model = self._binding.model_id
+        cfg.horizon, cfg.num_samples = self._horizon, self._local_samples
+        cfg.dim_state, cfg.dim_control = self._dim_state, self._dim_control
+        for d in range(self._dim_control):
+            cfg.u_min[d], cfg.u_max[d], cfg.sigmas[d] = float(u_min[d]), float(u_max[d]), float(sigmas[d])
+        cfg.lambda_mode, cfg.lambda_ = mode, float(lam0)
+        cfg.lbps_delta, cfg.essps_target_ess = float(lbps_delta), float(self._essps_target_ess)
+        cfg.lambda_min, cfg.lambda_max = float(lambda_min), float(lambda_max)
+        cfg.exploration = float(exploration)
+        cfg.use_sg_filter, cfg.sg_window_size, cfg.sg_poly_order = int(bool(use_sg_filter)), sg_window_size, sg_poly_order
+        # SG coefficients exactly as the reference forms them (fp32 pinv of the Vandermonde matrix)
+        self._coeffs = self._savitzky_golay_coeffs(sg_window_size, sg_poly_order)
+        if sg_window_size <= _capi.MAX_SG:
+            cfg.sg_coeffs_given = 1
+            for i, c in enumerate(self._coeffs.tolist()):
+                cfg.sg_coeffs[i] = c
+        cfg.seed, cfg.device = int(seed) & (2**64 - 1), device.index
+        cfg.sample_offset, cfg.total_samples = lo, self._num_samples
+        p = self._binding.params()
+        cfg.num_model_params = len(p)
+        for i, v in enumerate(p):
+            cfg.model_params[i] = float(v)
+        cfg.block_size = block_size
+        self._params_cache = list(p)
+        h = C.c_void_p()
+        with torch.cuda.device(device):
+            _capi.check(self._lib.mppi_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self._map_identity = None
+        self._bind_maps(required=False)
+        self._noise_keepalive = None
+        self._gathered = None
+
+    # ------------------------------------------------------------------ plumbing
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self._lib.mppi_destroy(h)
+            except Exception:
+                pass
+
+    def _bind_maps(self, required: bool) -> None:
+        """(Re)upload the occupancy grids when the model's map objects appear or change
+        (example/racing.py:227 sets them after the solver is constructed)."""
+        ident_fn = getattr(self._binding, "map_identity", None)
+        ident = ident_fn() if ident_fn else "static"
+        if ident == self._map_identity:
+            return
+        try:
+            specs = self._binding.maps()
+        except ValueError:
+            if required:
+                raise
+            return
+        for slot, (grid, cell, ox, oy) in enumerate(specs):
+            g = grid.detach().to(torch.float32).contiguous()
+            on_dev = int(g.is_cuda)
+            if g.is_cuda and g.device != self._device:
+                g, on_dev = g.to(self._device), 1
+            with torch.cuda.device(self._device):
+                _capi.check(self._lib.mppi_set_map(self._h, slot, g.data_ptr(), on_dev, g.shape[0], g.shape[1],
+                                                   float(cell), float(ox), float(oy)))
+        self._map_identity = ident
+
+    def _refresh_params(self) -> None:
+        p = self._binding.params()
+        if p != self._params_cache:
+            arr = (C.c_float * len(p))(*p)
+            _capi.check(self._lib.mppi_set_model_params(self._h, arr, len(p)))
+            self._params_cache = list(p)
+
+    def _device_state(self, state) -> torch.Tensor:
+        assert tuple(state.shape) == (self._dim_state,)  # mppi.py:247
+        if not torch.is_tensor(state):
+            return torch.tensor(np.asarray(state), device=self._device, dtype=self._dtype)  # mppi.py:249-250
+        return state.detach().to(self._device, self._dtype).contiguous()
+
+    def _device_refpath(self) -> Optional[torch.Tensor]:
+        if self._binding.model_id != _capi.MODEL_RACING:
+            return None
+        ref = self._binding.reference_path()
+        if ref is None:
+            raise ValueError("reference path, obstacle map, and lane map must be set before calling solve method.")
+        ref = torch.as_tensor(ref)
+        if tuple(ref.shape) != (self._horizon + 1, 4):
+            raise ValueError(f"reference_path must be [{self._horizon + 1}, 4], got {tuple(ref.shape)}")
+        return ref.detach().to(self._device, torch.float32).contiguous()
+
+    # ------------------------------------------------------------------ solve
+    def forward(self, state, info: Dict = {}, *, noise: Optional[torch.Tensor] = None):
+        """One MPPI solve (mppi.py:223-460).
+
+        Returns ``(action_seq [T, du], state_seq [1, T+1, ds])`` on the solver's device.
+        ``noise`` ([K,T,du], sigma already applied - what the reference keeps in
+        ``_action_noises``) replaces the in-kernel sampler for parity tests.
+        """
+        st = self._device_state(state)
+        self._bind_maps(required=True)
+        self._refresh_params()
+        ref = self._device_refpath()
+        T, du, ds = self._horizon, self._dim_control, self._dim_state
+        if noise is not None:
+            noise = torch.as_tensor(noise).detach().to(self._device, torch.float32).contiguous()
+            lo = self._shard_lo
+            if tuple(noise.shape) == (self._num_samples, T, du) and self._world > 1:
+                noise = noise[lo:lo + self._local_samples].contiguous()
+            assert tuple(noise.shape) == (self._local_samples, T, du)
+        self._noise_keepalive = (noise, st, ref)
+        action = torch.empty(T, du, device=self._device, dtype=torch.float32)
+        states = torch.empty(T + 1, ds, device=self._device, dtype=torch.float32)
+        s = _stream_ptr(self._device)
+        if self._world == 1:
+            _capi.check(self._lib.mppi_solve(self._h, st.data_ptr(), _ptr(ref), _ptr(noise), action.data_ptr(),
+                                             states.data_ptr(), s))
+        else:
+            self._sharded_solve(st, ref, noise, action, states, s)
+        return action, states.view(1, T + 1, ds)
+
+    def _sharded_solve(self, st, ref, noise, action, states, s) -> None:
+        """K split over ranks: roll the shard, exchange the shard partials
+        ((2 + T*du)-ish floats per rank), finish redundantly on every rank."""
+        import torch.distributed as dist
+
+        lib, h = self._lib, self._h
+        _capi.check(lib.mppi_shard_rollout(h, st.data_ptr(), _ptr(ref), _ptr(noise), s))
+        if self._auto_lambda in ("LBPS", "ESSPS"):
+            costs = self._wrap_costs()
+            all_costs = gather_shards(costs, self._num_samples, self._world, self._pg)
+            _capi.check(lib.mppi_shard_lambda(h, all_costs.data_ptr(), s))
+        part = self._wrap_partial()
+        gathered = torch.empty(self._world * part.numel(), device=self._device, dtype=torch.float32)
+        dist.all_gather_into_tensor(gathered, part, group=self._pg)
+        self._gathered = gathered
+        _capi.check(lib.mppi_shard_finish(h, gathered.data_ptr(), self._world, st.data_ptr(), action.data_ptr(),
+                                          states.data_ptr(), s))
+
+    def _wrap(self, ptr: int, n: int) -> torch.Tensor:
+        return wrap_device_memory(ptr, n, self._device)
+
+    def _wrap_costs(self) -> torch.Tensor:
+        p = C.c_void_p()
+        _capi.check(self._lib.mppi_costs_ptr(self._h, C.byref(p)))
+        return self._wrap(p.value, self._local_samples)
+
+    def _wrap_partial(self) -> torch.Tensor:
+        p = C.c_void_p()
+        _capi.check(self._lib.mppi_partial_ptr(self._h, C.byref(p)))
+        return self._wrap(p.value, self._lib.mppi_partial_floats(self._h))
+
+    def solve_host(self, state: np.ndarray, reference_path: Optional[np.ndarray] = None):
+        """End-to-end solve with HOST buffers through ``mppi_solve_host`` (H2D of the
+        inputs, the solve, D2H of both outputs, synchronised). numpy in, numpy out."""
+        self._bind_maps(required=True)
+        self._refresh_params()
+        state = np.ascontiguousarray(state, dtype=np.float32)
+        assert state.shape == (self._dim_state,)
+        ref_p = None
+        if self._binding.model_id == _capi.MODEL_RACING:
+            if reference_path is None:
+                r = self._binding.reference_path()
+                reference_path = None if r is None else torch.as_tensor(r).detach().cpu().numpy()
+            if reference_path is None:
+                raise ValueError("reference path must be set before calling solve method.")
+            reference_path = np.ascontiguousarray(reference_path, dtype=np.float32)
+            assert reference_path.shape == (self._horizon + 1, 4)
+            ref_p = reference_path.ctypes.data
+        action = np.empty((self._horizon, self._dim_control), dtype=np.float32)
+        states = np.empty((1, self._horizon + 1, self._dim_state), dtype=np.float32)
+        _capi.check(self._lib.mppi_solve_host(self._h, state.ctypes.data, ref_p, action.ctypes.data,
+                                              states.ctypes.data))
+        return action, states
+
+    def reset(self):
+        """Zero the warm start and the SG history (mppi.py:212-221)."""
+        _capi.check(self._lib.mppi_reset(self._h, _stream_ptr(self._device)))
+
+    # ------------------------------------------------------------------ inspection
+    def get_top_samples(self, num_samples: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Highest-weight samples of the last solve, weight-descending (mppi.py:462-487):
+        ``([n, T+1, ds], [n])``. Re-rolled on demand instead of stored."""
+        assert num_samples <= self._num_samples
+        if self._world > 1:
+            raise NotImplementedError("get_top_samples on a sharded solver returns are not merged across ranks yet")
+        traj = torch.empty(num_samples, self._horizon + 1, self._dim_state, device=self._device)
+        w = torch.empty(num_samples, device=self._device)
+        _capi.check(self._lib.mppi_top_samples(self._h, num_samples, traj.data_ptr(), w.data_ptr(),
+                                               _stream_ptr(self._device)))
+        return traj, w
+
+    def get_samples_from_posterior(self, optimal_solution: torch.Tensor, state: torch.Tensor, num_samples: int):
+        """mppi.py:489-506: sample action sequences from N(optimal_solution, diag sigma^2)
+        and roll them out. Returns ``(samples [n,T,du], states [n,T+1,ds])``."""
+        assert num_samples <= self._num_samples
+        st = self._device_state(state)
+        mean = optimal_solution.detach().to(self._device, torch.float32)
+        eps = torch.randn(num_samples, self._horizon, self._dim_control, device=self._device)
+        samples = (mean + eps * self._sigmas).contiguous()
+        traj = torch.empty(num_samples, self._horizon + 1, self._dim_state, device=self._device)
+        _capi.check(self._lib.mppi_rollout_actions(self._h, st.data_ptr(), samples.data_ptr(), num_samples,
+                                                   traj.data_ptr(), _stream_ptr(self._device)))
+        return samples, traj
+
+    @property
+    def _weights(self) -> torch.Tensor:
+        """softmax(-costs / lambda) of the last solve (mppi.py:376), this rank's shard."""
+        w = torch.empty(self._local_samples, device=self._device)
+        _capi.check(self._lib.mppi_weights(self._h, w.data_ptr(), _stream_ptr(self._device)))
+        return w
+
+    @property
+    def _costs(self) -> torch.Tensor:
+        return self._wrap_costs().clone()
+
+    def _lambdas(self) -> Tuple[float, float]:
+        used, nxt = C.c_double(), C.c_double()
+        _capi.check(self._lib.mppi_get_lambda(self._h, C.byref(used), C.byref(nxt), _stream_ptr(self._device)))
+        return used.value, nxt.value
+
+    @property
+    def _lambda(self) -> float:
+        """Temperature the next solve starts from (the reference's ``_lambda`` after ``forward``)."""
+        if self._auto_lambda is None:
+            return self._lambda_init
+        used, nxt = self._lambdas()
+        return nxt if self._auto_lambda == "MPO" else used
+
+    @property
+    def _previous_action_seq(self) -> torch.Tensor:
+        out = torch.empty(self._horizon, self._dim_control, device=self._device)
+        _capi.check(self._lib.mppi_get_carry(self._h, out.data_ptr(), None, _stream_ptr(self._device)))
+        return out
+
+    @_previous_action_seq.setter
+    def _previous_action_seq(self, value: torch.Tensor) -> None:
+        v = value.detach().to(self._device, torch.float32).contiguous()
+        assert tuple(v.shape) == (self._horizon, self._dim_control)
+        _capi.check(self._lib.mppi_set_carry(self._h, v.data_ptr(), None, _stream_ptr(self._device)))
+        torch.cuda.current_stream(self._device).synchronize()
+
+    @property
+    def _actions_history_for_sg(self) -> torch.Tensor:
+        out = torch.empty(self._horizon - 1, self._dim_control, device=self._device)
+        _capi.check(self._lib.mppi_get_carry(self._h, None, out.data_ptr(), _stream_ptr(self._device)))
+        return out
+
+    @_actions_history_for_sg.setter
+    def _actions_history_for_sg(self, value: torch.Tensor) -> None:
+        v = value.detach().to(self._device, torch.float32).contiguous()
+        assert tuple(v.shape) == (self._horizon - 1, self._dim_control)
+        _capi.check(self._lib.mppi_set_carry(self._h, None, v.data_ptr(), _stream_ptr(self._device)))
+        torch.cuda.current_stream(self._device).synchronize()
+
+    def sampler_noise(self, solve_index: Optional[int] = None) -> torch.Tensor:
+        """sigma*eps the in-kernel sampler uses for solve ``solve_index`` (default: the
+        next solve), [K_local, T, du] - so a test can hand the oracle the same noise."""
+        idx = self._lib.mppi_solve_index(self._h) if solve_index is None else solve_index
+        out = torch.empty(self._local_samples, self._horizon, self._dim_control, device=self._device)
+        _capi.check(self._lib.mppi_sample_noise(self._h, idx, out.data_ptr(), _stream_ptr(self._device)))
+        return out
+
+    def launch_info(self) -> Dict[str, int]:
+        g, b, s = C.c_int32(), C.c_int32(), C.c_int32()
+        _capi.check(self._lib.mppi_launch_info(self._h, C.byref(g), C.byref(b), C.byref(s)))
+        return {"grid": g.value, "block": b.value, "smem_bytes": s.value,
+                "launches_last_solve": self._lib.mppi_last_launch_count(self._h)}
+
+    def kernel_timing(self, enable: bool) -> None:
+        _capi.check(self._lib.mppi_kernel_timing(self._h, int(enable)))
+
+    def kernel_time_ms(self) -> Tuple[float, int]:
+        ms, n = C.c_double(), C.c_int32()
+        _capi.check(self._lib.mppi_kernel_time_ms(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    # ------------------------------------------------------------------ reference helpers kept verbatim in behaviour
+    def _savitzky_golay_coeffs(self, window_size: int, poly_order: int) -> torch.Tensor:
+        """First row of pinv(vander(-h..h)) in fp32 (mppi.py:568-596), on the host."""
+        if window_size % 2 == 0 or window_size <= poly_order:
+            raise ValueError("window_size must be odd and greater than poly_order.")
+        half = (window_size - 1) // 2
+        idx = torch.arange(-half, half + 1, dtype=torch.float32)
+        return torch.linalg.pinv(torch.vander(idx, N=poly_order + 1, increasing=True))[0]
+
+
+# ---------------------------------------------------------------------- sharding helpers (host logic, CPU-testable)
+
+
+def shard_bounds(num_samples: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous global sample ids [lo, hi) owned by ``rank``; sizes differ by at most 1."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
+    base, rem = divmod(num_samples, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_shards(local: torch.Tensor, total: int, world: int, group=None) -> torch.Tensor:
+    """all-gather of per-rank vectors whose lengths follow ``shard_bounds`` (differ by <= 1)."""
+    import torch.distributed as dist
+
+    sizes = [shard_bounds(total, world, r)[1] - shard_bounds(total, world, r)[0] for r in range(world)]
+    width = max(sizes)
+    padded = local.new_zeros(width)
+    padded[: local.numel()] = local
+    buf = local.new_empty(world * width)
+    if hasattr(dist, "all_gather_into_tensor") and local.is_cuda:
+        dist.all_gather_into_tensor(buf, padded, group=group)
+    else:
+        chunks = [local.new_empty(width) for _ in range(world)]
+        dist.all_gather(chunks, padded, group=group)
+        buf = torch.cat(chunks)
+    return torch.cat([buf[r * width: r * width + sizes[r]] for r in range(world)]).contiguous()
+
+
+class _CudaArrayView:
+    """Minimal __cuda_array_interface__ carrier so torch can alias engine-owned memory."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def wrap_device_memory(ptr: int, n: int, device: torch.device) -> torch.Tensor:
+    return torch.as_tensor(_CudaArrayView(ptr, n), device=device)

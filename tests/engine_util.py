@@ -1,0 +1,89 @@
+"""Helpers shared by the GPU tests: build engine solvers from golden configs."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+import mppi_playground_b200 as eng
+from oracle import fixtures as fx
+
+
+def engine_model(name: str):
+    if name == "pendulum":
+        return eng.PendulumModel()
+    if name == "cartpole":
+        return eng.CartpoleModel()
+    if name == "mountaincar":
+        return eng.MountainCarModel()
+    if name == "navigation2d":
+        e = fx.load_env_navigation2d()
+        return eng.Navigation2DModel(e.obstacle, e.cell, e.origin, u_min=e.u_min, u_max=e.u_max, goal=e.goal, lim=e.lim)
+    if name == "racing":
+        e = fx.load_env_racing()
+        q = e.Q
+        return eng.RacingModel(e.obstacle, e.lane, cell_size=e.cell, origin=e.origin, u_min=e.u_min, u_max=e.u_max,
+                               wheelbase=e.wheelbase, v_max=e.v_max, lim=e.lim, Qc=q[0], Ql=q[1], Qv=q[2], Qo=q[3],
+                               Qin=q[4], Qdin=q[5])
+    raise KeyError(name)
+
+
+def bounds(cfg: dict, model):
+    if "u_min" in cfg:
+        return torch.tensor(cfg["u_min"]), torch.tensor(cfg["u_max"])
+    return model.u_min.clone(), model.u_max.clone()
+
+
+def build_engine(cfg: dict, **overrides):
+    """(model descriptor, MPPI) for a golden-style cfg dict."""
+    model = engine_model(cfg["model"])
+    u_min, u_max = bounds(cfg, model)
+    kw = fx.solver_kwargs(cfg)
+    kw.update(overrides)
+    solver = eng.MPPI(dim_state=model.dim_state, dim_control=model.dim_control, dynamics=model.dynamics,
+                      cost_func=model.cost_func, u_min=u_min, u_max=u_max, sigmas=torch.tensor(cfg["sigmas"]), **kw)
+    return model, solver
+
+
+def build_oracle(cfg: dict, **overrides):
+    from oracle import mppi_oracle as mo
+
+    model = fx.oracle_model(cfg["model"])
+    u_min, u_max = (cfg["u_min"], cfg["u_max"]) if "u_min" in cfg else (model.u_min.tolist(), model.u_max.tolist())
+    kw = fx.solver_kwargs(cfg)
+    kw.update(overrides)
+    solver = mo.OracleMPPI(dim_state=model.dim_state, dim_control=model.dim_control, dynamics=model.dynamics,
+                           cost_func=model.cost, u_min=u_min, u_max=u_max, sigmas=cfg["sigmas"], **kw)
+    return model, solver
+
+
+class ParityStats:
+    """Differences between an engine solve and the oracle / golden solve."""
+
+    def __init__(self, costs, costs_ref, action, action_ref, states, states_ref, lam, lam_ref):
+        costs, costs_ref = np.asarray(costs, np.float64), np.asarray(costs_ref, np.float64)
+        rel = np.abs(costs - costs_ref) / (1.0 + np.abs(costs_ref))
+        self.cost_flip_frac = float(np.mean(np.abs(costs - costs_ref) > 1.0))  # occupancy cell flips (10000 each)
+        ok = np.abs(costs - costs_ref) <= 1.0
+        self.cost_rel_max = float(rel[ok].max()) if ok.any() else 0.0
+        self.action_err = float(np.max(np.abs(np.asarray(action) - np.asarray(action_ref))))
+        self.state_err = float(np.max(np.abs(np.asarray(states) - np.asarray(states_ref))))
+        self.lam_rel = abs(lam - lam_ref) / abs(lam_ref)
+
+    def __repr__(self):
+        return (f"cost_rel_max={self.cost_rel_max:.2e} flips={self.cost_flip_frac:.2e} "
+                f"action={self.action_err:.2e} state={self.state_err:.2e} lam_rel={self.lam_rel:.2e}")
+
+
+# fp32 tolerances of the parity bar (see DESIGN.md "parity"): the engine and the
+# reference's CPU path differ by libm ulps (CUDA sinf/cosf/tanf/expf vs SLEEF) and
+# by summation order; occupancy costs are discontinuous, so a rolled-out position
+# that lands within an ulp of a cell edge may flip one 10000-cost cell.
+TOL = dict(cost_rel=2e-4, flip_frac=4e-3, action=2e-3, state=5e-3, lam_rel=2e-3)
+
+
+def assert_parity(st: ParityStats, tol=TOL, smooth=False):
+    assert st.cost_rel_max <= tol["cost_rel"], st
+    assert st.cost_flip_frac <= (0.0 if smooth else tol["flip_frac"]), st
+    assert st.action_err <= tol["action"], st
+    assert st.state_err <= tol["state"], st
+    assert st.lam_rel <= tol["lam_rel"], st
