@@ -187,6 +187,12 @@ int mppi_prev_action_ptr(MppiHandle* h, const float** d_prev_action_seq);
 int32_t mppi_last_launch_count(const MppiHandle* h);
 /* Launch geometry picked for the rollout kernel. */
 int mppi_launch_info(const MppiHandle* h, int32_t* grid, int32_t* block, int32_t* smem_bytes);
+/* How the cell index x / cell_size of map `slot` is evaluated: fast_division = 1 when the
+ * 3-instruction exact sequence was proven bit-identical to the IEEE division for this cell size
+ * by an exhaustive device check over all 2^32 inputs (mismatches = 0), else the true division is
+ * used. model_flags: bit0 both racing grids share one geometry, bit1 unit wheelbase. */
+int mppi_map_info(const MppiHandle* h, int32_t slot, int32_t* fast_division, uint64_t* mismatches,
+                  int32_t* model_flags);
 /* Time the dominant (rollout) kernel of subsequent solves with CUDA events on
  * the launching stream: enable with 1, read back the mean/launch count with
  * mppi_kernel_time_ms (which synchronises the events). */

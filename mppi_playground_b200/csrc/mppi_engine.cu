@@ -46,15 +46,16 @@ constexpr unsigned kMaxSmem = 227 * 1024;
 struct ModelInfo {
   int ds, du, maps, n_params;
   bool refpath;
+  int tail_per_step;
 };
 ModelInfo model_info(int model) {
   switch (model) {
-    case MPPI_MODEL_PENDULUM: return {Pendulum::DS, Pendulum::DU, 0, 0, false};
-    case MPPI_MODEL_CARTPOLE: return {Cartpole::DS, Cartpole::DU, 0, 0, false};
-    case MPPI_MODEL_MOUNTAINCAR: return {MountainCar::DS, MountainCar::DU, 0, 0, false};
-    case MPPI_MODEL_NAVIGATION2D: return {Navigation2D::DS, Navigation2D::DU, 1, MPPI_NAV2D_NUM_PARAMS, false};
-    case MPPI_MODEL_RACING: return {Racing::DS, Racing::DU, 2, MPPI_RACING_NUM_PARAMS, true};
-    default: return {0, 0, 0, 0, false};
+    case MPPI_MODEL_PENDULUM: return {Pendulum::DS, Pendulum::DU, 0, 0, false, 0};
+    case MPPI_MODEL_CARTPOLE: return {Cartpole::DS, Cartpole::DU, 0, 0, false, 0};
+    case MPPI_MODEL_MOUNTAINCAR: return {MountainCar::DS, MountainCar::DU, 0, 0, false, 0};
+    case MPPI_MODEL_NAVIGATION2D: return {Navigation2D::DS, Navigation2D::DU, 1, MPPI_NAV2D_NUM_PARAMS, false, tail_per_step<Navigation2D>()};
+    case MPPI_MODEL_RACING: return {Racing::DS, Racing::DU, 2, MPPI_RACING_NUM_PARAMS, true, tail_per_step<Racing>()};
+    default: return {0, 0, 0, 0, false, 0};
   }
 }
 
@@ -125,6 +126,7 @@ struct MppiHandle {
   unsigned int* d_counter = nullptr;
   uint32_t* d_map[2] = {nullptr, nullptr};
   bool map_set[2] = {false, false};
+  unsigned long long fastdiv_mismatches[2] = {0, 0};
   // host-call staging (mppi_solve_host)
   float* h_pinned = nullptr;  // state | refpath | action_seq | state_seq
   float* d_stage = nullptr;
@@ -157,7 +159,8 @@ int pick_block(const MppiHandle* h, int n_maps, const unsigned* map_bytes, unsig
   double best_t = 1e300;
   const int cands[] = {512, 256, 128, 64};
   for (int bs : cands) {
-    SmemLayout L = make_layout(n_maps, map_bytes, h->cfg.horizon, h->E_pad, pa_bytes, h->mi.refpath, bs / 32);
+    SmemLayout L = make_layout(n_maps, map_bytes, h->cfg.horizon, h->E_pad, pa_bytes, h->mi.refpath, bs / 32,
+                               h->mi.tail_per_step);
     if (L.total > kMaxSmem) continue;
     long long blocks = ((long long)K + bs - 1) / bs;
     int per_sm = std::min<long long>({2048 / bs, (long long)(kMaxSmem / L.total), 65536 / (128LL * bs)});
@@ -219,7 +222,7 @@ int dispatch_solve(MppiHandle* h, const SolveParams& p, int mode, bool inject, c
 
 template <class M>
 int launch_finish(MppiHandle* h, const SolveParams& p, const float* parts, int n, cudaStream_t st) {
-  unsigned sm = finish_scratch_bytes(h->E_pad);
+  unsigned sm = finish_scratch_bytes(h->E_pad, h->cfg.horizon, h->mi.tail_per_step);
   finish_kernel<M><<<1, 256, sm, st>>>(p, parts, n);
   CUDA_TRY(cudaGetLastError());
   h->last_launches++;
@@ -297,12 +300,26 @@ int launch_rollout_actions(MppiHandle* h, const SolveParams& p, const float* act
   return MPPI_OK;
 }
 
+void refresh_model_flags(MppiHandle* h) {
+  SolveParams& b = h->base;
+  int flags = 0;
+  if (h->cfg.model == MPPI_MODEL_RACING) {
+    if (h->map_set[0] && h->map_set[1] && b.map_W[0] == b.map_W[1] && b.map_H[0] == b.map_H[1] &&
+        b.map_cell[0] == b.map_cell[1] && b.map_ox[0] == b.map_ox[1] && b.map_oy[0] == b.map_oy[1] &&
+        b.map_fastdiv[0] == b.map_fastdiv[1])
+      flags |= kFlagSameMapGeometry;
+    if (b.mp.v[4] == 1.0f) flags |= kFlagUnitWheelbase;
+  }
+  b.mp.flags = flags;
+}
+
 void refresh_launch_geometry(MppiHandle* h) {
   unsigned mb[2] = {h->base.map_bytes[0], h->base.map_bytes[1]};
   int bs = h->cfg.block_size > 0 ? h->cfg.block_size : pick_block(h, h->mi.maps, mb, h->base.prev_action_bytes);
   h->block = bs;
   h->grid = (h->cfg.num_samples + bs - 1) / bs;
-  h->smem = make_layout(h->mi.maps, mb, h->cfg.horizon, h->E_pad, h->base.prev_action_bytes, h->mi.refpath, bs / 32)
+  h->smem = make_layout(h->mi.maps, mb, h->cfg.horizon, h->E_pad, h->base.prev_action_bytes, h->mi.refpath, bs / 32,
+                        h->mi.tail_per_step)
                 .total;
 }
 
@@ -418,6 +435,7 @@ int mppi_create(const MppiConfig* cfg, MppiHandle** out) {
     b.sigma[d] = cfg->sigmas[d];
   }
   for (int i = 0; i < mi.n_params; ++i) b.mp.v[i] = cfg->model_params[i];
+  refresh_model_flags(h);
   b.prev_action = h->d_prev_action;
   b.prev_action_bytes = (unsigned)pad16((size_t)h->E_pad * 4);
   b.history = h->d_history;
@@ -493,6 +511,7 @@ int mppi_set_model_params(MppiHandle* h, const float* params, int32_t n) {
   if (!h || (!params && n > 0)) return fail(MPPI_ERR_INVALID, "null argument");
   if (n != h->mi.n_params) return fail(MPPI_ERR_INVALID, "model takes %d parameters, got %d", h->mi.n_params, n);
   for (int i = 0; i < n; ++i) h->base.mp.v[i] = params[i];
+  refresh_model_flags(h);
   return MPPI_OK;
 }
 
@@ -533,9 +552,24 @@ int mppi_set_map(MppiHandle* h, int32_t slot, const float* grid, int32_t on_devi
   b.map_words[slot] = words;
   b.map_bytes[slot] = (unsigned)bytes;
   b.map_cell[slot] = cell;
+  {  // exact fast division by the cell size: prove it for this divisor, or keep the true division
+    const float rcp = (float)(1.0 / (double)cell);
+    unsigned long long* d_bad = nullptr;
+    unsigned long long bad = 1;
+    if (cudaMalloc((void**)&d_bad, 8) == cudaSuccess) {
+      cudaMemset(d_bad, 0, 8);
+      check_fastdiv_kernel<<<148 * 8, 256>>>(cell, rcp, d_bad);
+      if (cudaMemcpy(&bad, d_bad, 8, cudaMemcpyDeviceToHost) != cudaSuccess) bad = 1;
+      cudaFree(d_bad);
+    }
+    b.map_rcp[slot] = rcp;
+    b.map_fastdiv[slot] = (bad == 0) ? 1 : 0;
+    h->fastdiv_mismatches[slot] = bad;
+  }
   b.map_ox[slot] = ox;
   b.map_oy[slot] = oy;
   h->map_set[slot] = true;
+  refresh_model_flags(h);
   refresh_launch_geometry(h);
   if (h->smem > kMaxSmem)
     return fail(MPPI_ERR_UNSUPPORTED, "occupancy maps need %u B of shared memory (> %u)", h->smem, kMaxSmem);
@@ -768,6 +802,14 @@ int mppi_launch_info(const MppiHandle* h, int32_t* grid, int32_t* block, int32_t
   if (grid) *grid = h->grid;
   if (block) *block = h->block;
   if (smem_bytes) *smem_bytes = (int32_t)h->smem;
+  return MPPI_OK;
+}
+
+int mppi_map_info(const MppiHandle* h, int32_t slot, int32_t* fast_division, uint64_t* mismatches, int32_t* model_flags) {
+  if (!h || slot < 0 || slot > 1) return fail(MPPI_ERR_INVALID, "bad argument");
+  if (fast_division) *fast_division = h->base.map_fastdiv[slot];
+  if (mismatches) *mismatches = h->fastdiv_mismatches[slot];
+  if (model_flags) *model_flags = h->base.mp.flags;
   return MPPI_OK;
 }
 

@@ -51,7 +51,8 @@ struct SolveParams {
   const uint32_t* map_bits[2];
   int map_W[2], map_H[2], map_words[2];
   unsigned map_bytes[2];  // padded to 16 B
-  float map_cell[2], map_ox[2], map_oy[2];
+  float map_cell[2], map_rcp[2], map_ox[2], map_oy[2];
+  int map_fastdiv[2];  // (cell, rcp) passed the exhaustive exact-division check
   const float* state;    // [ds]
   const float* refpath;  // [T+1,4] or null
   const float* noise;    // [K,T,du] or null
@@ -85,8 +86,14 @@ struct SmemLayout {
 
 __host__ __device__ inline unsigned align_up(unsigned x, unsigned a) { return (x + a - 1) / a * a; }
 
+// floats of scratch finish_solve needs: N (doubles) | opt | y | scales | Combined | tail rollout
+__host__ __device__ inline unsigned finish_scratch_core(int E_pad, int T, int tail_per_step) {
+  return (unsigned)E_pad * 20 + 256 * 4 + 64 + (unsigned)tail_per_step * (unsigned)(T + 1) * 4;
+}
+
 __host__ __device__ inline SmemLayout make_layout(int n_maps, const unsigned* map_bytes, int T, int E_pad,
-                                                   unsigned prev_action_bytes, bool refpath, int n_warps) {
+                                                   unsigned prev_action_bytes, bool refpath, int n_warps,
+                                                   int tail_per_step) {
   SmemLayout L;
   unsigned o = 16;  // mbarrier
   for (int i = 0; i < 2; ++i) {
@@ -105,7 +112,7 @@ __host__ __device__ inline SmemLayout make_layout(int n_maps, const unsigned* ma
   o = L.warpacc_off;
   {  // per-warp accumulators; the last block reuses the region as finish scratch
     unsigned acc = (unsigned)n_warps * (unsigned)E_pad * 4;
-    unsigned fin = (unsigned)E_pad * 20 + 256 * 4 + 64;
+    unsigned fin = finish_scratch_core(E_pad, T, tail_per_step);
     o += align_up(acc > fin ? acc : fin, 16);
   }
   L.red_off = o;
@@ -255,7 +262,7 @@ __device__ inline void mpo_update(const SolveParams& p, const Combined& c) {
 // smem: opt[E], y[(2T-1)*du] floats supplied by the caller.
 template <class M>
 __device__ inline void finish_solve(const SolveParams& p, const typename M::Ctx& ctx, const Combined& c,
-                                    const double* N, float* opt, float* ybuf) {
+                                    const double* N, float* opt, float* ybuf, float* tail) {
   constexpr int DS = M::DS, DU = M::DU;
   const int tid = threadIdx.x, nt = blockDim.x, T = p.T, E = p.E;
   const int H = (T - 1) * DU;
@@ -289,13 +296,24 @@ __device__ inline void finish_solve(const SolveParams& p, const typename M::Ctx&
   }
   for (int i = tid; i < H; i += nt)  // history = cat(history[1:], opt[0]) (mppi.py:455-458)
     p.history[i] = (i < H - DU) ? ybuf[i + DU] : opt[i - (H - DU)];
-  if (tid == 0) {  // optimal-trajectory rollout (mppi.py:448-449, 508-524)
+  if (tid == 32 % nt) {
+    DeviceScalars* sc = p.sc;
+    sc->lambda_used = sc->lambda;
+    sc->S = c.S;
+    sc->xmax = c.xmax;
+    sc->cmin = c.cmin;
+    sc->cmax = c.cmax;
+    if (p.lambda_mode == kLamMPO) mpo_update(p, c);
+  }
+  if (tid < DS) p.state_snapshot[tid] = p.state[tid];
+  // optimal-trajectory rollout (mppi.py:448-449, 508-524)
+  if constexpr (M::kParallelTail) {
+    __syncthreads();
+    M::rollout_block(ctx, p.state, opt, T, p.state_seq_out, tail);
+  } else if (tid == 0) {
     float s[DS], seen[DS], u[DU];
 #pragma unroll
-    for (int i = 0; i < DS; ++i) {
-      s[i] = p.state[i];
-      p.state_snapshot[i] = s[i];
-    }
+    for (int i = 0; i < DS; ++i) s[i] = p.state[i];
     for (int t = 0; t < T; ++t) {
 #pragma unroll
       for (int d = 0; d < DU; ++d) u[d] = opt[t * DU + d];
@@ -305,15 +323,6 @@ __device__ inline void finish_solve(const SolveParams& p, const typename M::Ctx&
     }
 #pragma unroll
     for (int i = 0; i < DS; ++i) p.state_seq_out[T * DS + i] = s[i];
-  }
-  if (tid == 32 % nt) {
-    DeviceScalars* sc = p.sc;
-    sc->lambda_used = sc->lambda;
-    sc->S = c.S;
-    sc->xmax = c.xmax;
-    sc->cmin = c.cmin;
-    sc->cmax = c.cmax;
-    if (p.lambda_mode == kLamMPO) mpo_update(p, c);
   }
 }
 
@@ -368,13 +377,21 @@ __device__ __forceinline__ float rollout_cost(const SolveParams& p, const typena
   return total + M::cost(ctx, s, zero, pa, T - 1);  // mppi.py:333-336
 }
 
+template <class M>
+__host__ __device__ constexpr int tail_per_step() {
+  if constexpr (M::kParallelTail)
+    return M::kTailScratchPerStep;
+  else
+    return 0;
+}
+
 template <class M, bool kInject, int kMode>
 __global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ SolveParams p) {
   constexpr int DU = M::DU;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
   const SmemLayout L =
-      make_layout(M::kMaps, p.map_bytes, p.T, p.E_pad, p.prev_action_bytes, M::kRefPath, n_warps);
+      make_layout(M::kMaps, p.map_bytes, p.T, p.E_pad, p.prev_action_bytes, M::kRefPath, n_warps, tail_per_step<M>());
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   float* nominal = reinterpret_cast<float*>(smem + L.nominal_off);
   float* warp_acc = reinterpret_cast<float*>(smem + L.warpacc_off);
@@ -412,7 +429,7 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ S
     MapView mv[2];
     for (int i = 0; i < M::kMaps; ++i)
       mv[i] = MapView{reinterpret_cast<const uint32_t*>(smem + L.map_off[i]), p.map_W[i], p.map_H[i], p.map_words[i],
-                      p.map_cell[i], p.map_ox[i], p.map_oy[i]};
+                      ExactDiv{p.map_cell[i], p.map_rcp[i], p.map_fastdiv[i]}, p.map_ox[i], p.map_oy[i]};
     if constexpr (M::kMaps == 1) {
       ctx.map = mv[0];
     } else {
@@ -539,9 +556,10 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ S
   float* ybuf = opt + p.E_pad;
   float* scale_buf = ybuf + 2 * p.E_pad;
   Combined* comb = reinterpret_cast<Combined*>(scale_buf + 256);
+  float* tail = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(comb) + 64);
   combine_partials(p.block_partials, (int)gridDim.x, p.P, p.E, comb, Nbuf, scale_buf, red);
   if (p.n_shards == 1) {
-    finish_solve<M>(p, ctx, *comb, Nbuf, opt, ybuf);
+    finish_solve<M>(p, ctx, *comb, Nbuf, opt, ybuf, tail);
   } else {
     for (int e = tid; e < p.E; e += blockDim.x) p.rank_partial[kPartialHeader + e] = (float)Nbuf[e];
     if (tid == 0) {
@@ -569,15 +587,16 @@ __global__ void __launch_bounds__(256, 1) finish_kernel(const __grid_constant__ 
   float* ybuf = opt + p.E_pad;
   float* scale_buf = ybuf + 2 * p.E_pad;
   Combined* comb = reinterpret_cast<Combined*>(scale_buf + 256);
-  void* red = reinterpret_cast<unsigned char*>(comb) + 64;
+  float* tail = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(comb) + 64);
+  void* red = smem + finish_scratch_core(p.E_pad, p.T, tail_per_step<M>());
   typename M::Ctx ctx{};
   if constexpr (M::kMaps >= 1) ctx.p = &p.mp;
   combine_partials(parts, n, p.P, p.E, comb, Nbuf, scale_buf, red);
-  finish_solve<M>(p, ctx, *comb, Nbuf, opt, ybuf);
+  finish_solve<M>(p, ctx, *comb, Nbuf, opt, ybuf, tail);
 }
 
-__host__ __device__ inline unsigned finish_scratch_bytes(int E_pad) {
-  return (unsigned)E_pad * 8 + (unsigned)E_pad * 4 * 3 + 256 * 4 + 64 + 64 * 8;
+__host__ __device__ inline unsigned finish_scratch_bytes(int E_pad, int T, int tail_per_step) {
+  return finish_scratch_core(E_pad, T, tail_per_step) + 64 * 8;
 }
 
 // ---------------------------------------------------------------------------
@@ -811,6 +830,23 @@ __global__ void weights_kernel(const float* __restrict__ costs, int K, const Dev
 __global__ void iota_kernel(int* out, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = i;
+}
+
+// Exhaustive proof obligation of ExactDiv: count the x (all 2^32 bit patterns) for which the
+// 3-instruction sequence differs from the IEEE quotient x / c.
+__global__ void check_fastdiv_kernel(float c, float r, unsigned long long* mismatches) {
+  unsigned long long bad = 0;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 32); i += stride) {
+    float x = __uint_as_float((unsigned)i);
+    float q = x * r;
+    float fast = fmaf(fmaf(-q, c, x), r, q);
+    float ref = x / c;
+    bool same = (__float_as_uint(fast) == __float_as_uint(ref)) || (isnan(fast) && isnan(ref));
+    bad += same ? 0 : 1;
+  }
+  bad = __reduce_add_sync(kFullMask, (unsigned)bad);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, bad);
 }
 
 __global__ void pack_map_kernel(const float* __restrict__ grid, int W, int H, int words, uint32_t* __restrict__ bits) {

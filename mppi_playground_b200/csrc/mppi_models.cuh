@@ -20,17 +20,39 @@
 
 namespace mppi {
 
+// x / c for a fixed divisor, bit-identical to the IEEE quotient: q0 = x * r with r = RN(1/c), one
+// exact residual (fma) and one correction (fma) - Markstein's sequence, 3 instructions instead of the
+// ~10 + range check of a full division. `fast` is only set after an EXHAUSTIVE device-side comparison
+// against `x / c` over all 2^32 bit patterns of x for this very (c, r) pair (check_fastdiv_kernel,
+// run once in mppi_set_map); otherwise the true division is used.
+struct ExactDiv {
+  float c, r;
+  int fast;
+};
+__device__ __forceinline__ float div_exact(float x, const ExactDiv& d) {
+  if (d.fast) {
+    float q = x * d.r;
+    float rem = fmaf(-q, d.c, x);
+    return fmaf(rem, d.r, q);
+  }
+  return x / d.c;
+}
+
 // Occupancy grid, bit-packed: bit (iy & 31) of word [ix * words + (iy >> 5)].
 struct MapView {
   const uint32_t* bits;
   int W, H, words;
-  float cell, ox, oy;
+  ExactDiv cell;
+  float ox, oy;
 };
 
-// src/envs/obstacle_map_2d.py:168-200 == src/envs/lane_map_2d.py:90-122.
-__device__ __forceinline__ float map_lookup(const MapView& m, float x, float y) {
-  int ix = __float2int_rn(x / m.cell + m.ox);  // :179-180 true division, round half-even, to integer
-  int iy = __float2int_rn(y / m.cell + m.oy);
+// cell index of a world coordinate: round(x / cell + origin) half-to-even, as integer
+// (src/envs/obstacle_map_2d.py:179-180)
+__device__ __forceinline__ int map_cell(float x, const ExactDiv& cell, float origin) {
+  return __float2int_rn(div_exact(x, cell) + origin);
+}
+
+__device__ __forceinline__ float map_value(const MapView& m, int ix, int iy) {
   bool oob = (ix < 0) | (ix >= m.W) | (iy < 0) | (iy >= m.H);  // :183-190
   ix = min(max(ix, 0), m.W - 1);                                // :191-192
   iy = min(max(iy, 0), m.H - 1);
@@ -39,14 +61,22 @@ __device__ __forceinline__ float map_lookup(const MapView& m, float x, float y) 
   return oob ? 1.0f : occ;  // :198
 }
 
+// src/envs/obstacle_map_2d.py:168-200 == src/envs/lane_map_2d.py:90-122.
+__device__ __forceinline__ float map_lookup(const MapView& m, float x, float y) {
+  return map_value(m, map_cell(x, m.cell, m.ox), map_cell(y, m.cell, m.oy));
+}
+
 struct ModelParams {
   float v[32];
+  int flags;  // model specific, set by the host (see kFlag*)
 };
+constexpr int kFlagSameMapGeometry = 1;  // Racing: obstacle and lane grids share W, H, cell, origin
+constexpr int kFlagUnitWheelbase = 2;    // Racing: L == 1.0f, so x / L == x exactly
 
 // ---------------------------------------------------------------------------
 struct Pendulum {  // example/pendulum.py:17-47
   static constexpr int DS = 2, DU = 1, kMaps = 0;
-  static constexpr bool kRefPath = false;
+  static constexpr bool kRefPath = false, kParallelTail = false;
   struct Ctx {};
   __device__ static __forceinline__ void step(const Ctx&, float (&s)[DS], const float (&u)[DU], float (&seen)[DS]) {
     seen[0] = s[0];
@@ -68,7 +98,7 @@ struct Pendulum {  // example/pendulum.py:17-47
 // ---------------------------------------------------------------------------
 struct Cartpole {  // example/cartpole.py:17-81
   static constexpr int DS = 4, DU = 1, kMaps = 0;
-  static constexpr bool kRefPath = false;
+  static constexpr bool kRefPath = false, kParallelTail = false;
   struct Ctx {};
   __device__ static __forceinline__ void step(const Ctx&, float (&s)[DS], const float (&u)[DU], float (&seen)[DS]) {
 #pragma unroll
@@ -99,7 +129,7 @@ struct Cartpole {  // example/cartpole.py:17-81
 // ---------------------------------------------------------------------------
 struct MountainCar {  // example/mountaincar.py:17-55
   static constexpr int DS = 2, DU = 1, kMaps = 0;
-  static constexpr bool kRefPath = false;
+  static constexpr bool kRefPath = false, kParallelTail = false;
   struct Ctx {};
   __device__ static __forceinline__ void step(const Ctx&, float (&s)[DS], const float (&u)[DU], float (&seen)[DS]) {
     float force = clampf(u[0], -1.0f, 1.0f);                          // :32
@@ -121,7 +151,7 @@ struct MountainCar {  // example/mountaincar.py:17-55
 // ---------------------------------------------------------------------------
 struct Navigation2D {  // src/envs/navigation_2d.py:218-279
   static constexpr int DS = 3, DU = 2, kMaps = 1;
-  static constexpr bool kRefPath = false;
+  static constexpr bool kRefPath = false, kParallelTail = true;
   struct Ctx {
     MapView map;
     const ModelParams* p;  // v_min v_max w_min w_max goal_x goal_y x_lo x_hi y_lo y_hi dt w_obst
@@ -149,18 +179,75 @@ struct Navigation2D {  // src/envs/navigation_2d.py:218-279
     float goal = sqrtf(dx * dx + dy * dy);              // :269
     return goal + p[11] * map_lookup(c.map, s[0], s[1]);  // :271-277
   }
+  // Optimal-trajectory rollout by one block (mppi.py:508-524). Same operations on the same values as
+  // T calls of step(); only the schedule differs: the heading chain is the one serial part, the
+  // sin/cos of every stage and the position increments are evaluated by T threads at once.
+  // scratch: 8 * (T + 1) floats.
+  __device__ static void rollout_block(const Ctx& c, const float* state, const float* opt, int T, float* out,
+                                       float* scratch) {
+    const float* p = c.p->v;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    float *wdt = scratch, *ths = wdt + (T + 1), *thw = ths + (T + 1), *dx = thw + (T + 1), *dy = dx + (T + 1),
+          *xs = dy + (T + 1), *ys = xs + (T + 1), *vc = ys + (T + 1);
+    for (int t = tid; t < T; t += nt) {
+      vc[t] = clampf(opt[2 * t], p[0], p[1]);
+      wdt[t] = clampf(opt[2 * t + 1], p[2], p[3]) * p[10];
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float th = state[2];
+      ths[0] = th;
+      for (int t = 0; t < T; ++t) {
+        float w = wrap_angle(th);
+        thw[t] = w;
+        th = wrap_angle(w + wdt[t]);
+        ths[t + 1] = th;
+      }
+    }
+    __syncthreads();
+    for (int t = tid; t < T; t += nt) {
+      float st, ct;
+      sincosf(thw[t], &st, &ct);
+      dx[t] = vc[t] * ct * p[10];
+      dy[t] = vc[t] * st * p[10];
+    }
+    __syncthreads();
+    if (tid == 0 || tid == 32) {
+      const bool isx = tid == 0;
+      float q = isx ? state[0] : state[1];
+      float* qs = isx ? xs : ys;
+      const float* dq = isx ? dx : dy;
+      const float lo = isx ? p[6] : p[8], hi = isx ? p[7] : p[9];
+      qs[0] = q;
+      for (int t = 0; t < T; ++t) {
+        q = clampf(q + dq[t], lo, hi);
+        qs[t + 1] = q;
+      }
+    }
+    __syncthreads();
+    for (int t = tid; t <= T; t += nt) {
+      out[t * DS + 0] = xs[t];
+      out[t * DS + 1] = ys[t];
+      out[t * DS + 2] = ths[t];
+    }
+  }
+  static constexpr int kTailScratchPerStep = 8;
 };
 
 // ---------------------------------------------------------------------------
 struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
   static constexpr int DS = 4, DU = 2, kMaps = 2;
-  static constexpr bool kRefPath = true;
+  static constexpr bool kRefPath = true, kParallelTail = true;
   struct Ctx {
     MapView obstacle, lane;
     const ModelParams* p;  // a_min a_max s_min s_max L v_max x_lo x_hi y_lo y_hi dt Qc Ql Qv Qo Qin Qdin
     const float4* ref;     // per stage t: (x, y, sin yaw, cos yaw) of reference_path[t]
     const float* ref_v;    // per stage t: target speed reference_path[t, 3]
   };
+  __device__ static __forceinline__ float yaw_rate(const ModelParams& mp, float v, float tan_steer) {
+    float r = v * tan_steer;  // racing_env.py:352  v * tan(steer) / L
+    return (mp.flags & kFlagUnitWheelbase) ? r : r / mp.v[4];
+  }
   __device__ static __forceinline__ void step(const Ctx& c, float (&s)[DS], const float (&u)[DU], float (&seen)[DS]) {
     const float* p = c.p->v;
 #pragma unroll
@@ -172,7 +259,7 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
     sincosf(th, &st, &ct);
     float dx = s[3] * ct;  // :349-352
     float dy = s[3] * st;
-    float dth = s[3] * tanf(steer) / p[4];
+    float dth = yaw_rate(*c.p, s[3], tanf(steer));
     float nx = s[0] + dx * p[10];  // :354-357
     float ny = s[1] + dy * p[10];
     float nth = wrap_angle(th + dth * p[10]);
@@ -192,14 +279,85 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
     float path = p[11] * (ec * ec) + p[12] * (el * el);     // :138
     float dv = s[3] - c.ref_v[t];
     float vel = p[13] * (dv * dv);                           // :141-143
-    float occ = map_lookup(c.obstacle, s[0], s[1]);          // :146-150
-    occ = occ + map_lookup(c.lane, s[0], s[1]);
+    float occ;                                               // :146-150
+    if (c.p->flags & kFlagSameMapGeometry) {  // one cell index serves both grids
+      int ix = map_cell(s[0], c.obstacle.cell, c.obstacle.ox), iy = map_cell(s[1], c.obstacle.cell, c.obstacle.oy);
+      occ = map_value(c.obstacle, ix, iy) + map_value(c.lane, ix, iy);
+    } else {
+      occ = map_lookup(c.obstacle, s[0], s[1]);
+      occ = occ + map_lookup(c.lane, s[0], s[1]);
+    }
     occ = p[14] * occ;                                       // :151
     float in = p[15] * (u[0] * u[0] + u[1] * u[1]);          // :154
     float d0 = u[0] - pu[0], d1 = u[1] - pu[1];
     in = in + p[16] * (d0 * d0 + d1 * d1);                   // :155
     return path + vel + occ + in;                            // :157
   }
+  // Optimal-trajectory rollout by one block (mppi.py:508-524): the same operations on the same values
+  // as T calls of step(), rescheduled. Serial parts are only the three cheap recurrences (speed:
+  // add+clamp; heading: two angle wraps; position: add+clamp); tan / sin / cos of all T stages run in
+  // parallel in between. scratch: 11 * (T + 1) floats.
+  __device__ static void rollout_block(const Ctx& c, const float* state, const float* opt, int T, float* out,
+                                       float* scratch) {
+    const float* p = c.p->v;
+    const int tid = threadIdx.x, nt = blockDim.x, S = T + 1;
+    float *adt = scratch, *tn = adt + S, *vs = tn + S, *cdt = vs + S, *ths = cdt + S, *thw = ths + S, *dx = thw + S,
+          *dy = dx + S, *xs = dy + S, *ys = xs + S;
+    for (int t = tid; t < T; t += nt) {
+      adt[t] = clampf(opt[2 * t], p[0], p[1]) * p[10];
+      tn[t] = tanf(clampf(opt[2 * t + 1], p[2], p[3]));
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float v = state[3];
+      vs[0] = v;
+      for (int t = 0; t < T; ++t) {
+        v = clampf(v + adt[t], -p[5], p[5]);
+        vs[t + 1] = v;
+      }
+    }
+    __syncthreads();
+    for (int t = tid; t < T; t += nt) cdt[t] = yaw_rate(*c.p, vs[t], tn[t]) * p[10];
+    __syncthreads();
+    if (tid == 0) {
+      float th = state[2];
+      ths[0] = th;
+      for (int t = 0; t < T; ++t) {
+        float w = wrap_angle(th);
+        thw[t] = w;
+        th = wrap_angle(w + cdt[t]);
+        ths[t + 1] = th;
+      }
+    }
+    __syncthreads();
+    for (int t = tid; t < T; t += nt) {
+      float st, ct;
+      sincosf(thw[t], &st, &ct);
+      dx[t] = vs[t] * ct * p[10];
+      dy[t] = vs[t] * st * p[10];
+    }
+    __syncthreads();
+    if (tid == 0 || tid == 32) {
+      const bool isx = tid == 0;
+      float q = isx ? state[0] : state[1];
+      float* qs = isx ? xs : ys;
+      const float* dq = isx ? dx : dy;
+      const float lo = isx ? p[6] : p[8], hi = isx ? p[7] : p[9];
+      qs[0] = q;
+      for (int t = 0; t < T; ++t) {
+        q = clampf(q + dq[t], lo, hi);
+        qs[t + 1] = q;
+      }
+    }
+    __syncthreads();
+    for (int t = tid; t <= T; t += nt) {
+      out[t * DS + 0] = xs[t];
+      out[t * DS + 1] = ys[t];
+      out[t * DS + 2] = ths[t];
+      out[t * DS + 3] = vs[t];
+    }
+  }
+  static constexpr int kTailScratchPerStep = 11;
 };
 
 }  // namespace mppi

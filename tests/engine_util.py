@@ -78,7 +78,24 @@ class ParityStats:
 # reference's CPU path differ by libm ulps (CUDA sinf/cosf/tanf/expf vs SLEEF) and
 # by summation order; occupancy costs are discontinuous, so a rolled-out position
 # that lands within an ulp of a cell edge may flip one 10000-cost cell.
-TOL = dict(cost_rel=2e-4, flip_frac=4e-3, action=2e-3, state=5e-3, lam_rel=2e-3)
+# Measured on B200 (gpurun_out/parity_report.jsonl, profiles/parity_r01.md): cost_rel <= 1.4e-6,
+# action <= 4e-5, state <= 6e-6, lambda (LBPS / ESSPS) <= 1e-5; the bars below are ~10x that.
+TOL = dict(cost_rel=2e-5, flip_frac=2e-3, action=5e-4, state=5e-4, lam_rel=1e-4)
+# MPO: the reference's fp32 autograd gradient carries a rounding term of
+# (ulp(logsumexp)/2) * E_w[c]/tau - several percent of the gradient when c/tau ~ 1e3 - so its own
+# lambda trajectory moves by O(1e-2) under ulp-level changes of the costs; lambda (and what
+# depends on it) is compared at that noise floor.
+TOL_MPO = dict(TOL, lam_rel=2e-2, action=5e-3, state=5e-3)
+
+
+# LBPS: lambda is the argmin of an objective that is flat at its minimum, so fp32 rounding of the
+# objective (relative ~1e-7) moves the argmin by ~sqrt(2 dJ / J'') ~ 1e-3 relative when the minimum is
+# interior; at the bracket ends (the recorded nav2d case sits at lambda_max) it is exact to ~1e-6.
+TOL_LBPS = dict(TOL, lam_rel=3e-3, action=2e-3, state=2e-3)
+
+
+def tol_for(lambda_):
+    return {"MPO": TOL_MPO, "LBPS": TOL_LBPS}.get(lambda_, TOL)
 
 
 def assert_parity(st: ParityStats, tol=TOL, smooth=False):
