@@ -193,6 +193,14 @@ int mppi_launch_info(const MppiHandle* h, int32_t* grid, int32_t* block, int32_t
  * used. model_flags: bit0 both racing grids share one geometry, bit1 unit wheelbase. */
 int mppi_map_info(const MppiHandle* h, int32_t slot, int32_t* fast_division, uint64_t* mismatches,
                   int32_t* model_flags);
+/* Profiling aid: with enable != 0 every block of the solve kernel stamps %globaltimer (ns) at
+ * 7 points (start, inputs staged, costs done, weights done, partial written, combined, finished);
+ * h_out (may be NULL) receives [min(max_blocks, grid), 8] stamps of the last solve. */
+int mppi_block_trace(MppiHandle* h, int32_t enable, uint64_t* h_out, int32_t max_blocks);
+/* Exhaustive device self-test of the bounded arithmetic helpers against the general ones, over every
+ * fp32 input of their claimed range: mismatches[0] tan_quarter vs tanf (|x| <= 0.78), [1]
+ * wrap_angle_bounded vs wrap_angle (|x| < 9), [2] floored_remainder vs the fmodf form. All must be 0. */
+int mppi_selftest(int32_t device, uint64_t mismatches[3]);
 /* Time the dominant (rollout) kernel of subsequent solves with CUDA events on
  * the launching stream: enable with 1, read back the mean/launch count with
  * mppi_kernel_time_ms (which synchronises the events). */

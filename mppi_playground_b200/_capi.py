@@ -68,6 +68,8 @@ PROTOTYPES = {
     "mppi_last_launch_count": (C.c_int32, [_P]),
     "mppi_launch_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mppi_map_info": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]),
+    "mppi_block_trace": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_uint64), C.c_int32]),
+    "mppi_selftest": (C.c_int, [C.c_int32, C.POINTER(C.c_uint64)]),
     "mppi_kernel_timing": (C.c_int, [_P, C.c_int32]),
     "mppi_kernel_time_ms": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "mppi_philox4x32_10": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),

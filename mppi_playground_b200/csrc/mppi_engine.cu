@@ -127,6 +127,8 @@ struct MppiHandle {
   uint32_t* d_map[2] = {nullptr, nullptr};
   bool map_set[2] = {false, false};
   unsigned long long fastdiv_mismatches[2] = {0, 0};
+  float proved_wheelbase = -1.0f, wheelbase_rcp = 1.0f;
+  bool wheelbase_exact = false;
   // host-call staging (mppi_solve_host)
   float* h_pinned = nullptr;  // state | refpath | action_seq | state_seq
   float* d_stage = nullptr;
@@ -143,6 +145,7 @@ struct MppiHandle {
   const float* last_noise = nullptr;
   int last_launches = 0;
   bool timing = false;
+  unsigned long long* d_trace = nullptr;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
 };
 
@@ -278,6 +281,7 @@ int make_params(MppiHandle* h, const float* d_state, const float* d_refpath, con
   p.key.solve_lo = (uint32_t)h->solve_count;
   p.key.solve_hi = (uint32_t)(h->solve_count >> 32);
   p.n_shards = n_shards;
+  p.trace = h->d_trace;
   *out = p;
   return MPPI_OK;
 }
@@ -300,15 +304,49 @@ int launch_rollout_actions(MppiHandle* h, const SolveParams& p, const float* act
   return MPPI_OK;
 }
 
+// Exhaustively prove (cell-size style) that x / c == the 3-instruction exact form for this divisor.
+bool prove_exact_division(float c, float* rcp_out) {
+  const float rcp = (float)(1.0 / (double)c);
+  *rcp_out = rcp;
+  unsigned long long* d_bad = nullptr;
+  unsigned long long bad = 1;
+  if (cudaMalloc((void**)&d_bad, 8) == cudaSuccess) {
+    cudaMemset(d_bad, 0, 8);
+    check_fastdiv_kernel<<<148 * 8, 256>>>(c, rcp, d_bad);
+    if (cudaMemcpy(&bad, d_bad, 8, cudaMemcpyDeviceToHost) != cudaSuccess) bad = 1;
+    cudaFree(d_bad);
+  }
+  return bad == 0;
+}
+
 void refresh_model_flags(MppiHandle* h) {
   SolveParams& b = h->base;
   int flags = 0;
+  const float* v = b.mp.v;
   if (h->cfg.model == MPPI_MODEL_RACING) {
     if (h->map_set[0] && h->map_set[1] && b.map_W[0] == b.map_W[1] && b.map_H[0] == b.map_H[1] &&
         b.map_cell[0] == b.map_cell[1] && b.map_ox[0] == b.map_ox[1] && b.map_oy[0] == b.map_oy[1] &&
         b.map_fastdiv[0] == b.map_fastdiv[1])
       flags |= kFlagSameMapGeometry;
-    if (b.mp.v[4] == 1.0f) flags |= kFlagUnitWheelbase;
+    // wheelbase division: v[17] holds RN(1/L); proven per distinct L (cached), trivially exact for L == 1
+    if (v[4] != h->proved_wheelbase) {
+      float rcp = 1.0f;
+      h->wheelbase_exact = (v[4] == 1.0f) ? true : prove_exact_division(v[4], &rcp);
+      if (v[4] == 1.0f) rcp = 1.0f;
+      h->wheelbase_rcp = rcp;
+      h->proved_wheelbase = v[4];
+    }
+    b.mp.v[17] = h->wheelbase_rcp;
+    if (h->wheelbase_exact) flags |= kFlagUnitWheelbase;  // "exact division available"
+    // bounded-variant preconditions (fp64, with margin): |steer| <= 0.78 and |v_max tan(s) / L dt| < 6
+    const double smax = std::max(fabs((double)v[2]), fabs((double)v[3]));
+    if (smax <= 0.78 && v[4] > 0.0f) {
+      const double yaw = fabs((double)v[5]) * tan(smax) / (double)v[4] * fabs((double)v[10]);
+      if (yaw < 6.0) flags |= kFlagBounded;
+    }
+  } else if (h->cfg.model == MPPI_MODEL_NAVIGATION2D) {
+    const double wmax = std::max(fabs((double)v[2]), fabs((double)v[3]));
+    if (wmax * fabs((double)v[10]) < 6.0) flags |= kFlagBounded;
   }
   b.mp.flags = flags;
 }
@@ -494,6 +532,7 @@ void mppi_destroy(MppiHandle* h) {
   cudaFree(h->d_idx_out);
   cudaFree(h->d_keys_out);
   cudaFree(h->d_sort_tmp);
+  cudaFree(h->d_trace);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -553,18 +592,11 @@ int mppi_set_map(MppiHandle* h, int32_t slot, const float* grid, int32_t on_devi
   b.map_bytes[slot] = (unsigned)bytes;
   b.map_cell[slot] = cell;
   {  // exact fast division by the cell size: prove it for this divisor, or keep the true division
-    const float rcp = (float)(1.0 / (double)cell);
-    unsigned long long* d_bad = nullptr;
-    unsigned long long bad = 1;
-    if (cudaMalloc((void**)&d_bad, 8) == cudaSuccess) {
-      cudaMemset(d_bad, 0, 8);
-      check_fastdiv_kernel<<<148 * 8, 256>>>(cell, rcp, d_bad);
-      if (cudaMemcpy(&bad, d_bad, 8, cudaMemcpyDeviceToHost) != cudaSuccess) bad = 1;
-      cudaFree(d_bad);
-    }
+    float rcp = 0.0f;
+    const bool ok = prove_exact_division(cell, &rcp);
     b.map_rcp[slot] = rcp;
-    b.map_fastdiv[slot] = (bad == 0) ? 1 : 0;
-    h->fastdiv_mismatches[slot] = bad;
+    b.map_fastdiv[slot] = ok ? 1 : 0;
+    h->fastdiv_mismatches[slot] = ok ? 0 : 1;
   }
   b.map_ox[slot] = ox;
   b.map_oy[slot] = oy;
@@ -810,6 +842,41 @@ int mppi_map_info(const MppiHandle* h, int32_t slot, int32_t* fast_division, uin
   if (fast_division) *fast_division = h->base.map_fastdiv[slot];
   if (mismatches) *mismatches = h->fastdiv_mismatches[slot];
   if (model_flags) *model_flags = h->base.mp.flags;
+  return MPPI_OK;
+}
+
+int mppi_block_trace(MppiHandle* h, int32_t enable, uint64_t* h_out, int32_t max_blocks) {
+  if (!h) return fail(MPPI_ERR_INVALID, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t n = (size_t)((h->cfg.num_samples + 63) / 64) * 8;
+  if (enable && !h->d_trace) {
+    CUDA_TRY(cudaMalloc((void**)&h->d_trace, n * 8));
+    CUDA_TRY(cudaMemset(h->d_trace, 0, n * 8));
+  }
+  if (h_out && h->d_trace) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    size_t blocks = std::min<size_t>((size_t)max_blocks, (size_t)h->grid);
+    CUDA_TRY(cudaMemcpy(h_out, h->d_trace, blocks * 8 * 8, cudaMemcpyDeviceToHost));
+  }
+  if (!enable && h->d_trace) {
+    cudaFree(h->d_trace);
+    h->d_trace = nullptr;
+  }
+  return MPPI_OK;
+}
+
+int mppi_selftest(int32_t device, uint64_t mismatches[3]) {
+  if (!mismatches) return fail(MPPI_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(device));
+  unsigned long long* d = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&d, 24));
+  CUDA_TRY(cudaMemset(d, 0, 24));
+  selftest_kernel<<<148 * 8, 256>>>(d);
+  unsigned long long hbad[3] = {1, 1, 1};
+  cudaError_t e = cudaMemcpy(hbad, d, 24, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(MPPI_ERR_CUDA, "selftest: %s", cudaGetErrorString(e));
+  for (int i = 0; i < 3; ++i) mismatches[i] = hbad[i];
   return MPPI_OK;
 }
 

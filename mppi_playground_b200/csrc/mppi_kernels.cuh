@@ -26,6 +26,7 @@ namespace mppi {
 enum SolveMode : int { kFused = 0, kCosts = 1, kReduce = 2 };
 enum LambdaMode : int { kLamFixed = 0, kLamMPO = 1, kLamLBPS = 2, kLamESSPS = 3 };
 
+constexpr int kMaxSegments = 4;    // combine_partials: threads = segments x entries
 constexpr int kPartialHeader = 8;  // xmax S xmax_tau S_tau Sc_tau cmin cmax pad
 constexpr int kMaxSgWindow = 33;
 
@@ -74,6 +75,7 @@ struct SolveParams {
   float mpo_epsilon;
   int use_sg, sg_window;
   float sg_coeffs[kMaxSgWindow];
+  unsigned long long* trace;  // optional [grid, 8] %globaltimer stamps per block (profiling aid), else null
   int n_shards;  // 1: finish inside the kernel
   int E, E_pad, P;
 };
@@ -81,14 +83,15 @@ struct SolveParams {
 // shared-memory carve-up (host and device agree through this helper)
 struct SmemLayout {
   unsigned map_off[2];
-  unsigned nominal_off, refraw_off, ref4_off, refv_off, warpacc_off, red_off, misc_off, total;
+  unsigned nominal_off, refraw_off, ref4_off, refv_off, warpacc_off, list_off, red_off, misc_off, total;
 };
 
 __host__ __device__ inline unsigned align_up(unsigned x, unsigned a) { return (x + a - 1) / a * a; }
 
 // floats of scratch finish_solve needs: N (doubles) | opt | y | scales | Combined | tail rollout
 __host__ __device__ inline unsigned finish_scratch_core(int E_pad, int T, int tail_per_step) {
-  return (unsigned)E_pad * 20 + 256 * 4 + 64 + (unsigned)tail_per_step * (unsigned)(T + 1) * 4;
+  return (unsigned)E_pad * 20 + 256 * 4 + 64 + (unsigned)E_pad * 8 * kMaxSegments +
+         (unsigned)tail_per_step * (unsigned)(T + 1) * 4;
 }
 
 __host__ __device__ inline SmemLayout make_layout(int n_maps, const unsigned* map_bytes, int T, int E_pad,
@@ -115,10 +118,12 @@ __host__ __device__ inline SmemLayout make_layout(int n_maps, const unsigned* ma
     unsigned fin = finish_scratch_core(E_pad, T, tail_per_step);
     o += align_up(acc > fin ? acc : fin, 16);
   }
+  L.list_off = o;
+  o += (unsigned)n_warps * 32 * 8;  // (thread, weight) of the samples with non-zero weight
   L.red_off = o;
-  o += 64 * 8;  // block reduction scratch (doubles)
+  o += 128 * 8;  // block reduction scratch (up to 4 x 32 doubles)
   L.misc_off = o;
-  o += 64;
+  o += 128;
   L.total = o;
   return L;
 }
@@ -175,63 +180,123 @@ __device__ __forceinline__ float perturbed_entry(const SolveParams& p, const flo
 // ---------------------------------------------------------------------------
 // finish: combine partials -> optimal sequence -> SG filter -> trajectory, carry
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ void stamp(const SolveParams& p, int slot);
+
 struct Combined {
   float xmax, xmax_tau, cmin, cmax;
   double S, S_tau, Sc_tau;
 };
 
+// Reduce up to 4 values per thread across the block in one pass (two barriers in total).
+template <class T, class Op, int N>
+__device__ __forceinline__ void block_reduce_n(T (&v)[N], Op op, T identity, void* scratch) {
+  T* s = reinterpret_cast<T*>(scratch);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[i] = op(v[i], __shfl_xor_sync(kFullMask, v[i], o));
+  __syncthreads();
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < N; ++i) s[i * 32 + warp] = v[i];
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    T r = (lane < nw) ? s[i * 32 + lane] : identity;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r = op(r, __shfl_xor_sync(kFullMask, r, o));
+    v[i] = r;
+  }
+}
+
+constexpr int kCombineChunk = 256;  // partials whose rescale factors are staged at once
+
 // Combine n partials (stride P) into `out` + N[E] (shared, doubles).
 // Deterministic: fixed traversal order, independent of which block runs it.
+// Work split: the block's threads form (segments x entries); a thread sums its segment of the
+// partials for one entry with 8 independent loads in flight, segments are then added in order.
 __device__ inline void combine_partials(const float* __restrict__ parts, int n, int P, int E, Combined* out,
-                                        double* N, float* scale_buf /*[256]*/, void* red) {
+                                        double* N, float* scale_buf /*[kCombineChunk]*/, void* red,
+                                        double* seg_buf /*[E_pad * kMaxSegments]*/) {
   const int tid = threadIdx.x, nt = blockDim.x;
-  float xm = -INFINITY, xmt = -INFINITY, cmin = INFINITY, cmax = -INFINITY;
+  float mx[2] = {-INFINITY, -INFINITY}, mn[2] = {INFINITY, INFINITY};  // (xmax, xmax_tau), (cmin, -cmax)
   for (int b = tid; b < n; b += nt) {
     const float* q = parts + (size_t)b * P;
-    xm = fmaxf(xm, q[0]);
-    xmt = fmaxf(xmt, q[2]);
-    cmin = fminf(cmin, q[5]);
-    cmax = fmaxf(cmax, q[6]);
+    mx[0] = fmaxf(mx[0], q[0]);
+    mx[1] = fmaxf(mx[1], q[2]);
+    mn[0] = fminf(mn[0], q[5]);
+    mn[1] = fminf(mn[1], -q[6]);
   }
-  xm = block_reduce(xm, OpMax(), -INFINITY, red);
-  xmt = block_reduce(xmt, OpMax(), -INFINITY, red);
-  cmin = block_reduce(cmin, OpMin(), INFINITY, red);
-  cmax = block_reduce(cmax, OpMax(), -INFINITY, red);
-  double S = 0.0, St = 0.0, Sct = 0.0;
+  block_reduce_n(mx, OpMax(), -INFINITY, red);
+  block_reduce_n(mn, OpMin(), INFINITY, red);
+  const float xm = mx[0], xmt = mx[1];
+  double sums[3] = {0.0, 0.0, 0.0};
   for (int b = tid; b < n; b += nt) {
     const float* q = parts + (size_t)b * P;
-    S += (double)q[1] * (double)expf(q[0] - xm);
+    sums[0] += (double)q[1] * (double)expf(q[0] - xm);
     if (xmt > -INFINITY) {
       double sc = (double)expf(q[2] - xmt);
-      St += (double)q[3] * sc;
-      Sct += (double)q[4] * sc;
+      sums[1] += (double)q[3] * sc;
+      sums[2] += (double)q[4] * sc;
     }
   }
-  S = block_reduce(S, OpAddD(), 0.0, red);
-  St = block_reduce(St, OpAddD(), 0.0, red);
-  Sct = block_reduce(Sct, OpAddD(), 0.0, red);
-  // weighted-sum numerators: thread e owns entry e, walks the partials in order
-  for (int e = tid; e < E; e += nt) N[e] = 0.0;
-  for (int b0 = 0; b0 < n; b0 += 256) {
-    int nb = min(256, n - b0);
+  block_reduce_n(sums, OpAddD(), 0.0, red);
+  // weighted-sum numerators
+  const int n_seg = max(1, min(kMaxSegments, nt / max(E, 1)));
+  const int seg = tid / E, e = tid - seg * E;  // threads beyond n_seg * E idle in the sums
+  const bool worker = (E <= nt) && seg < n_seg;
+  double acc = 0.0;
+  if (E <= nt) {
+    for (int b0 = 0; b0 < n; b0 += kCombineChunk) {
+      const int nb = min(kCombineChunk, n - b0);
+      __syncthreads();
+      if (tid < nb) scale_buf[tid] = expf(parts[(size_t)(b0 + tid) * P] - xm);
+      __syncthreads();
+      if (worker) {
+        const int per = (nb + n_seg - 1) / n_seg, lo = seg * per, hi = min(nb, lo + per);
+        const float* col = parts + (size_t)b0 * P + kPartialHeader + e;
+        int b = lo;
+        for (; b + 8 <= hi; b += 8) {
+          float x[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = col[(size_t)(b + j) * P];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc += (double)x[j] * (double)scale_buf[b + j];
+        }
+        for (; b < hi; ++b) acc += (double)col[(size_t)b * P] * (double)scale_buf[b];
+      }
+    }
+    if (worker) seg_buf[seg * E + e] = acc;
     __syncthreads();
-    if (tid < nb) scale_buf[tid] = expf(parts[(size_t)(b0 + tid) * P] - xm);
-    __syncthreads();
-    for (int e = tid; e < E; e += nt) {
-      double a = N[e];
-      for (int b = 0; b < nb; ++b)
-        a += (double)parts[(size_t)(b0 + b) * P + kPartialHeader + e] * (double)scale_buf[b];
-      N[e] = a;
+    if (tid < E) {
+      double a = 0.0;
+      for (int sgm = 0; sgm < n_seg; ++sgm) a += seg_buf[sgm * E + tid];
+      N[tid] = a;
+    }
+  } else {  // more entries than threads: each thread walks its entries (rare: T*du > blockDim)
+    for (int ee = tid; ee < E; ee += nt) N[ee] = 0.0;
+    for (int b0 = 0; b0 < n; b0 += kCombineChunk) {
+      const int nb = min(kCombineChunk, n - b0);
+      __syncthreads();
+      if (tid < nb) scale_buf[tid] = expf(parts[(size_t)(b0 + tid) * P] - xm);
+      __syncthreads();
+      for (int ee = tid; ee < E; ee += nt) {
+        double a = N[ee];
+        for (int b = 0; b < nb; ++b)
+          a += (double)parts[(size_t)(b0 + b) * P + kPartialHeader + ee] * (double)scale_buf[b];
+        N[ee] = a;
+      }
     }
   }
   if (tid == 0) {
     out->xmax = xm;
     out->xmax_tau = xmt;
-    out->cmin = cmin;
-    out->cmax = cmax;
-    out->S = S;
-    out->S_tau = St;
-    out->Sc_tau = Sct;
+    out->cmin = mn[0];
+    out->cmax = -mn[1];
+    out->S = sums[0];
+    out->S_tau = sums[1];
+    out->Sc_tau = sums[2];
   }
   __syncthreads();
 }
@@ -306,6 +371,7 @@ __device__ inline void finish_solve(const SolveParams& p, const typename M::Ctx&
     if (p.lambda_mode == kLamMPO) mpo_update(p, c);
   }
   if (tid < DS) p.state_snapshot[tid] = p.state[tid];
+  stamp(p, 7);
   // optimal-trajectory rollout (mppi.py:448-449, 508-524)
   if constexpr (M::kParallelTail) {
     __syncthreads();
@@ -329,9 +395,18 @@ __device__ inline void finish_solve(const SolveParams& p, const typename M::Ctx&
 // ---------------------------------------------------------------------------
 // the solve kernel
 // ---------------------------------------------------------------------------
-template <class M, bool kInject>
+template <class M, bool kBounded>
+__device__ __forceinline__ void model_step(const typename M::Ctx& ctx, float (&s)[M::DS], const float (&u)[M::DU],
+                                           float (&seen)[M::DS]) {
+  if constexpr (M::kHasBounded)
+    M::template step<kBounded>(ctx, s, u, seen);
+  else
+    M::step(ctx, s, u, seen);
+}
+
+template <class M, bool kInject, bool kBounded>
 __device__ __forceinline__ float rollout_cost(const SolveParams& p, const typename M::Ctx& ctx, const float* nominal,
-                                              bool zero_mean, uint32_t k_lo, uint32_t k_hi, long long k_local) {
+                                           bool zero_mean, uint32_t k_lo, uint32_t k_hi, long long k_local) {
   constexpr int DS = M::DS, DU = M::DU, SPC = Chunking<DU>::kStepsPerChunk;
   const int T = p.T;
   float s[DS], seen[DS];
@@ -357,7 +432,7 @@ __device__ __forceinline__ float rollout_cost(const SolveParams& p, const typena
         float pu[DU];  // info["prev_action"]: U[:, max(t-1, 0)]  (mppi.py:299-304)
 #pragma unroll
         for (int d = 0; d < DU; ++d) pu[d] = (t == 0) ? u[d] : up[d];
-        M::step(ctx, s, u, seen);                      // S[:, t+1] = dynamics(S[:, t], U[:, t])   (mppi.py:282-286)
+        model_step<M, kBounded>(ctx, s, u, seen);      // S[:, t+1] = dynamics(S[:, t], U[:, t])   (mppi.py:282-286)
         total = total + M::cost(ctx, seen, u, pu, t);  // stage cost on the stored S[:, t]        (mppi.py:307-311)
 #pragma unroll
         for (int d = 0; d < DU; ++d) {
@@ -375,6 +450,14 @@ __device__ __forceinline__ float rollout_cost(const SolveParams& p, const typena
     pa[d] = (T >= 2) ? upp[d] : up[d];
   }
   return total + M::cost(ctx, s, zero, pa, T - 1);  // mppi.py:333-336
+}
+
+__device__ __forceinline__ void stamp(const SolveParams& p, int slot) {
+  if (p.trace && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[(size_t)blockIdx.x * 8 + slot] = t;
+  }
 }
 
 template <class M>
@@ -398,6 +481,7 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ S
   void* red = smem + L.red_off;
   int* misc = reinterpret_cast<int*>(smem + L.misc_off);
 
+  stamp(p, 0);
   // ---- stage the block's read-only inputs into shared memory (TMA bulk copies)
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -456,6 +540,7 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ S
     ctx.ref_v = refv;
   }
 
+  stamp(p, 1);
   const long long k_local = (long long)blockIdx.x * blockDim.x + tid;
   const bool active = k_local < p.K;
   const long long k_global = p.k_offset + k_local;
@@ -467,10 +552,15 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ S
   if (kMode == kReduce) {
     if (active) cost = p.costs[k_local];
   } else if (active) {
-    cost = rollout_cost<M, kInject>(p, ctx, nominal, zero_mean, k_lo, k_hi, k_local);
+    bool bounded = false;  // uniform over the block: model flag + the solve's initial state
+    if constexpr (M::kHasBounded) bounded = (p.mp.flags & kFlagBounded) && M::state_in_bounds(ctx, p.state);
+    cost = bounded ? rollout_cost<M, kInject, true>(p, ctx, nominal, zero_mean, k_lo, k_hi, k_local)
+                   : rollout_cost<M, kInject, false>(p, ctx, nominal, zero_mean, k_lo, k_hi, k_local);
     p.costs[k_local] = cost;
   }
   if (kMode == kCosts) return;
+  __syncthreads();
+  stamp(p, 2);
 
   // ---- block-local softmax baseline (mppi.py:376; online-softmax form) -----------
   const float lam = (float)p.sc->lambda;
@@ -491,43 +581,65 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ S
     Sct_b = block_reduce(active ? et * cost : 0.0f, OpAddF(), 0.0f, red);
   }
 
-  // ---- pass 2: regenerate the perturbed controls, reduce sum_k w_k u_k -------------
-  const int n_groups = p.E_pad / 32;
-  float* my_acc = warp_acc + (size_t)warp * p.E_pad;
-  if (__any_sync(kFullMask, w != 0.0f)) {  // exact: a zero weight contributes exactly nothing
-    const float* nz = kInject && active ? (p.noise + (size_t)k_local * p.T * DU) : nullptr;
-    for (int g = 0; g < n_groups; ++g) {
-      float v[32];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
+  stamp(p, 3);
+  // ---- pass 2: regenerate the perturbed controls of the samples that carry weight and reduce
+  //      sum_k w_k u_k[t,d]. A zero weight contributes exactly nothing (the reference multiplies by
+  //      it), so only samples with w != 0 are listed; the list is walked chunk-parallel: thread
+  //      (g, c) owns the 4 entries of sampler chunk c and accumulates them over the listed samples
+  //      i = g, g+G, ... in order, groups are then added in order -> deterministic, all warps busy,
+  //      and the cost scales with the number of samples that matter, not with K.
+  int2* list = reinterpret_cast<int2*>(smem + L.list_off);
+  int* wcount = misc + 2;  // [n_warps]
+  {
+    const bool on = w != 0.0f;
+    const unsigned m = __ballot_sync(kFullMask, on);
+    if (lane == 0) wcount[warp] = __popc(m);
+    __syncthreads();
+    int off = 0, n_active = 0;
+    for (int i = 0; i < n_warps; ++i) {
+      off += (i < warp) ? wcount[i] : 0;
+      n_active += wcount[i];
+    }
+    if (on) list[off + __popc(m & ((1u << lane) - 1u))] = make_int2(tid, __float_as_int(w));
+    __syncthreads();
+    const int n_chunks = (p.E + 3) / 4;
+    float* group_acc = warp_acc;  // [G, E_pad]
+    const int G = (n_chunks <= (int)blockDim.x) ? max(1, min((int)blockDim.x / n_chunks, n_warps)) : 1;
+    const int g = (n_chunks <= (int)blockDim.x) ? tid / n_chunks : 0;
+    const long long block_k0 = (long long)blockIdx.x * blockDim.x;
+    for (int c = (n_chunks <= (int)blockDim.x) ? tid - g * n_chunks : tid; c < n_chunks && g < G;
+         c += (n_chunks <= (int)blockDim.x) ? n_chunks : (int)blockDim.x) {
+      float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      for (int i = g; i < n_active; i += G) {
+        const int2 it = list[i];
+        const float wi = __int_as_float(it.y);
+        const long long kl = block_k0 + it.x, kg = p.k_offset + kl;
+        const bool zm = kg >= p.explore_threshold;
         float z[4];
-        const int e0 = g * 32 + c * 4;
-        if (!kInject && e0 < p.E) normal4(p.key, k_lo, k_hi, (uint32_t)(g * 8 + c), z);
+        if (!kInject) normal4(p.key, (uint32_t)kg, (uint32_t)((unsigned long long)kg >> 32), (uint32_t)c, z);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int e = e0 + j;
-          float val = 0.0f;
-          if (e < p.E && active) {
+          const int e = c * 4 + j;
+          if (e < p.E) {
             const int t = e / DU, d = e - t * DU;
-            float eps = kInject ? nz[e] : p.sigma[d] * z[j];
-            val = w * perturbed_entry<DU>(p, nominal, zero_mean, t, d, eps);
+            float eps = kInject ? p.noise[(size_t)kl * p.E + e] : p.sigma[d] * z[j];
+            acc[j] = acc[j] + wi * perturbed_entry<DU>(p, nominal, zm, t, d, eps);
           }
-          v[c * 4 + j] = val;
         }
       }
-      float r = warp_transpose_sum(v, lane);
-      my_acc[g * 32 + lane] = r;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c * 4 + j < p.E_pad) group_acc[(size_t)g * p.E_pad + c * 4 + j] = acc[j];
     }
-  } else {
-    for (int e = lane; e < p.E_pad; e += 32) my_acc[e] = 0.0f;
+    __syncthreads();
+    float* part = p.block_partials + (size_t)blockIdx.x * p.P;
+    for (int e = tid; e < p.E; e += blockDim.x) {
+      float a = 0.0f;
+      for (int gg = 0; gg < G; ++gg) a += group_acc[(size_t)gg * p.E_pad + e];
+      part[kPartialHeader + e] = a;
+    }
   }
-  __syncthreads();
   float* part = p.block_partials + (size_t)blockIdx.x * p.P;
-  for (int e = tid; e < p.E; e += blockDim.x) {
-    float a = 0.0f;
-    for (int wv = 0; wv < n_warps; ++wv) a += warp_acc[(size_t)wv * p.E_pad + e];
-    part[kPartialHeader + e] = a;
-  }
   if (tid == 0) {
     part[0] = xmax_b;
     part[1] = S_b;
@@ -542,6 +654,7 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ S
   // ---- last block: combine and finish ------------------------------------------------
   __threadfence();
   __syncthreads();
+  stamp(p, 4);
   if (tid == 0) {
     unsigned ticket = atomicAdd(p.counter, 1u);
     misc[0] = (ticket == gridDim.x - 1) ? 1 : 0;
@@ -556,8 +669,10 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ S
   float* ybuf = opt + p.E_pad;
   float* scale_buf = ybuf + 2 * p.E_pad;
   Combined* comb = reinterpret_cast<Combined*>(scale_buf + 256);
-  float* tail = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(comb) + 64);
-  combine_partials(p.block_partials, (int)gridDim.x, p.P, p.E, comb, Nbuf, scale_buf, red);
+  double* seg_buf = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(comb) + 64);
+  float* tail = reinterpret_cast<float*>(seg_buf + (size_t)p.E_pad * kMaxSegments);
+  combine_partials(p.block_partials, (int)gridDim.x, p.P, p.E, comb, Nbuf, scale_buf, red, seg_buf);
+  stamp(p, 5);
   if (p.n_shards == 1) {
     finish_solve<M>(p, ctx, *comb, Nbuf, opt, ybuf, tail);
   } else {
@@ -574,6 +689,8 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ S
       q[7] = 0.0f;
     }
   }
+  __syncthreads();
+  stamp(p, 6);
   if (tid == 0) *p.counter = 0u;
 }
 
@@ -587,16 +704,17 @@ __global__ void __launch_bounds__(256, 1) finish_kernel(const __grid_constant__ 
   float* ybuf = opt + p.E_pad;
   float* scale_buf = ybuf + 2 * p.E_pad;
   Combined* comb = reinterpret_cast<Combined*>(scale_buf + 256);
-  float* tail = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(comb) + 64);
+  double* seg_buf = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(comb) + 64);
+  float* tail = reinterpret_cast<float*>(seg_buf + (size_t)p.E_pad * kMaxSegments);
   void* red = smem + finish_scratch_core(p.E_pad, p.T, tail_per_step<M>());
   typename M::Ctx ctx{};
   if constexpr (M::kMaps >= 1) ctx.p = &p.mp;
-  combine_partials(parts, n, p.P, p.E, comb, Nbuf, scale_buf, red);
+  combine_partials(parts, n, p.P, p.E, comb, Nbuf, scale_buf, red, seg_buf);
   finish_solve<M>(p, ctx, *comb, Nbuf, opt, ybuf, tail);
 }
 
 __host__ __device__ inline unsigned finish_scratch_bytes(int E_pad, int T, int tail_per_step) {
-  return finish_scratch_core(E_pad, T, tail_per_step) + 64 * 8;
+  return finish_scratch_core(E_pad, T, tail_per_step) + 128 * 8;
 }
 
 // ---------------------------------------------------------------------------
@@ -832,21 +950,49 @@ __global__ void iota_kernel(int* out, int n) {
   if (i < n) out[i] = i;
 }
 
-// Exhaustive proof obligation of ExactDiv: count the x (all 2^32 bit patterns) for which the
-// 3-instruction sequence differs from the IEEE quotient x / c.
+// Exhaustive proof obligation of ExactDiv: count the x (all 2^32 bit patterns inside the guarded
+// magnitude range of div_exact) for which the 3-instruction sequence differs from the IEEE x / c.
 __global__ void check_fastdiv_kernel(float c, float r, unsigned long long* mismatches) {
-  unsigned long long bad = 0;
+  unsigned bad = 0;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 32); i += stride) {
     float x = __uint_as_float((unsigned)i);
+    float ax = fabsf(x);
+    if (!(ax >= kFastDivMin && ax <= kFastDivMax)) continue;
     float q = x * r;
     float fast = fmaf(fmaf(-q, c, x), r, q);
     float ref = x / c;
-    bool same = (__float_as_uint(fast) == __float_as_uint(ref)) || (isnan(fast) && isnan(ref));
-    bad += same ? 0 : 1;
+    bad += (__float_as_uint(fast) == __float_as_uint(ref)) ? 0u : 1u;
   }
-  bad = __reduce_add_sync(kFullMask, (unsigned)bad);
-  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, bad);
+  bad = __reduce_add_sync(kFullMask, bad);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, (unsigned long long)bad);
+}
+
+// Exhaustive self-tests of the bounded helpers against the general ones (tests call these through
+// mppi_selftest): every float in the claimed range, bit-for-bit.
+__global__ void selftest_kernel(unsigned long long* bad /*[3]*/) {
+  unsigned b_tan = 0, b_wrap = 0, b_rem = 0;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 32); i += stride) {
+    const float x = __uint_as_float((unsigned)i);
+    const float ax = fabsf(x);
+    if (ax <= 0.78f) b_tan += (__float_as_uint(tan_quarter(x)) != __float_as_uint(tanf(x))) ? 1u : 0u;
+    if (ax < 9.0f) b_wrap += (__float_as_uint(wrap_angle_bounded(x)) != __float_as_uint(wrap_angle(x))) ? 1u : 0u;
+    if (ax < 1e30f) {  // lean floored remainder vs the textbook fmodf form
+      const float b = 6.28318548202514648f;
+      float m = fmodf(x, b);
+      if (m != 0.0f && (m < 0.0f)) m += b;
+      b_rem += (__float_as_uint(m) != __float_as_uint(floored_remainder(x, b))) ? 1u : 0u;
+    }
+  }
+  b_tan = __reduce_add_sync(kFullMask, b_tan);
+  b_wrap = __reduce_add_sync(kFullMask, b_wrap);
+  b_rem = __reduce_add_sync(kFullMask, b_rem);
+  if ((threadIdx.x & 31) == 0) {
+    if (b_tan) atomicAdd(bad + 0, (unsigned long long)b_tan);
+    if (b_wrap) atomicAdd(bad + 1, (unsigned long long)b_wrap);
+    if (b_rem) atomicAdd(bad + 2, (unsigned long long)b_rem);
+  }
 }
 
 __global__ void pack_map_kernel(const float* __restrict__ grid, int W, int H, int words, uint32_t* __restrict__ bits) {

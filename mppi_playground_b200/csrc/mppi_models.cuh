@@ -23,14 +23,18 @@ namespace mppi {
 // x / c for a fixed divisor, bit-identical to the IEEE quotient: q0 = x * r with r = RN(1/c), one
 // exact residual (fma) and one correction (fma) - Markstein's sequence, 3 instructions instead of the
 // ~10 + range check of a full division. `fast` is only set after an EXHAUSTIVE device-side comparison
-// against `x / c` over all 2^32 bit patterns of x for this very (c, r) pair (check_fastdiv_kernel,
-// run once in mppi_set_map); otherwise the true division is used.
+// against `x / c` over every fp32 x with 1e-30 <= |x| <= 1e30 for this very (c, r) pair
+// (check_fastdiv_kernel, run once in mppi_set_map); otherwise, and outside that range, the true
+// division is used.
 struct ExactDiv {
   float c, r;
   int fast;
 };
+// outside this magnitude range the residual fma can underflow / the product overflow: true division
+constexpr float kFastDivMin = 1e-30f, kFastDivMax = 1e30f;
 __device__ __forceinline__ float div_exact(float x, const ExactDiv& d) {
-  if (d.fast) {
+  const float ax = fabsf(x);
+  if (d.fast && ax >= kFastDivMin && ax <= kFastDivMax) {
     float q = x * d.r;
     float rem = fmaf(-q, d.c, x);
     return fmaf(rem, d.r, q);
@@ -66,17 +70,42 @@ __device__ __forceinline__ float map_lookup(const MapView& m, float x, float y) 
   return map_value(m, map_cell(x, m.cell, m.ox), map_cell(y, m.cell, m.oy));
 }
 
+// Heading recurrence of the unicycle / bicycle models, one thread, inputs prefetched 8 at a time:
+// thw[t] = wrap(ths[t]); ths[t+1] = wrap(thw[t] + inc[t]).
+template <bool kBounded>
+__device__ __forceinline__ void heading_chain(float th, const float* inc, float* thw, float* ths, int T) {
+  ths[0] = th;
+  for (int t0 = 0; t0 < T; t0 += 8) {
+    float cc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cc[j] = (t0 + j < T) ? inc[t0 + j] : 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (t0 + j < T) {
+        const float w = kBounded ? wrap_angle_bounded(th) : wrap_angle(th);
+        thw[t0 + j] = w;
+        th = kBounded ? wrap_angle_bounded(w + cc[j]) : wrap_angle(w + cc[j]);
+        ths[t0 + j + 1] = th;
+      }
+  }
+}
+
 struct ModelParams {
   float v[32];
   int flags;  // model specific, set by the host (see kFlag*)
 };
 constexpr int kFlagSameMapGeometry = 1;  // Racing: obstacle and lane grids share W, H, cell, origin
 constexpr int kFlagUnitWheelbase = 2;    // Racing: L == 1.0f, so x / L == x exactly
+// Host-verified bounds (mppi_engine.cu:refresh_model_flags) that make the branch-free helpers exact:
+//   steering clamp within +-0.78 rad  -> tan_quarter == tanf
+//   |yaw increment per step| < 6 rad  -> wrap_angle_bounded == wrap_angle on every rolled-out heading
+// The kernel additionally requires the solve's initial heading / speed to be in range (uniform check).
+constexpr int kFlagBounded = 4;
 
 // ---------------------------------------------------------------------------
 struct Pendulum {  // example/pendulum.py:17-47
   static constexpr int DS = 2, DU = 1, kMaps = 0;
-  static constexpr bool kRefPath = false, kParallelTail = false;
+  static constexpr bool kRefPath = false, kParallelTail = false, kHasBounded = false;
   struct Ctx {};
   __device__ static __forceinline__ void step(const Ctx&, float (&s)[DS], const float (&u)[DU], float (&seen)[DS]) {
     seen[0] = s[0];
@@ -98,7 +127,7 @@ struct Pendulum {  // example/pendulum.py:17-47
 // ---------------------------------------------------------------------------
 struct Cartpole {  // example/cartpole.py:17-81
   static constexpr int DS = 4, DU = 1, kMaps = 0;
-  static constexpr bool kRefPath = false, kParallelTail = false;
+  static constexpr bool kRefPath = false, kParallelTail = false, kHasBounded = false;
   struct Ctx {};
   __device__ static __forceinline__ void step(const Ctx&, float (&s)[DS], const float (&u)[DU], float (&seen)[DS]) {
 #pragma unroll
@@ -129,7 +158,7 @@ struct Cartpole {  // example/cartpole.py:17-81
 // ---------------------------------------------------------------------------
 struct MountainCar {  // example/mountaincar.py:17-55
   static constexpr int DS = 2, DU = 1, kMaps = 0;
-  static constexpr bool kRefPath = false, kParallelTail = false;
+  static constexpr bool kRefPath = false, kParallelTail = false, kHasBounded = false;
   struct Ctx {};
   __device__ static __forceinline__ void step(const Ctx&, float (&s)[DS], const float (&u)[DU], float (&seen)[DS]) {
     float force = clampf(u[0], -1.0f, 1.0f);                          // :32
@@ -151,26 +180,32 @@ struct MountainCar {  // example/mountaincar.py:17-55
 // ---------------------------------------------------------------------------
 struct Navigation2D {  // src/envs/navigation_2d.py:218-279
   static constexpr int DS = 3, DU = 2, kMaps = 1;
-  static constexpr bool kRefPath = false, kParallelTail = true;
+  static constexpr bool kRefPath = false, kParallelTail = true, kHasBounded = true;
   struct Ctx {
     MapView map;
     const ModelParams* p;  // v_min v_max w_min w_max goal_x goal_y x_lo x_hi y_lo y_hi dt w_obst
   };
+  // kBounded: the host proved |omega dt| < 6 and the kernel checked the initial heading, so every
+  // heading stays within the exact range of wrap_angle_bounded (same values, no slow path).
+  template <bool kBounded = false>
   __device__ static __forceinline__ void step(const Ctx& c, float (&s)[DS], const float (&u)[DU], float (&seen)[DS]) {
     const float* p = c.p->v;
 #pragma unroll
     for (int i = 0; i < DS; ++i) seen[i] = s[i];
     float v = clampf(u[0], p[0], p[1]);  // :235-236
     float w = clampf(u[1], p[2], p[3]);
-    float th = wrap_angle(s[2]);  // :237
+    float th = kBounded ? wrap_angle_bounded(s[2]) : wrap_angle(s[2]);  // :237
     float st, ct;
     sincosf(th, &st, &ct);
     float nx = s[0] + v * ct * p[10];  // :239-241
     float ny = s[1] + v * st * p[10];
-    float nth = wrap_angle(th + w * p[10]);
+    float nth = kBounded ? wrap_angle_bounded(th + w * p[10]) : wrap_angle(th + w * p[10]);
     s[0] = clampf(nx, p[6], p[7]);  // :244-251
     s[1] = clampf(ny, p[8], p[9]);
     s[2] = nth;
+  }
+  __device__ static __forceinline__ bool state_in_bounds(const Ctx&, const float* state) {
+    return fabsf(state[2]) < 9.0f;  // |theta + pi| < 4 pi with margin
   }
   __device__ static __forceinline__ float cost(const Ctx& c, const float (&s)[DS], const float (&)[DU],
                                                const float (&)[DU], int) {
@@ -194,15 +229,11 @@ struct Navigation2D {  // src/envs/navigation_2d.py:218-279
       wdt[t] = clampf(opt[2 * t + 1], p[2], p[3]) * p[10];
     }
     __syncthreads();
-    if (tid == 0) {
-      float th = state[2];
-      ths[0] = th;
-      for (int t = 0; t < T; ++t) {
-        float w = wrap_angle(th);
-        thw[t] = w;
-        th = wrap_angle(w + wdt[t]);
-        ths[t + 1] = th;
-      }
+    if (tid == 0) {  // heading: S[t+1].theta = wrap(wrap(S[t].theta) + c_t); thw keeps the inner wrap
+      if ((c.p->flags & kFlagBounded) && state_in_bounds(c, state))
+        heading_chain<true>(state[2], wdt, thw, ths, T);
+      else
+        heading_chain<false>(state[2], wdt, thw, ths, T);
     }
     __syncthreads();
     for (int t = tid; t < T; t += nt) {
@@ -218,11 +249,7 @@ struct Navigation2D {  // src/envs/navigation_2d.py:218-279
       float* qs = isx ? xs : ys;
       const float* dq = isx ? dx : dy;
       const float lo = isx ? p[6] : p[8], hi = isx ? p[7] : p[9];
-      qs[0] = q;
-      for (int t = 0; t < T; ++t) {
-        q = clampf(q + dq[t], lo, hi);
-        qs[t + 1] = q;
-      }
+      serial_chain(q, dq, qs, T, [lo, hi](float x, float d) { return clampf(x + d, lo, hi); });
     }
     __syncthreads();
     for (int t = tid; t <= T; t += nt) {
@@ -237,7 +264,7 @@ struct Navigation2D {  // src/envs/navigation_2d.py:218-279
 // ---------------------------------------------------------------------------
 struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
   static constexpr int DS = 4, DU = 2, kMaps = 2;
-  static constexpr bool kRefPath = true, kParallelTail = true;
+  static constexpr bool kRefPath = true, kParallelTail = true, kHasBounded = true;
   struct Ctx {
     MapView obstacle, lane;
     const ModelParams* p;  // a_min a_max s_min s_max L v_max x_lo x_hi y_lo y_hi dt Qc Ql Qv Qo Qin Qdin
@@ -245,29 +272,35 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
     const float* ref_v;    // per stage t: target speed reference_path[t, 3]
   };
   __device__ static __forceinline__ float yaw_rate(const ModelParams& mp, float v, float tan_steer) {
-    float r = v * tan_steer;  // racing_env.py:352  v * tan(steer) / L
-    return (mp.flags & kFlagUnitWheelbase) ? r : r / mp.v[4];
+    // racing_env.py:352  v * tan(steer) / L ; the division by the wheelbase goes through the proven
+    // exact 3-instruction form (trivially exact for L == 1) or the true division
+    return div_exact(v * tan_steer, ExactDiv{mp.v[4], mp.v[17], mp.flags & kFlagUnitWheelbase});
   }
+  // kBounded: host-proved steering / yaw bounds + kernel-checked initial state, see kFlagBounded.
+  template <bool kBounded = false>
   __device__ static __forceinline__ void step(const Ctx& c, float (&s)[DS], const float (&u)[DU], float (&seen)[DS]) {
     const float* p = c.p->v;
 #pragma unroll
     for (int i = 0; i < DS; ++i) seen[i] = s[i];
     float accel = clampf(u[0], p[0], p[1]);  // :345-346
     float steer = clampf(u[1], p[2], p[3]);
-    float th = wrap_angle(s[2]);  // :347
+    float th = kBounded ? wrap_angle_bounded(s[2]) : wrap_angle(s[2]);  // :347
     float st, ct;
     sincosf(th, &st, &ct);
     float dx = s[3] * ct;  // :349-352
     float dy = s[3] * st;
-    float dth = yaw_rate(*c.p, s[3], tanf(steer));
+    float dth = yaw_rate(*c.p, s[3], kBounded ? tan_quarter(steer) : tanf(steer));
     float nx = s[0] + dx * p[10];  // :354-357
     float ny = s[1] + dy * p[10];
-    float nth = wrap_angle(th + dth * p[10]);
+    float nth = kBounded ? wrap_angle_bounded(th + dth * p[10]) : wrap_angle(th + dth * p[10]);
     float nv = s[3] + accel * p[10];
     s[0] = clampf(nx, p[6], p[7]);  // :360-368
     s[1] = clampf(ny, p[8], p[9]);
     s[2] = nth;
     s[3] = clampf(nv, -p[5], p[5]);
+  }
+  __device__ static __forceinline__ bool state_in_bounds(const Ctx& c, const float* state) {
+    return fabsf(state[2]) < 9.0f && fabsf(state[3]) <= c.p->v[5];  // heading range, |v| <= v_max
   }
   __device__ static __forceinline__ float cost(const Ctx& c, const float (&s)[DS], const float (&u)[DU],
                                                const float (&pu)[DU], int t) {
@@ -305,29 +338,22 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
           *dy = dx + S, *xs = dy + S, *ys = xs + S;
     for (int t = tid; t < T; t += nt) {
       adt[t] = clampf(opt[2 * t], p[0], p[1]) * p[10];
-      tn[t] = tanf(clampf(opt[2 * t + 1], p[2], p[3]));
+      const float st = clampf(opt[2 * t + 1], p[2], p[3]);
+      tn[t] = (c.p->flags & kFlagBounded) ? tan_quarter(st) : tanf(st);
     }
     __syncthreads();
     if (tid == 0) {
-      float v = state[3];
-      vs[0] = v;
-      for (int t = 0; t < T; ++t) {
-        v = clampf(v + adt[t], -p[5], p[5]);
-        vs[t + 1] = v;
-      }
+      const float vm = p[5];
+      serial_chain(state[3], adt, vs, T, [vm](float v, float a) { return clampf(v + a, -vm, vm); });
     }
     __syncthreads();
     for (int t = tid; t < T; t += nt) cdt[t] = yaw_rate(*c.p, vs[t], tn[t]) * p[10];
     __syncthreads();
-    if (tid == 0) {
-      float th = state[2];
-      ths[0] = th;
-      for (int t = 0; t < T; ++t) {
-        float w = wrap_angle(th);
-        thw[t] = w;
-        th = wrap_angle(w + cdt[t]);
-        ths[t + 1] = th;
-      }
+    if (tid == 0) {  // heading: S[t+1].theta = wrap(wrap(S[t].theta) + c_t); thw keeps the inner wrap
+      if ((c.p->flags & kFlagBounded) && state_in_bounds(c, state))
+        heading_chain<true>(state[2], cdt, thw, ths, T);
+      else
+        heading_chain<false>(state[2], cdt, thw, ths, T);
     }
     __syncthreads();
     for (int t = tid; t < T; t += nt) {
@@ -343,11 +369,7 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
       float* qs = isx ? xs : ys;
       const float* dq = isx ? dx : dy;
       const float lo = isx ? p[6] : p[8], hi = isx ? p[7] : p[9];
-      qs[0] = q;
-      for (int t = 0; t < T; ++t) {
-        q = clampf(q + dq[t], lo, hi);
-        qs[t + 1] = q;
-      }
+      serial_chain(q, dq, qs, T, [lo, hi](float x, float d) { return clampf(x + d, lo, hi); });
     }
     __syncthreads();
     for (int t = tid; t <= T; t += nt) {

@@ -167,10 +167,12 @@ class MPPI(nn.Module):
 
     # ------------------------------------------------------------------ plumbing
     def __del__(self):
-        h, self._h = getattr(self, "_h", None), None
-        if h:
+        d = self.__dict__  # plain dict access: nn.Module.__setattr__ is unusable during interpreter shutdown
+        h, lib = d.get("_h"), d.get("_lib")
+        d["_h"] = None
+        if h and lib is not None:
             try:
-                self._lib.mppi_destroy(h)
+                lib.mppi_destroy(h)
             except Exception:
                 pass
 

@@ -248,3 +248,39 @@ def test_cell_index_division_is_proven_exact():
         print(f"slot {slot}: fast_division={fast.value} mismatches={bad.value} model_flags={flags.value}")
     assert flags.value & 1  # both racing grids share one geometry -> one cell index per stage
     assert flags.value & 2  # unit wheelbase
+
+
+def test_bounded_helpers_are_bit_identical_over_their_whole_range():
+    """tan_quarter == tanf on |x| <= 0.78, wrap_angle_bounded == wrap_angle on |x| < 9, lean floored
+    remainder == fmodf form: checked on the device for EVERY fp32 input of the range."""
+    import ctypes as C
+
+    from mppi_playground_b200 import _capi
+
+    bad = (C.c_uint64 * 3)()
+    _capi.check(_capi.load().mppi_selftest(0, bad))
+    assert list(bad) == [0, 0, 0], f"mismatches tan/wrap/remainder = {list(bad)}"
+
+
+def test_bounded_and_general_rollouts_agree_bit_for_bit():
+    """The bounded pass-1 loop (tan_quarter, wrap_angle_bounded) and the general loop give identical
+    solves. The general loop is forced by widening the ENV's steering clamp beyond pi/4 (that clears
+    kFlagBounded); the solver's own control bounds stay at +-0.25, so the sampled controls - and every
+    intermediate value - are the same in both runs."""
+    import mppi_playground_b200 as eng
+
+    cfg = dict(model="racing", horizon=40, num_samples=2048, sigmas=[0.5, 0.1], lambda_=1.0)
+    env = fx.load_env_racing()
+    ref, _ = eng.racing_reference_path(env.start_state, env.center_path, 0, 40)
+    model, solver = build_engine(cfg)
+    model.reference_path_tensor = ref
+    bounded_action, bounded_states = solver.forward(env.start_state)
+    bounded_costs = solver._costs
+
+    model2, solver2 = build_engine(cfg)
+    model2.u_min, model2.u_max = torch.tensor([-2.0, -0.9]), torch.tensor([2.0, 0.9])  # env clamp only
+    model2.reference_path_tensor = ref
+    general_action, general_states = solver2.forward(env.start_state)
+    assert torch.equal(solver2._costs, bounded_costs)
+    assert torch.equal(general_action, bounded_action)
+    assert torch.equal(general_states, bounded_states)

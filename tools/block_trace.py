@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""Per-block phase timeline of the fused solve kernel at the bench workload (profiling aid).
+   python tools/block_trace.py [--block-size N]   -> prints phase durations (us) across blocks."""
+import argparse
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import bench  # noqa: E402
+import mppi_playground_b200 as eng  # noqa: E402
+from engine_util import build_engine  # noqa: E402
+from mppi_playground_b200 import _capi  # noqa: E402
+from oracle import fixtures as fx  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--block-size", type=int, default=0)
+ap.add_argument("--solves", type=int, default=30)
+a = ap.parse_args()
+env = fx.load_env_racing()
+model, solver = build_engine(bench.CFG, block_size=a.block_size)
+state, cind = env.start_state.clone(), 0
+lib, h = solver._lib, solver._h
+for s in range(a.solves):
+    ref, cind = eng.racing_reference_path(state, env.center_path, cind, bench.HORIZON, v_max=env.v_max)
+    model.reference_path_tensor = ref
+    if s == a.solves - 1:
+        _capi.check(lib.mppi_block_trace(h, 1, None, 0))
+    _, seq = solver.forward(state)
+    state = seq[0, 1].cpu()
+info = solver.launch_info()
+g = info["grid"]
+buf = (C.c_uint64 * (g * 8))()
+_capi.check(lib.mppi_block_trace(h, 1, buf, g))
+t = np.array(buf, dtype=np.uint64).reshape(g, 8).astype(np.int64)
+t0 = t[:, 0].min()
+rel = (t - t0) / 1e3
+names = ["start", "staged", "costs", "weights", "partial", "combined", "finished", "pre-rollout"]
+print("launch", info)
+for i, n in enumerate(names):
+    col = rel[:, i][t[:, i] > 0]
+    if len(col):
+        print(f"{n:9s} n={len(col):4d} min={col.min():8.2f} median={np.median(col):8.2f} max={col.max():8.2f} us")
+d = rel[:, 2] - rel[:, 1]
+print("pass1 (staged->costs) per block: min %.2f median %.2f max %.2f us" % (d.min(), np.median(d), d.max()))
+d = rel[:, 4] - rel[:, 3]
+print("pass2 (weights->partial) per block: min %.2f median %.2f max %.2f us" % (d.min(), np.median(d), d.max()))
