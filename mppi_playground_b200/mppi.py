@@ -255,21 +255,32 @@ class MPPI(nn.Module):
 
     def _sharded_solve(self, st, ref, noise, action, states, s) -> None:
         """K split over ranks: roll the shard, exchange the shard partials
-        ((2 + T*du)-ish floats per rank), finish redundantly on every rank."""
+        ((8 + T*du) floats per rank), finish redundantly on every rank."""
         import torch.distributed as dist
 
-        lib, h = self._lib, self._h
-        _capi.check(lib.mppi_shard_rollout(h, st.data_ptr(), _ptr(ref), _ptr(noise), s))
+        self._shard_stage_rollout(st, ref, noise, s)
         if self._auto_lambda in ("LBPS", "ESSPS"):
-            costs = self._wrap_costs()
-            all_costs = gather_shards(costs, self._num_samples, self._world, self._pg)
-            _capi.check(lib.mppi_shard_lambda(h, all_costs.data_ptr(), s))
+            all_costs = gather_shards(self._wrap_costs(), self._num_samples, self._world, self._pg)
+            self._shard_stage_lambda(all_costs, s)
         part = self._wrap_partial()
         gathered = torch.empty(self._world * part.numel(), device=self._device, dtype=torch.float32)
         dist.all_gather_into_tensor(gathered, part, group=self._pg)
+        self._shard_stage_finish(gathered, st, action, states, s)
+
+    # the three stages of a sharded solve (mppi_shard_* of the C ABI); also driven in-process by
+    # solve_shards_inprocess() when one process owns several shards
+    def _shard_stage_rollout(self, st, ref, noise, s) -> None:
+        _capi.check(self._lib.mppi_shard_rollout(self._h, st.data_ptr(), _ptr(ref), _ptr(noise), s))
+
+    def _shard_stage_lambda(self, all_costs: torch.Tensor, s) -> None:
+        self._gathered_costs = all_costs
+        _capi.check(self._lib.mppi_shard_lambda(self._h, all_costs.data_ptr(), s))
+
+    def _shard_stage_finish(self, gathered: torch.Tensor, st, action, states, s) -> None:
         self._gathered = gathered
-        _capi.check(lib.mppi_shard_finish(h, gathered.data_ptr(), self._world, st.data_ptr(), action.data_ptr(),
-                                          states.data_ptr(), s))
+        n = gathered.numel() // self._lib.mppi_partial_floats(self._h)
+        _capi.check(self._lib.mppi_shard_finish(self._h, gathered.data_ptr(), n, st.data_ptr(), action.data_ptr(),
+                                                states.data_ptr(), s))
 
     def _wrap(self, ptr: int, n: int) -> torch.Tensor:
         return wrap_device_memory(ptr, n, self._device)
@@ -417,6 +428,45 @@ class MPPI(nn.Module):
         half = (window_size - 1) // 2
         idx = torch.arange(-half, half + 1, dtype=torch.float32)
         return torch.linalg.pinv(torch.vander(idx, N=poly_order + 1, increasing=True))[0]
+
+
+def solve_shards_inprocess(solvers, state, noise: Optional[torch.Tensor] = None):
+    """Drive ``world`` shard solvers (``MPPI(..., shard=(r, world))``) that live in ONE process - one
+    per GPU, or several on one GPU - through a sharded solve: stage 1 on every shard, concatenate the
+    partials (device-to-device copies instead of a collective), finish on every shard. Returns the
+    per-shard ``(action_seq, state_seq)`` list; all entries agree."""
+    world = len(solvers)
+    ctx = []
+    for sv in solvers:
+        assert sv._world == world
+        st = sv._device_state(state)
+        sv._bind_maps(required=True)
+        sv._refresh_params()
+        ref = sv._device_refpath()
+        nz = None
+        if noise is not None:
+            nz = torch.as_tensor(noise)[sv._shard_lo: sv._shard_lo + sv._local_samples]
+            nz = nz.detach().to(sv._device, torch.float32).contiguous()
+        sv._noise_keepalive = (nz, st, ref)
+        s = _stream_ptr(sv._device)
+        sv._shard_stage_rollout(st, ref, nz, s)
+        ctx.append((st, s))
+    if solvers[0]._auto_lambda in ("LBPS", "ESSPS"):
+        for sv in solvers:
+            torch.cuda.current_stream(sv._device).synchronize()
+        for sv, (st, s) in zip(solvers, ctx):
+            all_costs = torch.cat([o._wrap_costs().to(sv._device) for o in solvers]).contiguous()
+            sv._shard_stage_lambda(all_costs, s)
+    for sv in solvers:
+        torch.cuda.current_stream(sv._device).synchronize()
+    out = []
+    for sv, (st, s) in zip(solvers, ctx):
+        gathered = torch.cat([o._wrap_partial().to(sv._device) for o in solvers]).contiguous()
+        action = torch.empty(sv._horizon, sv._dim_control, device=sv._device)
+        states = torch.empty(sv._horizon + 1, sv._dim_state, device=sv._device)
+        sv._shard_stage_finish(gathered, st, action, states, s)
+        out.append((action, states.view(1, sv._horizon + 1, sv._dim_state)))
+    return out
 
 
 # ---------------------------------------------------------------------- sharding helpers (host logic, CPU-testable)

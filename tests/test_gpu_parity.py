@@ -284,3 +284,48 @@ def test_bounded_and_general_rollouts_agree_bit_for_bit():
     assert torch.equal(solver2._costs, bounded_costs)
     assert torch.equal(general_action, bounded_action)
     assert torch.equal(general_states, bounded_states)
+
+
+SHARD_CASES = [
+    dict(model="racing", horizon=80, num_samples=8192, sigmas=[0.5, 0.1], lambda_=1.0, use_sg_filter=True),
+    dict(model="navigation2d", horizon=30, num_samples=3000, sigmas=[0.5, 0.5], lambda_="ESSPS"),
+    dict(model="navigation2d", horizon=30, num_samples=2050, sigmas=[0.5, 0.5], lambda_="LBPS", lbps_delta=0.5),
+    dict(model="cartpole", horizon=20, num_samples=4096, u_min=[-3.0], u_max=[3.0], sigmas=[1.0], lambda_="MPO",
+         state0=[0.0, 0.1, 0.05, -0.1]),
+]
+
+
+@pytest.mark.parametrize("cfg", SHARD_CASES, ids=lambda c: f"{c['model']}-{c['lambda_']}")
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_solve_equals_single_solve(cfg, world):
+    """K split over `world` shard handles (here all on one GPU, partials concatenated in-process)
+    must reproduce the unsharded solve: the sampler is keyed by the GLOBAL sample id, the softmax
+    partials combine exactly, the lambda search runs on the gathered costs."""
+    import mppi_playground_b200 as eng
+    from mppi_playground_b200.mppi import solve_shards_inprocess
+
+    model, single = build_engine(cfg)
+    shards = []
+    for r in range(world):
+        m, sv = build_engine(cfg, shard=(r, world))
+        shards.append((m, sv))
+    state = _start_state(cfg)
+    env = fx.load_env_racing() if cfg["model"] == "racing" else None
+    cind = 0
+    for s in range(3):
+        if env is not None:
+            ref, cind = eng.racing_reference_path(state, env.center_path, cind, cfg["horizon"], v_max=env.v_max)
+            for m in [model] + [m for m, _ in shards]:
+                m.reference_path_tensor = ref
+        a1, s1 = single.forward(state)
+        outs = solve_shards_inprocess([sv for _, sv in shards], state)
+        costs = torch.cat([sv._costs for _, sv in shards])
+        assert torch.equal(costs, single._costs)  # same samples, same noise, same arithmetic
+        for a, st in outs:
+            assert torch.equal(a, outs[0][0]) and torch.equal(st, outs[0][1])  # every shard finishes alike
+            np.testing.assert_allclose(a.cpu().numpy(), a1.cpu().numpy(), rtol=2e-5, atol=2e-6)
+            np.testing.assert_allclose(st.cpu().numpy(), s1.cpu().numpy(), rtol=2e-5, atol=2e-5)
+        lam1 = single._lambdas()
+        for _, sv in shards:
+            np.testing.assert_allclose(sv._lambdas(), lam1, rtol=1e-6)
+        state = s1[0, 1].cpu()
