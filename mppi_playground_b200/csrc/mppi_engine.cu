@@ -342,11 +342,15 @@ void refresh_model_flags(MppiHandle* h) {
     const double smax = std::max(fabs((double)v[2]), fabs((double)v[3]));
     if (smax <= 0.78 && v[4] > 0.0f) {
       const double yaw = fabs((double)v[5]) * tan(smax) / (double)v[4] * fabs((double)v[10]);
-      if (yaw < 6.0) flags |= kFlagBounded;
+      if (yaw < 6.0 && (flags & kFlagSameMapGeometry) && b.map_fastdiv[0] && h->wheelbase_exact &&
+          fabsf(b.map_ox[0]) >= 1e-20f && fabsf(b.map_oy[0]) >= 1e-20f)
+        flags |= kFlagBounded;
     }
   } else if (h->cfg.model == MPPI_MODEL_NAVIGATION2D) {
     const double wmax = std::max(fabs((double)v[2]), fabs((double)v[3]));
-    if (wmax * fabs((double)v[10]) < 6.0) flags |= kFlagBounded;
+    if (wmax * fabs((double)v[10]) < 6.0 && h->map_set[0] && b.map_fastdiv[0] && fabsf(b.map_ox[0]) >= 1e-20f &&
+        fabsf(b.map_oy[0]) >= 1e-20f)
+      flags |= kFlagBounded;
   }
   b.mp.flags = flags;
 }

@@ -90,8 +90,9 @@ __host__ __device__ inline unsigned align_up(unsigned x, unsigned a) { return (x
 
 // floats of scratch finish_solve needs: N (doubles) | opt | y | scales | Combined | tail rollout
 __host__ __device__ inline unsigned finish_scratch_core(int E_pad, int T, int tail_per_step) {
-  return (unsigned)E_pad * 20 + 256 * 4 + 64 + (unsigned)E_pad * 8 * kMaxSegments +
-         (unsigned)tail_per_step * (unsigned)(T + 1) * 4;
+  return align_up((unsigned)E_pad * 20 + 256 * 4 + 64 + (unsigned)E_pad * 8 * kMaxSegments +
+                      (unsigned)tail_per_step * (unsigned)(T + 1) * 4,
+                  16);
 }
 
 __host__ __device__ inline SmemLayout make_layout(int n_maps, const unsigned* map_bytes, int T, int E_pad,
@@ -404,6 +405,15 @@ __device__ __forceinline__ void model_step(const typename M::Ctx& ctx, float (&s
     M::step(ctx, s, u, seen);
 }
 
+template <class M, bool kBounded>
+__device__ __forceinline__ float model_cost(const typename M::Ctx& ctx, const float (&s)[M::DS], const float (&u)[M::DU],
+                                            const float (&pu)[M::DU], int t) {
+  if constexpr (M::kHasBounded)
+    return M::template cost<kBounded>(ctx, s, u, pu, t);
+  else
+    return M::cost(ctx, s, u, pu, t);
+}
+
 template <class M, bool kInject, bool kBounded>
 __device__ __forceinline__ float rollout_cost(const SolveParams& p, const typename M::Ctx& ctx, const float* nominal,
                                            bool zero_mean, uint32_t k_lo, uint32_t k_hi, long long k_local) {
@@ -433,7 +443,7 @@ __device__ __forceinline__ float rollout_cost(const SolveParams& p, const typena
 #pragma unroll
         for (int d = 0; d < DU; ++d) pu[d] = (t == 0) ? u[d] : up[d];
         model_step<M, kBounded>(ctx, s, u, seen);      // S[:, t+1] = dynamics(S[:, t], U[:, t])   (mppi.py:282-286)
-        total = total + M::cost(ctx, seen, u, pu, t);  // stage cost on the stored S[:, t]        (mppi.py:307-311)
+        total = total + model_cost<M, kBounded>(ctx, seen, u, pu, t);  // stage cost on S[:, t]  (mppi.py:307-311)
 #pragma unroll
         for (int d = 0; d < DU; ++d) {
           upp[d] = up[d];
@@ -449,7 +459,7 @@ __device__ __forceinline__ float rollout_cost(const SolveParams& p, const typena
     zero[d] = 0.0f;
     pa[d] = (T >= 2) ? upp[d] : up[d];
   }
-  return total + M::cost(ctx, s, zero, pa, T - 1);  // mppi.py:333-336
+  return total + model_cost<M, kBounded>(ctx, s, zero, pa, T - 1);  // mppi.py:333-336
 }
 
 __device__ __forceinline__ void stamp(const SolveParams& p, int slot) {

@@ -56,6 +56,16 @@ __device__ __forceinline__ int map_cell(float x, const ExactDiv& cell, float ori
   return __float2int_rn(div_exact(x, cell) + origin);
 }
 
+// Same index when the divisor passed the exhaustive check and |x| <= 1e30 (callers guarantee the upper
+// bound: rolled-out positions are clamped to the map limits and the initial state is range-checked).
+// For |x| < 1e-30 the quotient is below half an ulp of any origin >= 1e-22 (or the origin is 0), so the
+// index is round(origin) exactly; this keeps the hot loop free of the division's slow-path call.
+__device__ __forceinline__ int map_cell_bounded(float x, const ExactDiv& cell, float origin) {
+  float q = x * cell.r;
+  q = fmaf(fmaf(-q, cell.c, x), cell.r, q);
+  return __float2int_rn((fabsf(x) >= kFastDivMin) ? q + origin : origin);
+}
+
 __device__ __forceinline__ float map_value(const MapView& m, int ix, int iy) {
   bool oob = (ix < 0) | (ix >= m.W) | (iy < 0) | (iy >= m.H);  // :183-190
   ix = min(max(ix, 0), m.W - 1);                                // :191-192
@@ -205,14 +215,18 @@ struct Navigation2D {  // src/envs/navigation_2d.py:218-279
     s[2] = nth;
   }
   __device__ static __forceinline__ bool state_in_bounds(const Ctx&, const float* state) {
-    return fabsf(state[2]) < 9.0f;  // |theta + pi| < 4 pi with margin
+    return fabsf(state[2]) < 9.0f && fabsf(state[0]) <= kFastDivMax && fabsf(state[1]) <= kFastDivMax;
   }
+  template <bool kBounded = false>
   __device__ static __forceinline__ float cost(const Ctx& c, const float (&s)[DS], const float (&)[DU],
                                                const float (&)[DU], int) {
     const float* p = c.p->v;
     float dx = s[0] - p[4], dy = s[1] - p[5];
-    float goal = sqrtf(dx * dx + dy * dy);              // :269
-    return goal + p[11] * map_lookup(c.map, s[0], s[1]);  // :271-277
+    float goal = sqrtf(dx * dx + dy * dy);  // :269
+    float occ = kBounded ? map_value(c.map, map_cell_bounded(s[0], c.map.cell, c.map.ox),
+                                     map_cell_bounded(s[1], c.map.cell, c.map.oy))
+                         : map_lookup(c.map, s[0], s[1]);
+    return goal + p[11] * occ;  // :271-277
   }
   // Optimal-trajectory rollout by one block (mppi.py:508-524). Same operations on the same values as
   // T calls of step(); only the schedule differs: the heading chain is the one serial part, the
@@ -271,10 +285,18 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
     const float4* ref;     // per stage t: (x, y, sin yaw, cos yaw) of reference_path[t]
     const float* ref_v;    // per stage t: target speed reference_path[t, 3]
   };
+  template <bool kBounded = false>
   __device__ static __forceinline__ float yaw_rate(const ModelParams& mp, float v, float tan_steer) {
     // racing_env.py:352  v * tan(steer) / L ; the division by the wheelbase goes through the proven
     // exact 3-instruction form (trivially exact for L == 1) or the true division
-    return div_exact(v * tan_steer, ExactDiv{mp.v[4], mp.v[17], mp.flags & kFlagUnitWheelbase});
+    const float r = v * tan_steer;
+    if (kBounded) {  // kFlagBounded implies the proven divisor; |r| <= v_max tan(0.78) << 1e30, and a
+                     // quotient of |r| < 1e-30 only feeds `theta + q * dt`, where it vanishes like r itself
+      float q = r * mp.v[17];
+      q = fmaf(fmaf(-q, mp.v[4], r), mp.v[17], q);
+      return (fabsf(r) >= kFastDivMin) ? q : r;
+    }
+    return div_exact(r, ExactDiv{mp.v[4], mp.v[17], mp.flags & kFlagUnitWheelbase});
   }
   // kBounded: host-proved steering / yaw bounds + kernel-checked initial state, see kFlagBounded.
   template <bool kBounded = false>
@@ -289,7 +311,7 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
     sincosf(th, &st, &ct);
     float dx = s[3] * ct;  // :349-352
     float dy = s[3] * st;
-    float dth = yaw_rate(*c.p, s[3], kBounded ? tan_quarter(steer) : tanf(steer));
+    float dth = yaw_rate<kBounded>(*c.p, s[3], kBounded ? tan_quarter(steer) : tanf(steer));
     float nx = s[0] + dx * p[10];  // :354-357
     float ny = s[1] + dy * p[10];
     float nth = kBounded ? wrap_angle_bounded(th + dth * p[10]) : wrap_angle(th + dth * p[10]);
@@ -300,8 +322,10 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
     s[3] = clampf(nv, -p[5], p[5]);
   }
   __device__ static __forceinline__ bool state_in_bounds(const Ctx& c, const float* state) {
-    return fabsf(state[2]) < 9.0f && fabsf(state[3]) <= c.p->v[5];  // heading range, |v| <= v_max
+    return fabsf(state[2]) < 9.0f && fabsf(state[3]) <= c.p->v[5] && fabsf(state[0]) <= kFastDivMax &&
+           fabsf(state[1]) <= kFastDivMax;  // heading range, |v| <= v_max, finite position
   }
+  template <bool kBounded = false>
   __device__ static __forceinline__ float cost(const Ctx& c, const float (&s)[DS], const float (&u)[DU],
                                                const float (&pu)[DU], int t) {
     const float* p = c.p->v;
@@ -313,7 +337,11 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
     float dv = s[3] - c.ref_v[t];
     float vel = p[13] * (dv * dv);                           // :141-143
     float occ;                                               // :146-150
-    if (c.p->flags & kFlagSameMapGeometry) {  // one cell index serves both grids
+    if (kBounded) {  // kFlagBounded implies: one shared geometry, proven exact division
+      int ix = map_cell_bounded(s[0], c.obstacle.cell, c.obstacle.ox);
+      int iy = map_cell_bounded(s[1], c.obstacle.cell, c.obstacle.oy);
+      occ = map_value(c.obstacle, ix, iy) + map_value(c.lane, ix, iy);
+    } else if (c.p->flags & kFlagSameMapGeometry) {  // one cell index serves both grids
       int ix = map_cell(s[0], c.obstacle.cell, c.obstacle.ox), iy = map_cell(s[1], c.obstacle.cell, c.obstacle.oy);
       occ = map_value(c.obstacle, ix, iy) + map_value(c.lane, ix, iy);
     } else {

@@ -320,7 +320,10 @@ def test_sharded_solve_equals_single_solve(cfg, world):
         a1, s1 = single.forward(state)
         outs = solve_shards_inprocess([sv for _, sv in shards], state)
         costs = torch.cat([sv._costs for _, sv in shards])
-        assert torch.equal(costs, single._costs)  # same samples, same noise, same arithmetic
+        if s == 0:
+            assert torch.equal(costs, single._costs)  # same samples, same noise, same arithmetic
+        else:  # the carried warm starts agree to summation order only, so do the next solves' costs
+            np.testing.assert_allclose(costs.cpu().numpy(), single._costs.cpu().numpy(), rtol=2e-5, atol=1e-5)
         for a, st in outs:
             assert torch.equal(a, outs[0][0]) and torch.equal(st, outs[0][1])  # every shard finishes alike
             np.testing.assert_allclose(a.cpu().numpy(), a1.cpu().numpy(), rtol=2e-5, atol=2e-6)
