@@ -144,6 +144,8 @@ struct MppiHandle {
   bool solved = false;
   const float* last_noise = nullptr;
   int last_launches = 0;
+  const float* inline_state = nullptr;  // set for the duration of a host-call solve
+  const float* inline_ref = nullptr;
   bool timing = false;
   unsigned long long* d_trace = nullptr;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
@@ -282,6 +284,12 @@ int make_params(MppiHandle* h, const float* d_state, const float* d_refpath, con
   p.key.solve_hi = (uint32_t)(h->solve_count >> 32);
   p.n_shards = n_shards;
   p.trace = h->d_trace;
+  p.inline_inputs = 0;
+  if (h->inline_state) {
+    p.inline_inputs = 1;
+    for (int i = 0; i < h->mi.ds; ++i) p.state_inline[i] = h->inline_state[i];
+    if (h->inline_ref) memcpy(p.ref_inline, h->inline_ref, (size_t)(h->cfg.horizon + 1) * 16);
+  }
   *out = p;
   return MPPI_OK;
 }
@@ -453,7 +461,7 @@ int mppi_create(const MppiConfig* cfg, MppiHandle** out) {
   // staging for mppi_solve_host: state | refpath | action | state_seq
   size_t stage_floats = 8 + (size_t)(T + 1) * 4 + (size_t)h->E_pad + (size_t)(T + 1) * DS + 8;
   ALLOC(h->d_stage, stage_floats * 4);
-  if (cudaMallocHost((void**)&h->h_pinned, stage_floats * 4) != cudaSuccess)
+  if (cudaHostAlloc((void**)&h->h_pinned, stage_floats * 4, cudaHostAllocMapped) != cudaSuccess)
     return cleanup(fail(MPPI_ERR_CUDA, "cudaMallocHost failed"));
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess)
     return cleanup(fail(MPPI_ERR_CUDA, "cudaStreamCreate failed"));
@@ -650,23 +658,34 @@ int mppi_solve_host(MppiHandle* h, const float* h_state, const float* h_refpath,
   const int T = h->cfg.horizon, DS = h->mi.ds;
   const size_t n_state = 8, n_ref = (size_t)(T + 1) * 4, n_act = (size_t)h->E_pad, n_seq = (size_t)(T + 1) * DS;
   float* hp = h->h_pinned;
-  memcpy(hp, h_state, DS * 4);
-  size_t in_floats = n_state;
-  if (h->mi.refpath) {
-    memcpy(hp + n_state, h_refpath, n_ref * 4);
-    in_floats += n_ref;
-  }
   cudaStream_t st = h->own_stream;
-  CUDA_TRY(cudaMemcpyAsync(h->d_stage, hp, in_floats * 4, cudaMemcpyHostToDevice, st));
-  float* d_act = h->d_stage + n_state + n_ref;
+  // outputs: the finishing block stores straight into the pinned, device-mapped staging buffer
+  // (UVA: the pinned host pointer is valid on the device), so no D2H copy is enqueued
+  float* d_act = hp + n_state + n_ref;
   float* d_seq = d_act + n_act;
-  int rc = solve_impl(h, h->d_stage, h->mi.refpath ? h->d_stage + n_state : nullptr, nullptr, d_act, d_seq, st);
+  int rc;
+  const bool inline_ok = (!h->mi.refpath || n_ref <= (size_t)kInlineRefFloats) &&
+                         !(h->cfg.lambda_mode == MPPI_LAMBDA_LBPS || h->cfg.lambda_mode == MPPI_LAMBDA_ESSPS);
+  if (inline_ok) {
+    // inputs: state and reference path ride in the kernel parameter block - no H2D copy either
+    h->inline_state = h_state;
+    h->inline_ref = h->mi.refpath ? h_refpath : nullptr;
+    rc = solve_impl(h, h->d_stage, h->mi.refpath ? h->d_stage + n_state : nullptr, nullptr, d_act, d_seq, st);
+    h->inline_state = h->inline_ref = nullptr;
+  } else {
+    memcpy(hp, h_state, DS * 4);
+    size_t in_floats = n_state;
+    if (h->mi.refpath) {
+      memcpy(hp + n_state, h_refpath, n_ref * 4);
+      in_floats += n_ref;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->d_stage, hp, in_floats * 4, cudaMemcpyHostToDevice, st));
+    rc = solve_impl(h, h->d_stage, h->mi.refpath ? h->d_stage + n_state : nullptr, nullptr, d_act, d_seq, st);
+  }
   if (rc) return rc;
-  float* hout = hp + n_state + n_ref;
-  CUDA_TRY(cudaMemcpyAsync(hout, d_act, (n_act + n_seq) * 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
-  memcpy(h_action_seq, hout, (size_t)h->E * 4);
-  memcpy(h_state_seq, hout + n_act, n_seq * 4);
+  memcpy(h_action_seq, d_act, (size_t)h->E * 4);
+  memcpy(h_state_seq, d_seq, n_seq * 4);
   return MPPI_OK;
 }
 

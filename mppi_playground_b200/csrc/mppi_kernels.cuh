@@ -26,7 +26,8 @@ namespace mppi {
 enum SolveMode : int { kFused = 0, kCosts = 1, kReduce = 2 };
 enum LambdaMode : int { kLamFixed = 0, kLamMPO = 1, kLamLBPS = 2, kLamESSPS = 3 };
 
-constexpr int kMaxSegments = 4;    // combine_partials: threads = segments x entries
+constexpr int kInlineRefFloats = 512;
+constexpr int kMaxSegments = 16;   // combine_partials: threads = segments x float4 columns
 constexpr int kPartialHeader = 8;  // xmax S xmax_tau S_tau Sc_tau cmin cmax pad
 constexpr int kMaxSgWindow = 33;
 
@@ -75,6 +76,10 @@ struct SolveParams {
   float mpo_epsilon;
   int use_sg, sg_window;
   float sg_coeffs[kMaxSgWindow];
+  // host-call path (mppi_solve_host): the solve's inputs travel inside the kernel parameter block
+  int inline_inputs;
+  float state_inline[8];
+  float ref_inline[kInlineRefFloats];  // [T+1,4] when (T+1)*4 <= kInlineRefFloats
   unsigned long long* trace;  // optional [grid, 8] %globaltimer stamps per block (profiling aid), else null
   int n_shards;  // 1: finish inside the kernel
   int E, E_pad, P;
@@ -183,6 +188,14 @@ __device__ __forceinline__ float perturbed_entry(const SolveParams& p, const flo
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void stamp(const SolveParams& p, int slot);
 
+// state / reference path of this solve: device buffers, or the copies inside the parameter block
+__device__ __forceinline__ const float* state_of(const SolveParams& p) {
+  return p.inline_inputs ? p.state_inline : p.state;
+}
+__device__ __forceinline__ const float* refpath_of(const SolveParams& p) {
+  return p.inline_inputs ? p.ref_inline : p.refpath;
+}
+
 struct Combined {
   float xmax, xmax_tau, cmin, cmax;
   double S, S_tau, Sc_tau;
@@ -213,88 +226,133 @@ __device__ __forceinline__ void block_reduce_n(T (&v)[N], Op op, T identity, voi
 
 constexpr int kCombineChunk = 256;  // partials whose rescale factors are staged at once
 
-// Combine n partials (stride P) into `out` + N[E] (shared, doubles).
+// Combine n partials (stride P, rows 32 B aligned) into `out` + N[E_pad] (shared, doubles).
 // Deterministic: fixed traversal order, independent of which block runs it.
-// Work split: the block's threads form (segments x entries); a thread sums its segment of the
-// partials for one entry with 8 independent loads in flight, segments are then added in order.
-__device__ inline void combine_partials(const float* __restrict__ parts, int n, int P, int E, Combined* out,
+// Two block reductions for the header (maxima, then rescaled sums); the numerators are summed by
+// (segment, float4 column) threads with four 16 B loads in flight each, segments added in order.
+__device__ inline void combine_partials(const float* __restrict__ parts, int n, int P, int E_pad, Combined* out,
                                         double* N, float* scale_buf /*[kCombineChunk]*/, void* red,
-                                        double* seg_buf /*[E_pad * kMaxSegments]*/) {
+                                        double* seg_buf /*[kMaxSegments, E_pad]*/) {
   const int tid = threadIdx.x, nt = blockDim.x;
-  float mx[2] = {-INFINITY, -INFINITY}, mn[2] = {INFINITY, INFINITY};  // (xmax, xmax_tau), (cmin, -cmax)
-  for (int b = tid; b < n; b += nt) {
-    const float* q = parts + (size_t)b * P;
-    mx[0] = fmaxf(mx[0], q[0]);
-    mx[1] = fmaxf(mx[1], q[2]);
-    mn[0] = fminf(mn[0], q[5]);
-    mn[1] = fminf(mn[1], -q[6]);
+  // header pass: every thread keeps the header of its first partial in registers so that the common
+  // case n <= blockDim costs ONE global round trip for both reductions and the rescale factors
+  float4 h0 = make_float4(-INFINITY, 0.f, -INFINITY, 0.f), h1 = make_float4(0.f, INFINITY, -INFINITY, 0.f);
+  if (tid < n) {
+    const float4* q = reinterpret_cast<const float4*>(parts + (size_t)tid * P);
+    h0 = q[0];
+    h1 = q[1];
+  }
+  float mx[4] = {h0.x, h0.z, -h1.y, h1.z};  // xmax, xmax_tau, -cmin, cmax
+  for (int b = tid + nt; b < n; b += nt) {
+    const float4* q = reinterpret_cast<const float4*>(parts + (size_t)b * P);
+    const float4 g0 = q[0], g1 = q[1];
+    mx[0] = fmaxf(mx[0], g0.x);
+    mx[1] = fmaxf(mx[1], g0.z);
+    mx[2] = fmaxf(mx[2], -g1.y);
+    mx[3] = fmaxf(mx[3], g1.z);
   }
   block_reduce_n(mx, OpMax(), -INFINITY, red);
-  block_reduce_n(mn, OpMin(), INFINITY, red);
   const float xm = mx[0], xmt = mx[1];
   double sums[3] = {0.0, 0.0, 0.0};
-  for (int b = tid; b < n; b += nt) {
-    const float* q = parts + (size_t)b * P;
-    sums[0] += (double)q[1] * (double)expf(q[0] - xm);
+  const float my_scale = (tid < n) ? expf(h0.x - xm) : 0.0f;
+  if (tid < n) {
+    sums[0] = (double)h0.y * (double)my_scale;
     if (xmt > -INFINITY) {
-      double sc = (double)expf(q[2] - xmt);
-      sums[1] += (double)q[3] * sc;
-      sums[2] += (double)q[4] * sc;
+      double sc = (double)expf(h0.z - xmt);
+      sums[1] = (double)h0.w * sc;
+      sums[2] = (double)h1.x * sc;
     }
   }
-  block_reduce_n(sums, OpAddD(), 0.0, red);
+  for (int b = tid + nt; b < n; b += nt) {
+    const float4* q = reinterpret_cast<const float4*>(parts + (size_t)b * P);
+    const float4 g0 = q[0], g1 = q[1];
+    sums[0] += (double)g0.y * (double)expf(g0.x - xm);
+    if (xmt > -INFINITY) {
+      double sc = (double)expf(g0.z - xmt);
+      sums[1] += (double)g0.w * sc;
+      sums[2] += (double)g1.x * sc;
+    }
+  }
+  if (tid < kCombineChunk) scale_buf[tid] = my_scale;  // rescale factors of the first chunk
+  block_reduce_n(sums, OpAddD(), 0.0, red);            // (its barriers also publish scale_buf)
   // weighted-sum numerators
-  const int n_seg = max(1, min(kMaxSegments, nt / max(E, 1)));
-  const int seg = tid / E, e = tid - seg * E;  // threads beyond n_seg * E idle in the sums
-  const bool worker = (E <= nt) && seg < n_seg;
-  double acc = 0.0;
-  if (E <= nt) {
+  const int n_vec = E_pad / 4;
+  const int n_seg = max(1, min(kMaxSegments, nt / n_vec));
+  const int seg = tid / n_vec, vc = tid - seg * n_vec;
+  if (n_vec <= nt) {
+    const bool worker = seg < n_seg;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
     for (int b0 = 0; b0 < n; b0 += kCombineChunk) {
       const int nb = min(kCombineChunk, n - b0);
-      __syncthreads();
-      if (tid < nb) scale_buf[tid] = expf(parts[(size_t)(b0 + tid) * P] - xm);
-      __syncthreads();
+      if (b0 > 0 || nt < kCombineChunk) {
+        __syncthreads();
+        for (int i = tid; i < nb; i += nt) scale_buf[i] = expf(parts[(size_t)(b0 + i) * P] - xm);
+        __syncthreads();
+      }
       if (worker) {
         const int per = (nb + n_seg - 1) / n_seg, lo = seg * per, hi = min(nb, lo + per);
-        const float* col = parts + (size_t)b0 * P + kPartialHeader + e;
+        const float* col = parts + (size_t)b0 * P + kPartialHeader + 4 * vc;
         int b = lo;
-        for (; b + 8 <= hi; b += 8) {
-          float x[8];
+        for (; b + 12 <= hi; b += 12) {  // 12 x 16 B in flight per thread
+          float4 x[12];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = col[(size_t)(b + j) * P];
+          for (int j = 0; j < 12; ++j) x[j] = *reinterpret_cast<const float4*>(col + (size_t)(b + j) * P);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc += (double)x[j] * (double)scale_buf[b + j];
+          for (int j = 0; j < 12; ++j) {
+            const double sc = (double)scale_buf[b + j];
+            acc[0] += (double)x[j].x * sc;
+            acc[1] += (double)x[j].y * sc;
+            acc[2] += (double)x[j].z * sc;
+            acc[3] += (double)x[j].w * sc;
+          }
         }
-        for (; b < hi; ++b) acc += (double)col[(size_t)b * P] * (double)scale_buf[b];
+        if (b < hi) {  // remainder (< 12 rows): still issued together
+          float4 x[12];
+#pragma unroll
+          for (int j = 0; j < 12; ++j)
+            x[j] = (b + j < hi) ? *reinterpret_cast<const float4*>(col + (size_t)(b + j) * P)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < 12; ++j)
+            if (b + j < hi) {
+              const double sc = (double)scale_buf[b + j];
+              acc[0] += (double)x[j].x * sc;
+              acc[1] += (double)x[j].y * sc;
+              acc[2] += (double)x[j].z * sc;
+              acc[3] += (double)x[j].w * sc;
+            }
+        }
       }
     }
-    if (worker) seg_buf[seg * E + e] = acc;
+    if (worker)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) seg_buf[(size_t)seg * E_pad + 4 * vc + j] = acc[j];
     __syncthreads();
-    if (tid < E) {
+    for (int e = tid; e < E_pad; e += nt) {
       double a = 0.0;
-      for (int sgm = 0; sgm < n_seg; ++sgm) a += seg_buf[sgm * E + tid];
-      N[tid] = a;
+      for (int sgm = 0; sgm < n_seg; ++sgm) a += seg_buf[(size_t)sgm * E_pad + e];
+      N[e] = a;
     }
-  } else {  // more entries than threads: each thread walks its entries (rare: T*du > blockDim)
-    for (int ee = tid; ee < E; ee += nt) N[ee] = 0.0;
+  } else {  // more float4 columns than threads (T*du > 4*blockDim): each thread walks its entries
+    for (int e = tid; e < E_pad; e += nt) N[e] = 0.0;
     for (int b0 = 0; b0 < n; b0 += kCombineChunk) {
       const int nb = min(kCombineChunk, n - b0);
       __syncthreads();
-      if (tid < nb) scale_buf[tid] = expf(parts[(size_t)(b0 + tid) * P] - xm);
+      for (int i = tid; i < nb; i += nt) scale_buf[i] = expf(parts[(size_t)(b0 + i) * P] - xm);
       __syncthreads();
-      for (int ee = tid; ee < E; ee += nt) {
-        double a = N[ee];
+      for (int e = tid; e < E_pad; e += nt) {
+        double a = N[e];
         for (int b = 0; b < nb; ++b)
-          a += (double)parts[(size_t)(b0 + b) * P + kPartialHeader + ee] * (double)scale_buf[b];
-        N[ee] = a;
+          a += (double)parts[(size_t)(b0 + b) * P + kPartialHeader + e] * (double)scale_buf[b];
+        N[e] = a;
       }
     }
   }
   if (tid == 0) {
     out->xmax = xm;
     out->xmax_tau = xmt;
-    out->cmin = mn[0];
-    out->cmax = -mn[1];
+    out->cmin = -mx[2];
+    out->cmax = mx[3];
     out->S = sums[0];
     out->S_tau = sums[1];
     out->Sc_tau = sums[2];
@@ -371,16 +429,17 @@ __device__ inline void finish_solve(const SolveParams& p, const typename M::Ctx&
     sc->cmax = c.cmax;
     if (p.lambda_mode == kLamMPO) mpo_update(p, c);
   }
-  if (tid < DS) p.state_snapshot[tid] = p.state[tid];
+  const float* state = state_of(p);
+  if (tid < DS) p.state_snapshot[tid] = state[tid];
   stamp(p, 7);
   // optimal-trajectory rollout (mppi.py:448-449, 508-524)
   if constexpr (M::kParallelTail) {
     __syncthreads();
-    M::rollout_block(ctx, p.state, opt, T, p.state_seq_out, tail);
+    M::rollout_block(ctx, state, opt, T, p.state_seq_out, tail);
   } else if (tid == 0) {
     float s[DS], seen[DS], u[DU];
 #pragma unroll
-    for (int i = 0; i < DS; ++i) s[i] = p.state[i];
+    for (int i = 0; i < DS; ++i) s[i] = state[i];
     for (int t = 0; t < T; ++t) {
 #pragma unroll
       for (int d = 0; d < DU; ++d) u[d] = opt[t * DU + d];
@@ -420,8 +479,11 @@ __device__ __forceinline__ float rollout_cost(const SolveParams& p, const typena
   constexpr int DS = M::DS, DU = M::DU, SPC = Chunking<DU>::kStepsPerChunk;
   const int T = p.T;
   float s[DS], seen[DS];
+  {
+    const float* state = state_of(p);
 #pragma unroll
-  for (int i = 0; i < DS; ++i) s[i] = __ldg(p.state + i);
+    for (int i = 0; i < DS; ++i) s[i] = state[i];
+  }
   float u[DU], up[DU], upp[DU];
 #pragma unroll
   for (int d = 0; d < DU; ++d) up[d] = upp[d] = 0.0f;
@@ -502,18 +564,20 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ S
     unsigned bytes = p.prev_action_bytes;
     if (kMode != kReduce) {
       for (int i = 0; i < M::kMaps; ++i) bytes += p.map_bytes[i];
-      if (M::kRefPath && p.ref_bulk_ok) bytes += (unsigned)(p.T + 1) * 16;
+      if (M::kRefPath && p.ref_bulk_ok && !p.inline_inputs) bytes += (unsigned)(p.T + 1) * 16;
     }
     mbar_expect_tx(bar, bytes);
     bulk_g2s(nominal, p.prev_action, p.prev_action_bytes, bar);
     if (kMode != kReduce) {
       for (int i = 0; i < M::kMaps; ++i) bulk_g2s(smem + L.map_off[i], p.map_bits[i], p.map_bytes[i], bar);
-      if (M::kRefPath && p.ref_bulk_ok) bulk_g2s(smem + L.refraw_off, p.refpath, (unsigned)(p.T + 1) * 16, bar);
+      if (M::kRefPath && p.ref_bulk_ok && !p.inline_inputs)
+        bulk_g2s(smem + L.refraw_off, p.refpath, (unsigned)(p.T + 1) * 16, bar);
     }
   }
-  if (M::kRefPath && kMode != kReduce && !p.ref_bulk_ok) {
+  if (M::kRefPath && kMode != kReduce && (!p.ref_bulk_ok || p.inline_inputs)) {
     float* raw = reinterpret_cast<float*>(smem + L.refraw_off);
-    for (int i = tid; i < (p.T + 1) * 4; i += blockDim.x) raw[i] = p.refpath[i];
+    const float* src = refpath_of(p);
+    for (int i = tid; i < (p.T + 1) * 4; i += blockDim.x) raw[i] = src[i];
   }
   mbar_wait(bar, 0);
   __syncthreads();
@@ -563,7 +627,7 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ S
     if (active) cost = p.costs[k_local];
   } else if (active) {
     bool bounded = false;  // uniform over the block: model flag + the solve's initial state
-    if constexpr (M::kHasBounded) bounded = (p.mp.flags & kFlagBounded) && M::state_in_bounds(ctx, p.state);
+    if constexpr (M::kHasBounded) bounded = (p.mp.flags & kFlagBounded) && M::state_in_bounds(ctx, state_of(p));
     cost = bounded ? rollout_cost<M, kInject, true>(p, ctx, nominal, zero_mean, k_lo, k_hi, k_local)
                    : rollout_cost<M, kInject, false>(p, ctx, nominal, zero_mean, k_lo, k_hi, k_local);
     p.costs[k_local] = cost;
@@ -681,7 +745,7 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ S
   Combined* comb = reinterpret_cast<Combined*>(scale_buf + 256);
   double* seg_buf = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(comb) + 64);
   float* tail = reinterpret_cast<float*>(seg_buf + (size_t)p.E_pad * kMaxSegments);
-  combine_partials(p.block_partials, (int)gridDim.x, p.P, p.E, comb, Nbuf, scale_buf, red, seg_buf);
+  combine_partials(p.block_partials, (int)gridDim.x, p.P, p.E_pad, comb, Nbuf, scale_buf, red, seg_buf);
   stamp(p, 5);
   if (p.n_shards == 1) {
     finish_solve<M>(p, ctx, *comb, Nbuf, opt, ybuf, tail);
@@ -719,7 +783,7 @@ __global__ void __launch_bounds__(256, 1) finish_kernel(const __grid_constant__ 
   void* red = smem + finish_scratch_core(p.E_pad, p.T, tail_per_step<M>());
   typename M::Ctx ctx{};
   if constexpr (M::kMaps >= 1) ctx.p = &p.mp;
-  combine_partials(parts, n, p.P, p.E, comb, Nbuf, scale_buf, red, seg_buf);
+  combine_partials(parts, n, p.P, p.E_pad, comb, Nbuf, scale_buf, red, seg_buf);
   finish_solve<M>(p, ctx, *comb, Nbuf, opt, ybuf, tail);
 }
 

@@ -80,15 +80,16 @@ __device__ __forceinline__ float map_lookup(const MapView& m, float x, float y) 
   return map_value(m, map_cell(x, m.cell, m.ox), map_cell(y, m.cell, m.oy));
 }
 
-// Heading recurrence of the unicycle / bicycle models, one thread, inputs prefetched 8 at a time:
-// thw[t] = wrap(ths[t]); ths[t+1] = wrap(thw[t] + inc[t]).
-template <bool kBounded>
-__device__ __forceinline__ void heading_chain(float th, const float* inc, float* thw, float* ths, int T) {
+// Heading recurrence of the unicycle / bicycle models, one thread; the per-stage increments inc(t)
+// do not depend on the heading, so they are evaluated eight at a time ahead of the dependent chain:
+// thw[t] = wrap(ths[t]); ths[t+1] = wrap(thw[t] + inc(t)).
+template <bool kBounded, class Inc>
+__device__ __forceinline__ void heading_chain(float th, Inc inc, float* thw, float* ths, int T) {
   ths[0] = th;
   for (int t0 = 0; t0 < T; t0 += 8) {
     float cc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) cc[j] = (t0 + j < T) ? inc[t0 + j] : 0.0f;
+    for (int j = 0; j < 8; ++j) cc[j] = (t0 + j < T) ? inc(t0 + j) : 0.0f;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (t0 + j < T) {
@@ -245,9 +246,9 @@ struct Navigation2D {  // src/envs/navigation_2d.py:218-279
     __syncthreads();
     if (tid == 0) {  // heading: S[t+1].theta = wrap(wrap(S[t].theta) + c_t); thw keeps the inner wrap
       if ((c.p->flags & kFlagBounded) && state_in_bounds(c, state))
-        heading_chain<true>(state[2], wdt, thw, ths, T);
+        heading_chain<true>(state[2], [wdt](int t) { return wdt[t]; }, thw, ths, T);
       else
-        heading_chain<false>(state[2], wdt, thw, ths, T);
+        heading_chain<false>(state[2], [wdt](int t) { return wdt[t]; }, thw, ths, T);
     }
     __syncthreads();
     for (int t = tid; t < T; t += nt) {
@@ -362,26 +363,41 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
                                        float* scratch) {
     const float* p = c.p->v;
     const int tid = threadIdx.x, nt = blockDim.x, S = T + 1;
-    float *adt = scratch, *tn = adt + S, *vs = tn + S, *cdt = vs + S, *ths = cdt + S, *thw = ths + S, *dx = thw + S,
-          *dy = dx + S, *xs = dy + S, *ys = xs + S;
-    for (int t = tid; t < T; t += nt) {
-      adt[t] = clampf(opt[2 * t], p[0], p[1]) * p[10];
-      const float st = clampf(opt[2 * t + 1], p[2], p[3]);
-      tn[t] = (c.p->flags & kFlagBounded) ? tan_quarter(st) : tanf(st);
-    }
-    __syncthreads();
+    float *tn = scratch, *vs = tn + S, *ths = vs + S, *thw = ths + S, *dx = thw + S, *dy = dx + S, *xs = dy + S,
+          *ys = xs + S;
+    const bool bounded = (c.p->flags & kFlagBounded) && state_in_bounds(c, state);
+    // phase 1: thread 0 walks the speed recurrence (it forms accel*dt itself, off the chain) while the
+    // other warps take tan(steer) of every stage
     if (tid == 0) {
-      const float vm = p[5];
-      serial_chain(state[3], adt, vs, T, [vm](float v, float a) { return clampf(v + a, -vm, vm); });
+      const float vm = p[5], a_lo = p[0], a_hi = p[1], dt = p[10];
+      float v = state[3];
+      vs[0] = v;
+      for (int t0 = 0; t0 < T; t0 += 8) {
+        float a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = (t0 + j < T) ? clampf(opt[2 * (t0 + j)], a_lo, a_hi) * dt : 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (t0 + j < T) {
+            v = clampf(v + a[j], -vm, vm);
+            vs[t0 + j + 1] = v;
+          }
+      }
+    } else if (tid >= 32) {
+      for (int t = tid - 32; t < T; t += nt - 32) {
+        const float st = clampf(opt[2 * t + 1], p[2], p[3]);
+        tn[t] = bounded ? tan_quarter(st) : tanf(st);
+      }
     }
     __syncthreads();
-    for (int t = tid; t < T; t += nt) cdt[t] = yaw_rate(*c.p, vs[t], tn[t]) * p[10];
-    __syncthreads();
-    if (tid == 0) {  // heading: S[t+1].theta = wrap(wrap(S[t].theta) + c_t); thw keeps the inner wrap
-      if ((c.p->flags & kFlagBounded) && state_in_bounds(c, state))
-        heading_chain<true>(state[2], cdt, thw, ths, T);
+    // phase 2: heading recurrence; the yaw increments v_t tan(steer_t) / L * dt are formed ahead of it
+    if (tid == 0) {
+      const ModelParams& mp = *c.p;
+      const float dt = p[10];
+      if (bounded)
+        heading_chain<true>(state[2], [&](int t) { return yaw_rate<true>(mp, vs[t], tn[t]) * dt; }, thw, ths, T);
       else
-        heading_chain<false>(state[2], cdt, thw, ths, T);
+        heading_chain<false>(state[2], [&](int t) { return yaw_rate<false>(mp, vs[t], tn[t]) * dt; }, thw, ths, T);
     }
     __syncthreads();
     for (int t = tid; t < T; t += nt) {

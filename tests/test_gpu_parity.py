@@ -326,9 +326,40 @@ def test_sharded_solve_equals_single_solve(cfg, world):
             np.testing.assert_allclose(costs.cpu().numpy(), single._costs.cpu().numpy(), rtol=2e-5, atol=1e-5)
         for a, st in outs:
             assert torch.equal(a, outs[0][0]) and torch.equal(st, outs[0][1])  # every shard finishes alike
-            np.testing.assert_allclose(a.cpu().numpy(), a1.cpu().numpy(), rtol=2e-5, atol=2e-6)
-            np.testing.assert_allclose(st.cpu().numpy(), s1.cpu().numpy(), rtol=2e-5, atol=2e-5)
+            at = 2e-6 if s == 0 else tol_for(cfg["lambda_"])["action"]
+            np.testing.assert_allclose(a.cpu().numpy(), a1.cpu().numpy(), rtol=2e-5, atol=at)
+            np.testing.assert_allclose(st.cpu().numpy(), s1.cpu().numpy(), rtol=2e-5, atol=max(at, 2e-5))
         lam1 = single._lambdas()
+        lam_tol = 1e-6 if s == 0 else tol_for(cfg["lambda_"])["lam_rel"]  # later solves: see the costs note
         for _, sv in shards:
-            np.testing.assert_allclose(sv._lambdas(), lam1, rtol=1e-6)
+            np.testing.assert_allclose(sv._lambdas(), lam1, rtol=lam_tol)
         state = s1[0, 1].cpu()
+
+
+@pytest.mark.parametrize("cfg", [dict(model="racing", horizon=80, num_samples=4096, sigmas=[0.5, 0.1], lambda_=1.0,
+                                      use_sg_filter=True),
+                                 dict(model="navigation2d", horizon=30, num_samples=2048, sigmas=[0.5, 0.5],
+                                      lambda_="ESSPS"),
+                                 dict(model="cartpole", horizon=20, num_samples=1024, u_min=[-3.0], u_max=[3.0],
+                                      sigmas=[1.0], lambda_="MPO", state0=[0.0, 0.1, 0.05, -0.1])],
+                         ids=["racing", "navigation2d-ESSPS", "cartpole-MPO"])
+def test_host_buffer_solve_equals_device_buffer_solve(cfg):
+    """mppi_solve_host (inputs inside the kernel parameter block, outputs stored straight into pinned
+    host memory) returns bit-for-bit what mppi_solve returns for device buffers."""
+    import mppi_playground_b200 as eng
+
+    model_d, dev = build_engine(cfg)
+    model_h, host = build_engine(cfg)
+    state = _start_state(cfg)
+    env = fx.load_env_racing() if cfg["model"] == "racing" else None
+    cind = 0
+    for _ in range(3):
+        ref = None
+        if env is not None:
+            ref, cind = eng.racing_reference_path(state, env.center_path, cind, cfg["horizon"], v_max=env.v_max)
+            model_d.reference_path_tensor = model_h.reference_path_tensor = ref
+        a_d, s_d = dev.forward(state)
+        a_h, s_h = host.solve_host(state.numpy(), None if ref is None else ref.numpy())
+        np.testing.assert_array_equal(a_h, a_d.cpu().numpy())
+        np.testing.assert_array_equal(s_h, s_d.cpu().numpy())
+        state = s_d[0, 1].cpu()
