@@ -230,7 +230,7 @@ constexpr int kCombineChunk = 256;  // partials whose rescale factors are staged
 // Deterministic: fixed traversal order, independent of which block runs it.
 // Two block reductions for the header (maxima, then rescaled sums); the numerators are summed by
 // (segment, float4 column) threads with four 16 B loads in flight each, segments added in order.
-__device__ inline void combine_partials(const float* __restrict__ parts, int n, int P, int E_pad, Combined* out,
+__device__ __noinline__ void combine_partials(const float* __restrict__ parts, int n, int P, int E_pad, Combined* out,
                                         double* N, float* scale_buf /*[kCombineChunk]*/, void* red,
                                         double* seg_buf /*[kMaxSegments, E_pad]*/) {
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -293,12 +293,12 @@ __device__ inline void combine_partials(const float* __restrict__ parts, int n, 
         const int per = (nb + n_seg - 1) / n_seg, lo = seg * per, hi = min(nb, lo + per);
         const float* col = parts + (size_t)b0 * P + kPartialHeader + 4 * vc;
         int b = lo;
-        for (; b + 12 <= hi; b += 12) {  // 12 x 16 B in flight per thread
-          float4 x[12];
+        for (; b + 8 <= hi; b += 8) {  // 8 x 16 B in flight per thread
+          float4 x[8];
 #pragma unroll
-          for (int j = 0; j < 12; ++j) x[j] = *reinterpret_cast<const float4*>(col + (size_t)(b + j) * P);
+          for (int j = 0; j < 8; ++j) x[j] = *reinterpret_cast<const float4*>(col + (size_t)(b + j) * P);
 #pragma unroll
-          for (int j = 0; j < 12; ++j) {
+          for (int j = 0; j < 8; ++j) {
             const double sc = (double)scale_buf[b + j];
             acc[0] += (double)x[j].x * sc;
             acc[1] += (double)x[j].y * sc;
@@ -306,14 +306,14 @@ __device__ inline void combine_partials(const float* __restrict__ parts, int n, 
             acc[3] += (double)x[j].w * sc;
           }
         }
-        if (b < hi) {  // remainder (< 12 rows): still issued together
-          float4 x[12];
+        if (b < hi) {  // remainder (< 8 rows): still issued together
+          float4 x[8];
 #pragma unroll
-          for (int j = 0; j < 12; ++j)
+          for (int j = 0; j < 8; ++j)
             x[j] = (b + j < hi) ? *reinterpret_cast<const float4*>(col + (size_t)(b + j) * P)
                                 : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int j = 0; j < 12; ++j)
+          for (int j = 0; j < 8; ++j)
             if (b + j < hi) {
               const double sc = (double)scale_buf[b + j];
               acc[0] += (double)x[j].x * sc;
@@ -385,8 +385,12 @@ __device__ inline void mpo_update(const SolveParams& p, const Combined& c) {
 // Everything after the weighted sum (mppi.py:381-458). Runs in ONE block.
 // smem: opt[E], y[(2T-1)*du] floats supplied by the caller.
 template <class M>
-__device__ inline void finish_solve(const SolveParams& p, const typename M::Ctx& ctx, const Combined& c,
-                                    const double* N, float* opt, float* ybuf, float* tail) {
+__device__ __noinline__ void finish_solve(const SolveParams& p, const Combined& c, const double* N, float* opt,
+                                          float* ybuf, float* tail) {
+  // the rollout of the optimal sequence only needs the model parameters (dynamics never read the maps
+  // or the reference path); a local context keeps the caller's register-resident one from escaping
+  typename M::Ctx ctx{};
+  if constexpr (M::kMaps >= 1) ctx.p = &p.mp;
   constexpr int DS = M::DS, DU = M::DU;
   const int tid = threadIdx.x, nt = blockDim.x, T = p.T, E = p.E;
   const int H = (T - 1) * DU;
@@ -748,7 +752,7 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ S
   combine_partials(p.block_partials, (int)gridDim.x, p.P, p.E_pad, comb, Nbuf, scale_buf, red, seg_buf);
   stamp(p, 5);
   if (p.n_shards == 1) {
-    finish_solve<M>(p, ctx, *comb, Nbuf, opt, ybuf, tail);
+    finish_solve<M>(p, *comb, Nbuf, opt, ybuf, tail);
   } else {
     for (int e = tid; e < p.E; e += blockDim.x) p.rank_partial[kPartialHeader + e] = (float)Nbuf[e];
     if (tid == 0) {
@@ -781,10 +785,8 @@ __global__ void __launch_bounds__(256, 1) finish_kernel(const __grid_constant__ 
   double* seg_buf = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(comb) + 64);
   float* tail = reinterpret_cast<float*>(seg_buf + (size_t)p.E_pad * kMaxSegments);
   void* red = smem + finish_scratch_core(p.E_pad, p.T, tail_per_step<M>());
-  typename M::Ctx ctx{};
-  if constexpr (M::kMaps >= 1) ctx.p = &p.mp;
   combine_partials(parts, n, p.P, p.E_pad, comb, Nbuf, scale_buf, red, seg_buf);
-  finish_solve<M>(p, ctx, *comb, Nbuf, opt, ybuf, tail);
+  finish_solve<M>(p, *comb, Nbuf, opt, ybuf, tail);
 }
 
 __host__ __device__ inline unsigned finish_scratch_bytes(int E_pad, int T, int tail_per_step) {

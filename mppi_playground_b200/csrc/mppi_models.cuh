@@ -233,7 +233,7 @@ struct Navigation2D {  // src/envs/navigation_2d.py:218-279
   // T calls of step(); only the schedule differs: the heading chain is the one serial part, the
   // sin/cos of every stage and the position increments are evaluated by T threads at once.
   // scratch: 8 * (T + 1) floats.
-  __device__ static void rollout_block(const Ctx& c, const float* state, const float* opt, int T, float* out,
+  __device__ static __noinline__ void rollout_block(const Ctx& c, const float* state, const float* opt, int T, float* out,
                                        float* scratch) {
     const float* p = c.p->v;
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -359,45 +359,32 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
   // as T calls of step(), rescheduled. Serial parts are only the three cheap recurrences (speed:
   // add+clamp; heading: two angle wraps; position: add+clamp); tan / sin / cos of all T stages run in
   // parallel in between. scratch: 11 * (T + 1) floats.
-  __device__ static void rollout_block(const Ctx& c, const float* state, const float* opt, int T, float* out,
+  __device__ static __noinline__ void rollout_block(const Ctx& c, const float* state, const float* opt, int T, float* out,
                                        float* scratch) {
     const float* p = c.p->v;
     const int tid = threadIdx.x, nt = blockDim.x, S = T + 1;
-    float *tn = scratch, *vs = tn + S, *ths = vs + S, *thw = ths + S, *dx = thw + S, *dy = dx + S, *xs = dy + S,
-          *ys = xs + S;
+    float *adt = scratch, *tn = adt + S, *vs = tn + S, *cdt = vs + S, *ths = cdt + S, *thw = ths + S, *dx = thw + S,
+          *dy = dx + S, *xs = dy + S, *ys = xs + S;
     const bool bounded = (c.p->flags & kFlagBounded) && state_in_bounds(c, state);
-    // phase 1: thread 0 walks the speed recurrence (it forms accel*dt itself, off the chain) while the
-    // other warps take tan(steer) of every stage
-    if (tid == 0) {
-      const float vm = p[5], a_lo = p[0], a_hi = p[1], dt = p[10];
-      float v = state[3];
-      vs[0] = v;
-      for (int t0 = 0; t0 < T; t0 += 8) {
-        float a[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] = (t0 + j < T) ? clampf(opt[2 * (t0 + j)], a_lo, a_hi) * dt : 0.0f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (t0 + j < T) {
-            v = clampf(v + a[j], -vm, vm);
-            vs[t0 + j + 1] = v;
-          }
-      }
-    } else if (tid >= 32) {
-      for (int t = tid - 32; t < T; t += nt - 32) {
-        const float st = clampf(opt[2 * t + 1], p[2], p[3]);
-        tn[t] = bounded ? tan_quarter(st) : tanf(st);
-      }
+    for (int t = tid; t < T; t += nt) {
+      adt[t] = clampf(opt[2 * t], p[0], p[1]) * p[10];
+      const float st = clampf(opt[2 * t + 1], p[2], p[3]);
+      tn[t] = bounded ? tan_quarter(st) : tanf(st);
     }
     __syncthreads();
-    // phase 2: heading recurrence; the yaw increments v_t tan(steer_t) / L * dt are formed ahead of it
     if (tid == 0) {
-      const ModelParams& mp = *c.p;
-      const float dt = p[10];
+      const float vm = p[5];
+      serial_chain(state[3], adt, vs, T, [vm](float v, float a) { return clampf(v + a, -vm, vm); });
+    }
+    __syncthreads();
+    for (int t = tid; t < T; t += nt)
+      cdt[t] = (bounded ? yaw_rate<true>(*c.p, vs[t], tn[t]) : yaw_rate<false>(*c.p, vs[t], tn[t])) * p[10];
+    __syncthreads();
+    if (tid == 0) {  // heading: S[t+1].theta = wrap(wrap(S[t].theta) + c_t); thw keeps the inner wrap
       if (bounded)
-        heading_chain<true>(state[2], [&](int t) { return yaw_rate<true>(mp, vs[t], tn[t]) * dt; }, thw, ths, T);
+        heading_chain<true>(state[2], [cdt](int t) { return cdt[t]; }, thw, ths, T);
       else
-        heading_chain<false>(state[2], [&](int t) { return yaw_rate<false>(mp, vs[t], tn[t]) * dt; }, thw, ths, T);
+        heading_chain<false>(state[2], [cdt](int t) { return cdt[t]; }, thw, ths, T);
     }
     __syncthreads();
     for (int t = tid; t < T; t += nt) {
