@@ -48,6 +48,15 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the solve kernel from the committed ncu capture (null if absent)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -220,7 +229,9 @@ def run_b200(args, rank, local_rank, world):
             spent += time.perf_counter() - c0
         e2e = {"value": n_e2e / spent, "unit": "solves/s", "h2d_bytes_per_step": H2D_BYTES,
                "d2h_bytes_per_step": D2H_BYTES, "steps": n_e2e,
-               "api": "mppi_solve_host (C ABI, pinned staging, H2D + solve + D2H + stream sync per step)"}
+               "api": "mppi_solve_host (C ABI, host buffers): state + reference path travel host->device inside the "
+                      "kernel parameter block, the finishing block stores action_seq / state_seq into mapped pinned "
+                      "host memory, stream sync, copy to the caller's buffers - every step"}
     else:
         n_e2e = min(args.steps, 500)
         spent = torch.zeros(1, dtype=torch.float64, device=device)
@@ -272,7 +283,7 @@ def run_b200(args, rank, local_rank, world):
             "e2e": e2e,
             "gpu_launches": launches,
             "roofline": {"bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": (ach / fp32_peak) if ach else None, "traffic": None,
+                         "frac": (ach / fp32_peak) if ach else None, "traffic": ncu_traffic() if world == 1 else None,
                          "kernel": "solve_kernel<Racing,false,kFused>", "kernel_ms": kern_ms, "kernel_launches": kern_n,
                          "algorithmic_flops_per_launch": FLOPS_PER_SOLVE / share,
                          "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz ({peak_src} MEASURED_PEAKS.json has no "
