@@ -157,9 +157,11 @@ def run_b200(args, rank, local_rank, world):
     stream = torch.cuda.current_stream(device)
     sp = stream.cuda_stream
 
+    fused = world == 1 or getattr(solver, "_fused", False)
+
     def solve(i):
         j = i % n_rec
-        if world == 1:
+        if fused:
             _capi.check(lib.mppi_solve(h, states_d[j].data_ptr(), refs_d[j].data_ptr(), None, action.data_ptr(),
                                        seq.data_ptr(), sp))
         else:
@@ -209,7 +211,7 @@ def run_b200(args, rank, local_rank, world):
 
     # ---- end to end through the C ABI with HOST buffers (H2D + solve + D2H + sync every step)
     e2e = None
-    if world == 1:
+    if fused:
         a_h = np.empty((HORIZON, 2), np.float32)
         s_h = np.empty((HORIZON + 1, 4), np.float32)
         st_np, rf_np = states_h.numpy(), refs_h.numpy()
@@ -227,6 +229,10 @@ def run_b200(args, rank, local_rank, world):
             _capi.check(lib.mppi_solve_host(h, st_np[j].ctypes.data, rf_np[j].ctypes.data, a_h.ctypes.data,
                                             s_h.ctypes.data))
             spent += time.perf_counter() - c0
+        if world > 1:
+            t_max = torch.tensor([spent], device=device, dtype=torch.float64)
+            dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+            spent = t_max.item()
         e2e = {"value": n_e2e / spent, "unit": "solves/s", "h2d_bytes_per_step": H2D_BYTES,
                "d2h_bytes_per_step": D2H_BYTES, "steps": n_e2e,
                "api": "mppi_solve_host (C ABI, host buffers): state + reference path travel host->device inside the "
@@ -277,7 +283,10 @@ def run_b200(args, rank, local_rank, world):
                                  "800x800 obstacle + lane occupancy grids, circuit centre line from tests/golden",
                        "l2": "flushed between timed steps (192 MiB memset outside the per-step CUDA events)",
                        "ms_per_step_back_to_back_no_flush": b2b_ms,
-                       "parallelism": f"sample-sharded x{world}" if world > 1 else "single GPU, one fused kernel",
+                       "parallelism": (f"K sharded over {world} GPUs, one fused kernel per GPU, shard partials exchanged by "
+                                       "peer stores over NVLink inside the kernel" if fused else
+                                       f"K sharded over {world} GPUs, NCCL all-gather of the partials + finish kernel")
+                       if world > 1 else "single GPU, one fused kernel",
                        "launch": info},
             "clocks": clocks,
             "e2e": e2e,

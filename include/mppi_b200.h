@@ -158,6 +158,21 @@ int mppi_shard_lambda(MppiHandle* h, const float* d_costs_all, void* stream);
 int mppi_shard_finish(MppiHandle* h, const float* d_partials, int32_t n_shards, const float* d_state,
                       float* d_action_seq, float* d_state_seq, void* stream);
 int32_t mppi_partial_floats(const MppiHandle* h);
+/* Fused peer exchange (one process per GPU on one NVLink/NVSwitch node): every rank exports a CUDA IPC
+ * handle of its mailbox (64 bytes), the caller all-gathers the handles ([world][64]) and connects. From
+ * then on mppi_solve / mppi_solve_host on these shard handles (fixed lambda / MPO) is ONE kernel launch
+ * per GPU: the finishing block stores the shard partial into every peer's mailbox over NVLink, waits for
+ * the peers' sequence flags and finishes the solve - no collective call, no second launch.
+ * LBPS / ESSPS handles keep using the staged mppi_shard_* path. mppi_p2p_status reports a timed-out
+ * exchange (a peer that never launched its solve). */
+int mppi_p2p_export(MppiHandle* h, uint8_t handle_out[64]);
+int mppi_p2p_connect(MppiHandle* h, const uint8_t* handles, int32_t world, int32_t rank);
+int mppi_p2p_status(MppiHandle* h, int32_t* timed_out);
+/* Same wiring for shard handles that live in ONE process (one process driving several GPUs with peer
+ * access enabled, or several shards on one GPU): the mailboxes are plain device pointers. The shard
+ * solves must then run concurrently (one stream per handle). */
+int mppi_p2p_mailbox_ptr(MppiHandle* h, uint64_t* ptr);
+int mppi_p2p_connect_local(MppiHandle* h, const uint64_t* mailbox_ptrs, int32_t world, int32_t rank);
 /* Device buffers owned by the handle, valid until mppi_destroy. */
 int mppi_costs_ptr(MppiHandle* h, const float** d_costs);     /* [num_samples] of the last solve */
 int mppi_partial_ptr(MppiHandle* h, const float** d_partial); /* [mppi_partial_floats()] */

@@ -144,6 +144,13 @@ struct MppiHandle {
   bool solved = false;
   const float* last_noise = nullptr;
   int last_launches = 0;
+  // fused peer exchange (mppi_p2p_*)
+  float* d_mailbox = nullptr;
+  float* d_gather_scratch = nullptr;
+  int* d_error_flag = nullptr;
+  int p2p_world = 0, p2p_rank = 0;
+  float* peer_mailbox[kMaxPeers] = {};
+  bool peer_opened[kMaxPeers] = {};
   const float* inline_state = nullptr;  // set for the duration of a host-call solve
   const float* inline_ref = nullptr;
   bool timing = false;
@@ -270,7 +277,7 @@ int check_ready(MppiHandle* h) {
 
 // Per-solve parameter block: base + this call's pointers + sampler counter.
 int make_params(MppiHandle* h, const float* d_state, const float* d_refpath, const float* d_noise, float* d_action,
-                float* d_state_seq, int n_shards, SolveParams* out) {
+                float* d_state_seq, int n_shards, SolveParams* out, bool use_p2p = false) {
   if (!d_state) return fail(MPPI_ERR_INVALID, "state is null");
   if (h->mi.refpath && !d_refpath) return fail(MPPI_ERR_INVALID, "this model needs a reference path [T+1,4]");
   SolveParams p = h->base;
@@ -284,6 +291,15 @@ int make_params(MppiHandle* h, const float* d_state, const float* d_refpath, con
   p.key.solve_hi = (uint32_t)(h->solve_count >> 32);
   p.n_shards = n_shards;
   p.trace = h->d_trace;
+  p.p2p_world = 0;
+  if (n_shards > 1 && h->p2p_world > 1 && use_p2p) {
+    p.p2p_world = h->p2p_world;
+    p.p2p_rank = h->p2p_rank;
+    p.p2p_seq = (unsigned)(h->solve_count + 1);
+    for (int r = 0; r < h->p2p_world; ++r) p.peer_mailbox[r] = h->peer_mailbox[r];
+    p.gather_scratch = h->d_gather_scratch;
+    p.error_flag = h->d_error_flag;
+  }
   p.inline_inputs = 0;
   if (h->inline_state) {
     p.inline_inputs = 1;
@@ -545,6 +561,11 @@ void mppi_destroy(MppiHandle* h) {
   cudaFree(h->d_keys_out);
   cudaFree(h->d_sort_tmp);
   cudaFree(h->d_trace);
+  for (int r = 0; r < kMaxPeers; ++r)
+    if (h->peer_opened[r]) cudaIpcCloseMemHandle(h->peer_mailbox[r]);
+  cudaFree(h->d_mailbox);
+  cudaFree(h->d_gather_scratch);
+  cudaFree(h->d_error_flag);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -627,11 +648,16 @@ static int solve_impl(MppiHandle* h, const float* d_state, const float* d_refpat
   if (!d_action || !d_state_seq) return fail(MPPI_ERR_INVALID, "output pointer is null");
   CUDA_TRY(cudaSetDevice(h->device));
   SolveParams p;
-  rc = make_params(h, d_state, d_refpath, d_noise, d_action, d_state_seq, 1, &p);
+  const bool lam_search = h->cfg.lambda_mode == MPPI_LAMBDA_LBPS || h->cfg.lambda_mode == MPPI_LAMBDA_ESSPS;
+  const bool fused_shards = h->p2p_world > 1 && !lam_search;
+  if (h->cfg.total_samples != h->cfg.num_samples && !fused_shards)
+    return fail(MPPI_ERR_STATE, "this handle owns a shard: use mppi_shard_* (or connect the peers with mppi_p2p_connect)");
+  rc = make_params(h, d_state, d_refpath, d_noise, d_action, d_state_seq, fused_shards ? h->p2p_world : 1, &p,
+                   fused_shards);
   if (rc) return rc;
   h->last_launches = 0;
   const bool inject = d_noise != nullptr;
-  if (h->cfg.lambda_mode == MPPI_LAMBDA_LBPS || h->cfg.lambda_mode == MPPI_LAMBDA_ESSPS) {
+  if (lam_search) {
     if ((rc = dispatch_solve(h, p, kCosts, inject, st))) return rc;
     if ((rc = launch_search(h, h->d_costs, h->cfg.num_samples, st))) return rc;
     if ((rc = dispatch_solve(h, p, kReduce, inject, st))) return rc;
@@ -734,6 +760,73 @@ int mppi_shard_finish(MppiHandle* h, const float* d_partials, int32_t n_shards, 
   if (rc) return rc;
   h->solve_count++;
   h->solved = true;
+  return MPPI_OK;
+}
+
+int mppi_p2p_export(MppiHandle* h, uint8_t handle_out[64]) {
+  if (!h || !handle_out) return fail(MPPI_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (!h->d_mailbox) {
+    const size_t bytes = mailbox_floats(h->P) * 4;
+    CUDA_TRY(cudaMalloc((void**)&h->d_mailbox, bytes));
+    CUDA_TRY(cudaMemset(h->d_mailbox, 0, bytes));
+    CUDA_TRY(cudaMalloc((void**)&h->d_gather_scratch, (size_t)kMaxPeers * h->P * 4));
+    CUDA_TRY(cudaMalloc((void**)&h->d_error_flag, 16));
+    CUDA_TRY(cudaMemset(h->d_error_flag, 0, 16));
+    CUDA_TRY(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t ipc;
+  CUDA_TRY(cudaIpcGetMemHandle(&ipc, h->d_mailbox));
+  memcpy(handle_out, &ipc, 64);
+  return MPPI_OK;
+}
+
+int mppi_p2p_connect(MppiHandle* h, const uint8_t* handles, int32_t world, int32_t rank) {
+  if (!h || !handles) return fail(MPPI_ERR_INVALID, "null argument");
+  if (world < 2 || world > kMaxPeers || rank < 0 || rank >= world)
+    return fail(MPPI_ERR_INVALID, "p2p world must be in [2, %d]", kMaxPeers);
+  if (!h->d_mailbox) return fail(MPPI_ERR_STATE, "call mppi_p2p_export first");
+  CUDA_TRY(cudaSetDevice(h->device));
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      h->peer_mailbox[r] = h->d_mailbox;
+      continue;
+    }
+    cudaIpcMemHandle_t ipc;
+    memcpy(&ipc, handles + (size_t)r * 64, 64);
+    void* ptr = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&ptr, ipc, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_mailbox[r] = (float*)ptr;
+    h->peer_opened[r] = true;
+  }
+  h->p2p_world = world;
+  h->p2p_rank = rank;
+  return MPPI_OK;
+}
+
+int mppi_p2p_connect_local(MppiHandle* h, const uint64_t* mailbox_ptrs, int32_t world, int32_t rank) {
+  if (!h || !mailbox_ptrs) return fail(MPPI_ERR_INVALID, "null argument");
+  if (world < 2 || world > kMaxPeers || rank < 0 || rank >= world)
+    return fail(MPPI_ERR_INVALID, "p2p world must be in [2, %d]", kMaxPeers);
+  if (!h->d_mailbox || (uint64_t)(uintptr_t)h->d_mailbox != mailbox_ptrs[rank])
+    return fail(MPPI_ERR_STATE, "mailbox_ptrs[rank] must be this handle's own mailbox (mppi_p2p_export first)");
+  for (int r = 0; r < world; ++r) h->peer_mailbox[r] = (float*)(uintptr_t)mailbox_ptrs[r];
+  h->p2p_world = world;
+  h->p2p_rank = rank;
+  return MPPI_OK;
+}
+
+int mppi_p2p_mailbox_ptr(MppiHandle* h, uint64_t* ptr) {
+  if (!h || !ptr) return fail(MPPI_ERR_INVALID, "null argument");
+  *ptr = (uint64_t)(uintptr_t)h->d_mailbox;
+  return MPPI_OK;
+}
+
+int mppi_p2p_status(MppiHandle* h, int32_t* timed_out) {
+  if (!h || !timed_out) return fail(MPPI_ERR_INVALID, "null argument");
+  *timed_out = 0;
+  if (h->d_error_flag) CUDA_TRY(cudaMemcpy(timed_out, h->d_error_flag, 4, cudaMemcpyDeviceToHost));
   return MPPI_OK;
 }
 

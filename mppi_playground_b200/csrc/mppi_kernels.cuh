@@ -27,6 +27,7 @@ enum SolveMode : int { kFused = 0, kCosts = 1, kReduce = 2 };
 enum LambdaMode : int { kLamFixed = 0, kLamMPO = 1, kLamLBPS = 2, kLamESSPS = 3 };
 
 constexpr int kInlineRefFloats = 512;
+constexpr int kMaxPeers = 8;
 constexpr int kMaxSegments = 16;   // combine_partials: threads = segments x float4 columns
 constexpr int kPartialHeader = 8;  // xmax S xmax_tau S_tau Sc_tau cmin cmax pad
 constexpr int kMaxSgWindow = 33;
@@ -82,6 +83,14 @@ struct SolveParams {
   float ref_inline[kInlineRefFloats];  // [T+1,4] when (T+1)*4 <= kInlineRefFloats
   unsigned long long* trace;  // optional [grid, 8] %globaltimer stamps per block (profiling aid), else null
   int n_shards;  // 1: finish inside the kernel
+  // fused peer exchange (NVLink P2P, one launch per solve on every GPU): each rank owns a mailbox
+  // [2 parities][kMaxPeers][P] floats followed by [2][kMaxPeers] sequence flags; peer_mailbox[r] is rank
+  // r's mailbox mapped into this process (CUDA IPC). 0 ranks = staged path (rank_partial + finish_kernel).
+  int p2p_world, p2p_rank;
+  unsigned p2p_seq;  // sequence number of this solve (>= 1)
+  float* peer_mailbox[kMaxPeers];
+  float* gather_scratch;  // [kMaxPeers, P] private copy of the gathered partials
+  int* error_flag;        // set when the exchange times out
   int E, E_pad, P;
 };
 
@@ -457,6 +466,77 @@ __device__ __noinline__ void finish_solve(const SolveParams& p, const Combined& 
 }
 
 // ---------------------------------------------------------------------------
+// fused shard exchange over peer memory
+// ---------------------------------------------------------------------------
+__host__ __device__ inline size_t mailbox_floats(int P) { return (size_t)2 * kMaxPeers * P + 2 * kMaxPeers; }
+
+__device__ __forceinline__ void st_release_sys(unsigned* ptr, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* ptr) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_volatile(const float* ptr) {
+  float v;
+  asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(ptr) : "memory");
+  return v;
+}
+
+// Last block of every rank: push this shard's partial into every rank's mailbox (peer stores over
+// NVLink), publish a sequence flag, wait for all ranks' flags in the own mailbox, and leave the gathered
+// partials in gather_scratch. Double-buffered by the parity of the sequence number: a rank can only
+// reach solve s+2 after every rank published s+1, i.e. after every rank finished reading solve s.
+__device__ inline bool exchange_partials(const SolveParams& p, const Combined& c, const double* N) {
+  const int tid = threadIdx.x, nt = blockDim.x, G = p.p2p_world, P = p.P;
+  const unsigned seq = p.p2p_seq, parity = seq & 1u;
+  const size_t slot = ((size_t)parity * kMaxPeers + p.p2p_rank) * P;
+  for (int r = 0; r < G; ++r) {
+    float* dst = p.peer_mailbox[r] + slot;
+    for (int e = tid; e < p.E_pad; e += nt) dst[kPartialHeader + e] = (e < p.E) ? (float)N[e] : 0.0f;
+    if (tid == 0) {
+      dst[0] = c.xmax;
+      dst[1] = (float)c.S;
+      dst[2] = c.xmax_tau;
+      dst[3] = (float)c.S_tau;
+      dst[4] = (float)c.Sc_tau;
+      dst[5] = c.cmin;
+      dst[6] = c.cmax;
+      dst[7] = 0.0f;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ int timed_out;
+  if (tid == 0) timed_out = 0;
+  __syncthreads();
+  if (tid < G) {
+    unsigned* peer_flags = reinterpret_cast<unsigned*>(p.peer_mailbox[tid] + (size_t)2 * kMaxPeers * P);
+    st_release_sys(peer_flags + parity * kMaxPeers + p.p2p_rank, seq);
+    const unsigned* my_flags = reinterpret_cast<const unsigned*>(p.peer_mailbox[p.p2p_rank] + (size_t)2 * kMaxPeers * P);
+    const long long t0 = clock64();
+    while (ld_acquire_sys(my_flags + parity * kMaxPeers + tid) != seq) {
+      if (clock64() - t0 > 4000000000LL) {  // ~2 s: a peer never arrived - do not hang the GPU
+        timed_out = 1;
+        break;
+      }
+      __nanosleep(100);
+    }
+  }
+  __syncthreads();
+  if (timed_out) {
+    if (tid == 0 && p.error_flag) *p.error_flag = 1;
+    return false;
+  }
+  const float* mine = p.peer_mailbox[p.p2p_rank] + (size_t)parity * kMaxPeers * P;
+  for (int i = tid; i < G * P; i += nt) p.gather_scratch[i] = ld_volatile(mine + i);
+  __threadfence();
+  __syncthreads();
+  return true;
+}
+
+// ---------------------------------------------------------------------------
 // the solve kernel
 // ---------------------------------------------------------------------------
 template <class M, bool kBounded>
@@ -753,6 +833,11 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ S
   stamp(p, 5);
   if (p.n_shards == 1) {
     finish_solve<M>(p, *comb, Nbuf, opt, ybuf, tail);
+  } else if (p.p2p_world > 0) {
+    if (exchange_partials(p, *comb, Nbuf)) {
+      combine_partials(p.gather_scratch, p.p2p_world, p.P, p.E_pad, comb, Nbuf, scale_buf, red, seg_buf);
+      finish_solve<M>(p, *comb, Nbuf, opt, ybuf, tail);
+    }
   } else {
     for (int e = tid; e < p.E; e += blockDim.x) p.rank_partial[kPartialHeader + e] = (float)Nbuf[e];
     if (tid == 0) {

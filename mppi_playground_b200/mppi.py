@@ -68,12 +68,15 @@ class MPPI(nn.Module):
         shard: Optional[Tuple[int, int]] = None,
         process_group=None,
         block_size: int = 0,
+        fused_exchange: bool = True,
     ) -> None:
         """Arguments up to ``seed`` are the reference's (mppi.py:24-47).
 
         Keyword-only extensions: ``shard=(rank, world)`` / ``process_group``
         split the K samples over one process per GPU (``num_samples`` stays the
-        GLOBAL count); ``block_size`` overrides the launch geometry.
+        GLOBAL count); ``block_size`` overrides the launch geometry; ``fused_exchange`` (default) wires the
+        ranks' mailboxes over CUDA IPC so that a fixed-lambda / MPO sharded solve is one kernel launch per GPU
+        with the partials exchanged by peer stores over NVLink (False: NCCL all-gather + a finish kernel).
         """
         super().__init__()
         u_min, u_max, sigmas = (torch.as_tensor(x) for x in (u_min, u_max, sigmas))
@@ -164,6 +167,23 @@ class MPPI(nn.Module):
         self._bind_maps(required=False)
         self._noise_keepalive = None
         self._gathered = None
+        self._fused = False
+        if self._world > 1 and process_group is not None and fused_exchange and self._auto_lambda in (None, "MPO"):
+            self._connect_peers(process_group)
+
+    def _connect_peers(self, group) -> None:
+        """Exchange the CUDA IPC handles of the shard mailboxes (64 bytes per rank, once) and connect."""
+        import torch.distributed as dist
+
+        mine = (C.c_uint8 * 64)()
+        with torch.cuda.device(self._device):
+            _capi.check(self._lib.mppi_p2p_export(self._h, mine))
+        handles = [None] * self._world
+        dist.all_gather_object(handles, bytes(mine), group=group)
+        flat = (C.c_uint8 * (64 * self._world)).from_buffer_copy(b"".join(handles))
+        with torch.cuda.device(self._device):
+            _capi.check(self._lib.mppi_p2p_connect(self._h, flat, self._world, self._rank))
+        self._fused = True
 
     # ------------------------------------------------------------------ plumbing
     def __del__(self):
@@ -246,7 +266,7 @@ class MPPI(nn.Module):
         action = torch.empty(T, du, device=self._device, dtype=torch.float32)
         states = torch.empty(T + 1, ds, device=self._device, dtype=torch.float32)
         s = _stream_ptr(self._device)
-        if self._world == 1:
+        if self._world == 1 or self._fused:
             _capi.check(self._lib.mppi_solve(self._h, st.data_ptr(), _ptr(ref), _ptr(noise), action.data_ptr(),
                                              states.data_ptr(), s))
         else:
@@ -428,6 +448,41 @@ class MPPI(nn.Module):
         half = (window_size - 1) // 2
         idx = torch.arange(-half, half + 1, dtype=torch.float32)
         return torch.linalg.pinv(torch.vander(idx, N=poly_order + 1, increasing=True))[0]
+
+
+def connect_shards_inprocess(solvers) -> None:
+    """Wire the fused peer exchange between shard solvers that live in ONE process (``shard=(r, world)``,
+    fixed lambda / MPO). Afterwards every shard's ``forward`` is a single launch, but the shards wait for
+    each other inside the kernel, so they must be launched concurrently: one CUDA stream (or GPU) each,
+    see ``solve_fused_shards_inprocess``."""
+    world = len(solvers)
+    ptrs = (C.c_uint64 * world)()
+    scratch = (C.c_uint8 * 64)()
+    for r, sv in enumerate(solvers):
+        with torch.cuda.device(sv._device):
+            _capi.check(sv._lib.mppi_p2p_export(sv._h, scratch))
+        v = C.c_uint64()
+        _capi.check(sv._lib.mppi_p2p_mailbox_ptr(sv._h, C.byref(v)))
+        ptrs[r] = v.value
+    for r, sv in enumerate(solvers):
+        _capi.check(sv._lib.mppi_p2p_connect_local(sv._h, ptrs, world, r))
+        sv._fused = True
+
+
+def solve_fused_shards_inprocess(solvers, state, streams, noise: Optional[torch.Tensor] = None):
+    """Launch one fused sharded solve per solver, each on its own stream, then wait for all."""
+    out = []
+    for sv, st in zip(solvers, streams):
+        with torch.cuda.stream(st):
+            out.append(sv.forward(state, noise=noise))
+    for st in streams:
+        st.synchronize()
+    for sv in solvers:
+        flag = C.c_int32()
+        _capi.check(sv._lib.mppi_p2p_status(sv._h, C.byref(flag)))
+        if flag.value:
+            raise RuntimeError("fused shard exchange timed out (a shard's solve was not running concurrently)")
+    return out
 
 
 def solve_shards_inprocess(solvers, state, noise: Optional[torch.Tensor] = None):

@@ -365,3 +365,38 @@ def test_host_buffer_solve_equals_device_buffer_solve(cfg):
         np.testing.assert_array_equal(a_h, a_d.cpu().numpy())
         np.testing.assert_array_equal(s_h, s_d.cpu().numpy())
         state = s_d[0, 1].cpu()
+
+
+@pytest.mark.parametrize("cfg", [SHARD_CASES[0], SHARD_CASES[3]], ids=["racing-fixed", "cartpole-MPO"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_fused_peer_exchange_equals_staged_and_single(cfg, world):
+    """The fused shard exchange (partials stored into the peers' mailboxes by the finishing block, sequence
+    flags, no second launch) against the unsharded solve. The shard handles live on one GPU here and run
+    concurrently on separate streams; on a multi-GPU box the same kernel path runs over NVLink
+    (tools/mgpu_check.py)."""
+    import mppi_playground_b200 as eng
+    from mppi_playground_b200.mppi import connect_shards_inprocess, solve_fused_shards_inprocess
+
+    model, single = build_engine(cfg)
+    shards = [build_engine(cfg, shard=(r, world)) for r in range(world)]
+    solvers = [sv for _, sv in shards]
+    connect_shards_inprocess(solvers)
+    streams = [torch.cuda.Stream() for _ in solvers]
+    state = _start_state(cfg)
+    env = fx.load_env_racing() if cfg["model"] == "racing" else None
+    cind = 0
+    for s in range(4):
+        if env is not None:
+            ref, cind = eng.racing_reference_path(state, env.center_path, cind, cfg["horizon"], v_max=env.v_max)
+            for m in [model] + [m for m, _ in shards]:
+                m.reference_path_tensor = ref
+        a1, s1 = single.forward(state)
+        torch.cuda.synchronize()
+        outs = solve_fused_shards_inprocess(solvers, state, streams)
+        assert all(sv.launch_info()["launches_last_solve"] == 1 for sv in solvers)
+        at = 2e-6 if s == 0 else tol_for(cfg["lambda_"])["action"]
+        for a, st in outs:
+            assert torch.equal(a, outs[0][0]) and torch.equal(st, outs[0][1])
+            np.testing.assert_allclose(a.cpu().numpy(), a1.cpu().numpy(), rtol=2e-5, atol=at)
+            np.testing.assert_allclose(st.cpu().numpy(), s1.cpu().numpy(), rtol=2e-5, atol=max(at, 2e-5))
+        state = s1[0, 1].cpu()
