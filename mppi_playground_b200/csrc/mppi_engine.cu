@@ -347,6 +347,8 @@ void refresh_model_flags(MppiHandle* h) {
   SolveParams& b = h->base;
   int flags = 0;
   const float* v = b.mp.v;
+  // solver control bounds inside the env's own clamp (both models: params 0..3 = lo0 hi0 lo1 hi1)
+  const bool clamp_redundant = b.u_min[0] >= v[0] && b.u_max[0] <= v[1] && b.u_min[1] >= v[2] && b.u_max[1] <= v[3];
   if (h->cfg.model == MPPI_MODEL_RACING) {
     if (h->map_set[0] && h->map_set[1] && b.map_W[0] == b.map_W[1] && b.map_H[0] == b.map_H[1] &&
         b.map_cell[0] == b.map_cell[1] && b.map_ox[0] == b.map_ox[1] && b.map_oy[0] == b.map_oy[1] &&
@@ -366,13 +368,13 @@ void refresh_model_flags(MppiHandle* h) {
     const double smax = std::max(fabs((double)v[2]), fabs((double)v[3]));
     if (smax <= 0.78 && v[4] > 0.0f) {
       const double yaw = fabs((double)v[5]) * tan(smax) / (double)v[4] * fabs((double)v[10]);
-      if (yaw < 6.0 && (flags & kFlagSameMapGeometry) && b.map_fastdiv[0] && h->wheelbase_exact &&
+      if (yaw < 6.0 && clamp_redundant && (flags & kFlagSameMapGeometry) && b.map_fastdiv[0] && h->wheelbase_exact &&
           fabsf(b.map_ox[0]) >= 1e-20f && fabsf(b.map_oy[0]) >= 1e-20f)
         flags |= kFlagBounded;
     }
   } else if (h->cfg.model == MPPI_MODEL_NAVIGATION2D) {
     const double wmax = std::max(fabs((double)v[2]), fabs((double)v[3]));
-    if (wmax * fabs((double)v[10]) < 6.0 && h->map_set[0] && b.map_fastdiv[0] && fabsf(b.map_ox[0]) >= 1e-20f &&
+    if (wmax * fabs((double)v[10]) < 6.0 && clamp_redundant && h->map_set[0] && b.map_fastdiv[0] && fabsf(b.map_ox[0]) >= 1e-20f &&
         fabsf(b.map_oy[0]) >= 1e-20f)
       flags |= kFlagBounded;
   }

@@ -110,6 +110,9 @@ constexpr int kFlagUnitWheelbase = 2;    // Racing: L == 1.0f, so x / L == x exa
 // Host-verified bounds (mppi_engine.cu:refresh_model_flags) that make the branch-free helpers exact:
 //   steering clamp within +-0.78 rad  -> tan_quarter == tanf
 //   |yaw increment per step| < 6 rad  -> wrap_angle_bounded == wrap_angle on every rolled-out heading
+//   solver bounds [u_min, u_max] inside the env's own clamp -> that second clamp of a sampled control is
+//                                        the identity and is skipped (samples only; the SG-filtered optimal
+//                                        sequence can overshoot, so the tail rollout keeps the clamp)
 // The kernel additionally requires the solve's initial heading / speed to be in range (uniform check).
 constexpr int kFlagBounded = 4;
 
@@ -203,8 +206,8 @@ struct Navigation2D {  // src/envs/navigation_2d.py:218-279
     const float* p = c.p->v;
 #pragma unroll
     for (int i = 0; i < DS; ++i) seen[i] = s[i];
-    float v = clampf(u[0], p[0], p[1]);  // :235-236
-    float w = clampf(u[1], p[2], p[3]);
+    float v = kBounded ? u[0] : clampf(u[0], p[0], p[1]);  // :235-236 (identity under kFlagBounded)
+    float w = kBounded ? u[1] : clampf(u[1], p[2], p[3]);
     float th = kBounded ? wrap_angle_bounded(s[2]) : wrap_angle(s[2]);  // :237
     float st, ct;
     sincosf(th, &st, &ct);
@@ -305,8 +308,8 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
     const float* p = c.p->v;
 #pragma unroll
     for (int i = 0; i < DS; ++i) seen[i] = s[i];
-    float accel = clampf(u[0], p[0], p[1]);  // :345-346
-    float steer = clampf(u[1], p[2], p[3]);
+    float accel = kBounded ? u[0] : clampf(u[0], p[0], p[1]);  // :345-346 (identity under kFlagBounded)
+    float steer = kBounded ? u[1] : clampf(u[1], p[2], p[3]);
     float th = kBounded ? wrap_angle_bounded(s[2]) : wrap_angle(s[2]);  // :347
     float st, ct;
     sincosf(th, &st, &ct);

@@ -400,3 +400,81 @@ def test_fused_peer_exchange_equals_staged_and_single(cfg, world):
             np.testing.assert_allclose(a.cpu().numpy(), a1.cpu().numpy(), rtol=2e-5, atol=at)
             np.testing.assert_allclose(st.cpu().numpy(), s1.cpu().numpy(), rtol=2e-5, atol=max(at, 2e-5))
         state = s1[0, 1].cpu()
+
+
+EDGE_CASES = [
+    dict(model="pendulum", horizon=1, num_samples=64, u_min=[-2.0], u_max=[2.0], sigmas=[1.0], lambda_=1.0,
+         state0=[1.0, 0.5]),
+    dict(model="pendulum", horizon=2, num_samples=1, u_min=[-2.0], u_max=[2.0], sigmas=[1.0], lambda_=0.5,
+         state0=[40.0, -3.0]),  # one sample; heading far outside [-pi, pi] (general remainder path)
+    dict(model="cartpole", horizon=7, num_samples=33, u_min=[-3.0], u_max=[3.0], sigmas=[1.0], lambda_=0.01,
+         use_sg_filter=True, sg_window_size=7, sg_poly_order=2, state0=[0.0, 0.3, 0.02, 0.1]),
+    dict(model="mountaincar", horizon=13, num_samples=257, u_min=[-1.0], u_max=[1.0], sigmas=[1.0], lambda_="ESSPS",
+         exploration=0.5, state0=[0.55, 0.06]),  # clamps at the right wall: exercises the in-place quirk
+    dict(model="navigation2d", horizon=9, num_samples=1000, sigmas=[0.5, 0.5], lambda_=3.0, exploration=1.0,
+         state0=[9.9, 9.9, 0.3]),  # every sample zero-mean; starts next to the map edge (out-of-bounds cells)
+    dict(model="racing", horizon=5, num_samples=96, sigmas=[0.5, 0.1], lambda_=10.0, use_sg_filter=True,
+         state0=[39.95, -39.95, 3.1, 9.5]),  # corner of the map, speed above v_max: general (unbounded) loop
+    dict(model="racing", horizon=127, num_samples=640, sigmas=[0.5, 0.1], lambda_="MPO"),
+]
+
+
+@pytest.mark.parametrize("cfg", EDGE_CASES, ids=lambda c: f"{c['model']}-T{c['horizon']}-K{c['num_samples']}")
+def test_edge_shapes_match_oracle(cfg):
+    """Ragged / minimal sizes and boundary states, in-kernel sampler, two closed-loop solves vs the oracle."""
+    import mppi_playground_b200 as eng
+
+    model, solver = build_engine(cfg)
+    omodel, oracle = build_oracle(cfg, burn_constructor_draw=False)
+    state = _start_state(cfg)
+    env = fx.load_env_racing() if cfg["model"] == "racing" else None
+    cind = 0
+    for s in range(2):
+        if env is not None:
+            ref, cind = eng.racing_reference_path(state, env.center_path, cind, cfg["horizon"], v_max=env.v_max)
+            model.reference_path_tensor, omodel.reference_path = ref, ref
+        noise = solver.sampler_noise().cpu()
+        action, states = solver.forward(state)
+        tr = oracle.forward(state, noise=noise)
+        used, nxt = solver._lambdas()
+        st = ParityStats(solver._costs.cpu().numpy(), tr.costs.numpy(), action.cpu().numpy(), tr.action_seq.numpy(),
+                         states.cpu().numpy(), tr.state_seq.numpy(), used, tr.lam)
+        _report(f"edge/{cfg['model']}-T{cfg['horizon']}-K{cfg['num_samples']}", s, st)
+        assert_parity(st, tol=tol_for(cfg["lambda_"]), smooth=cfg["model"] in SMOOTH)
+        n = min(5, cfg["num_samples"])
+        traj, w = solver.get_top_samples(n)
+        otraj, ow = oracle.get_top_samples(n)
+        np.testing.assert_allclose(w.cpu().numpy(), ow.numpy(), rtol=5e-3, atol=1e-7)
+        if n == 1 or abs(float(ow[0] - ow[1])) > 1e-3 * float(ow[0]):  # unambiguous best sample
+            np.testing.assert_allclose(traj[0].cpu().numpy(), otraj[0].numpy(), rtol=0, atol=5e-4)
+        oracle.prev_action_seq = action.cpu().clone()
+        if cfg.get("use_sg_filter"):
+            oracle.history = solver._actions_history_for_sg.cpu().clone()
+        if oracle.mode == "MPO":
+            sync_mpo(oracle, nxt)
+        state = states[0, 1].cpu().clone()
+
+
+def test_cost_weights_and_maps_are_reread_every_solve():
+    """The racing cost weights are plain attributes of the controller (example/racing.py:41-46) and the
+    grids can be replaced (set_cost_map): changes between solves must reach the kernel."""
+    import mppi_playground_b200 as eng
+
+    cfg = dict(model="racing", horizon=30, num_samples=2048, sigmas=[0.5, 0.1], lambda_=1.0)
+    model, solver = build_engine(cfg)
+    omodel, oracle = build_oracle(cfg, burn_constructor_draw=False)
+    env = fx.load_env_racing()
+    ref, _ = eng.racing_reference_path(env.start_state, env.center_path, 0, 30)
+    model.reference_path_tensor, omodel.reference_path = ref, ref
+    for step, (qc, qo) in enumerate([(2.0, 10000.0), (7.5, 10.0)]):
+        model.Qc, model.Qo, omodel.Qc, omodel.Qo = qc, qo, qc, qo
+        noise = solver.sampler_noise().cpu()
+        action, states = solver.forward(env.start_state)
+        tr = oracle.forward(env.start_state, noise=noise)
+        st = ParityStats(solver._costs.cpu().numpy(), tr.costs.numpy(), action.cpu().numpy(), tr.action_seq.numpy(),
+                         states.cpu().numpy(), tr.state_seq.numpy(), 1.0, 1.0)
+        assert_parity(st)
+        oracle.prev_action_seq = action.cpu().clone()
+    solver.reset()
+    oracle.reset()
+    assert float(solver._previous_action_seq.abs().max()) == 0.0
