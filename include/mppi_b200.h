@@ -216,6 +216,19 @@ int mppi_block_trace(MppiHandle* h, int32_t enable, uint64_t* h_out, int32_t max
  * fp32 input of their claimed range: mismatches[0] tan_quarter vs tanf (|x| <= 0.78), [1]
  * wrap_angle_bounded vs wrap_angle (|x| < 9), [2] floored_remainder vs the fmodf form. All must be 0. */
 int mppi_selftest(int32_t device, uint64_t mismatches[3]);
+/* ---- racing reference path on the device ("next" row: example/racing.py:161-218) ------------------
+ * racing_controller.calc_ref_trajectory runs on the host before every solve in the reference (a Python
+ * loop over the N centre-line points). MppiRefPath keeps the centre line [n,3] (x, y, yaw), the per-row
+ * index offsets int(round(travel / DL)) (formed on the host in fp64 like the reference, [rows] = T+1) and
+ * the carried path index on the device; mppi_refpath_update writes the [T+1,4] reference path for d_state
+ * into d_refpath_out with one small kernel - no host round trip between env step and solve.
+ * mppi_refpath_index reads (current != NULL) and/or sets (set_value >= 0) the carried index. */
+typedef struct MppiRefPath MppiRefPath;
+int mppi_refpath_create(int32_t device, const float* h_path, int32_t n, const int32_t* h_index_offsets, int32_t rows,
+                        float v_max, MppiRefPath** out);
+void mppi_refpath_destroy(MppiRefPath* r);
+int mppi_refpath_update(MppiRefPath* r, const float* d_state, float* d_refpath_out, void* stream);
+int mppi_refpath_index(MppiRefPath* r, int32_t set_value, int32_t* current, void* stream);
 /* Time the dominant (rollout) kernel of subsequent solves with CUDA events on
  * the launching stream: enable with 1, read back the mean/launch count with
  * mppi_kernel_time_ms (which synchronises the events). */

@@ -14,7 +14,7 @@ and raises if libmppi_b200.so or a CUDA device is missing - there is no CPU path
 """
 from .mppi import MPPI, shard_bounds  # noqa: F401
 from .models import (CartpoleModel, MountainCarModel, Navigation2DModel, PendulumModel,  # noqa: F401
-                     RacingModel, racing_reference_path)
+                     RacingModel, RacingReferencePath, racing_reference_path)
 
 __all__ = ["MPPI", "PendulumModel", "CartpoleModel", "MountainCarModel", "Navigation2DModel", "RacingModel",
-           "racing_reference_path", "shard_bounds"]
+           "racing_reference_path", "RacingReferencePath", "shard_bounds"]

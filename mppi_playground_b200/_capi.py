@@ -75,6 +75,11 @@ PROTOTYPES = {
     "mppi_map_info": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]),
     "mppi_block_trace": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_uint64), C.c_int32]),
     "mppi_selftest": (C.c_int, [C.c_int32, C.POINTER(C.c_uint64)]),
+    "mppi_refpath_create": (C.c_int, [C.c_int32, _FP, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_float,
+                                      C.POINTER(_P)]),
+    "mppi_refpath_destroy": (None, [_P]),
+    "mppi_refpath_update": (C.c_int, [_P, _FP, _FP, _P]),
+    "mppi_refpath_index": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), _P]),
     "mppi_kernel_timing": (C.c_int, [_P, C.c_int32]),
     "mppi_kernel_time_ms": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "mppi_philox4x32_10": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),

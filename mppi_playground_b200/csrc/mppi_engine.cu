@@ -998,6 +998,74 @@ int mppi_selftest(int32_t device, uint64_t mismatches[3]) {
   return MPPI_OK;
 }
 
+// ---- racing reference path on the device ("next" row 1) -----------------------------
+struct MppiRefPath {
+  int device = 0, n = 0, rows = 0;
+  float v_max = 0.f;
+  float* d_path = nullptr;
+  int* d_dind = nullptr;
+  int* d_cind = nullptr;
+};
+
+int mppi_refpath_create(int32_t device, const float* h_path, int32_t n, const int32_t* h_index_offsets, int32_t rows,
+                        float v_max, MppiRefPath** out) {
+  if (!h_path || !h_index_offsets || !out || n < 1 || rows < 1) return fail(MPPI_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(device));
+  MppiRefPath* r = new (std::nothrow) MppiRefPath();
+  if (!r) return fail(MPPI_ERR_INVALID, "out of host memory");
+  r->device = device;
+  r->n = n;
+  r->rows = rows;
+  r->v_max = v_max;
+  cudaError_t e = cudaMalloc((void**)&r->d_path, (size_t)n * 12);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&r->d_dind, (size_t)rows * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&r->d_cind, 16);
+  if (e == cudaSuccess) e = cudaMemcpy(r->d_path, h_path, (size_t)n * 12, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(r->d_dind, h_index_offsets, (size_t)rows * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(r->d_cind, 0, 16);
+  if (e != cudaSuccess) {
+    cudaFree(r->d_path);
+    cudaFree(r->d_dind);
+    cudaFree(r->d_cind);
+    delete r;
+    return fail(MPPI_ERR_CUDA, "refpath create: %s", cudaGetErrorString(e));
+  }
+  *out = r;
+  return MPPI_OK;
+}
+
+void mppi_refpath_destroy(MppiRefPath* r) {
+  if (!r) return;
+  cudaSetDevice(r->device);
+  cudaFree(r->d_path);
+  cudaFree(r->d_dind);
+  cudaFree(r->d_cind);
+  delete r;
+}
+
+int mppi_refpath_update(MppiRefPath* r, const float* d_state, float* d_refpath_out, void* stream) {
+  if (!r || !d_state || !d_refpath_out) return fail(MPPI_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(r->device));
+  racing_refpath_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(r->d_path, r->n, d_state, r->d_dind, r->rows, r->v_max,
+                                                               r->d_cind, d_refpath_out);
+  CUDA_TRY(cudaGetLastError());
+  return MPPI_OK;
+}
+
+int mppi_refpath_index(MppiRefPath* r, int32_t set_value, int32_t* current, void* stream) {
+  if (!r) return fail(MPPI_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(r->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (set_value >= 0) CUDA_TRY(cudaMemcpyAsync(r->d_cind, &set_value, 4, cudaMemcpyHostToDevice, st));
+  if (current) {
+    CUDA_TRY(cudaMemcpyAsync(current, r->d_cind, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  } else if (set_value >= 0) {
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return MPPI_OK;
+}
+
 int mppi_kernel_timing(MppiHandle* h, int32_t enable) {
   if (!h) return fail(MPPI_ERR_INVALID, "null handle");
   h->timing = enable != 0;

@@ -1245,4 +1245,75 @@ __global__ void rollout_actions_kernel(SolveParams p, const float* __restrict__ 
   for (int d = 0; d < DS; ++d) out[p.T * DS + d] = s[d];
 }
 
+// racing_controller.calc_ref_trajectory (example/racing.py:161-218) on the device: nearest centre-line
+// point (first minimum of the fp32 distance, never behind the carried index), then one row per stage at the
+// host-precomputed index offsets (the reference accumulates them in Python fp64, see
+// models.racing_reference_path). One block. *cind is read and updated in place.
+__global__ void __launch_bounds__(1024, 1) racing_refpath_kernel(const float* __restrict__ path, int n,
+                                                                  const float* __restrict__ state,
+                                                                  const int* __restrict__ dind, int rows, float v_max,
+                                                                  int* cind, float* __restrict__ out) {
+  __shared__ float s_d[32];
+  __shared__ int s_i[32];
+  __shared__ int s_ind, s_beyond;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float sx = state[0], sy = state[1];
+  float best = INFINITY;
+  int besti = 0x7fffffff;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const float dx = path[3 * i] - sx, dy = path[3 * i + 1] - sy;
+    float d = dx * dx + dy * dy;  // squared distance: same argmin as the hypot, formed like the host twin
+    if (d < best) {  // strided scan visits indices in increasing order per thread
+      best = d;
+      besti = i;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float od = __shfl_xor_sync(kFullMask, best, o);
+    int oi = __shfl_xor_sync(kFullMask, besti, o);
+    if (od < best || (od == best && oi < besti)) {
+      best = od;
+      besti = oi;
+    }
+  }
+  if (lane == 0) {
+    s_d[warp] = best;
+    s_i[warp] = besti;
+  }
+  if (tid == 0) s_beyond = 0;
+  __syncthreads();
+  if (warp == 0) {
+    best = (lane < (int)(blockDim.x >> 5)) ? s_d[lane] : INFINITY;
+    besti = (lane < (int)(blockDim.x >> 5)) ? s_i[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float od = __shfl_xor_sync(kFullMask, best, o);
+      int oi = __shfl_xor_sync(kFullMask, besti, o);
+      if (od < best || (od == best && oi < besti)) {
+        best = od;
+        besti = oi;
+      }
+    }
+    if (lane == 0) {
+      int ind = max(*cind, besti);  // racing.py:201-202
+      s_ind = ind;
+      *cind = ind;
+    }
+  }
+  __syncthreads();
+  const int ind = s_ind;
+  for (int i = tid; i < rows; i += blockDim.x)
+    if (ind + dind[i] >= n) s_beyond = 1;  // benign race: every writer stores 1
+  __syncthreads();
+  const float v = s_beyond ? 0.0f : v_max;  // racing.py:213-216: one row past the end zeroes every target speed
+  for (int i = tid; i < rows; i += blockDim.x) {
+    const int idx = min(ind + dind[i], n - 1);
+    out[4 * i + 0] = path[3 * idx + 0];
+    out[4 * i + 1] = path[3 * idx + 1];
+    out[4 * i + 2] = path[3 * idx + 2];
+    out[4 * i + 3] = v;
+  }
+}
+
 }  // namespace mppi

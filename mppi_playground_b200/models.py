@@ -95,8 +95,8 @@ class Navigation2DModel(_Descriptor):
         self.goal, self.lim, self.dt, self.obstacle_weight = tuple(goal), tuple(lim), dt, obstacle_weight
 
     def params(self):
-        return [self.u_min[0].item(), self.u_max[0].item(), self.u_min[1].item(), self.u_max[1].item(),
-                self.goal[0], self.goal[1], *self.lim, self.dt, self.obstacle_weight]
+        lo, hi = self.u_min.tolist(), self.u_max.tolist()
+        return [lo[0], hi[0], lo[1], hi[1], self.goal[0], self.goal[1], *self.lim, self.dt, self.obstacle_weight]
 
     def maps(self):
         return [(self.obstacle_grid, self.cell_size, *self.origin)]
@@ -122,9 +122,9 @@ class RacingModel(_Descriptor):
         self.reference_path_tensor: Optional[torch.Tensor] = None
 
     def params(self):
-        return [self.u_min[0].item(), self.u_max[0].item(), self.u_min[1].item(), self.u_max[1].item(),
-                self.wheelbase, self.v_max, *self.lim, self.dt, self.Qc, self.Ql, self.Qv, self.Qo, self.Qin,
-                self.Qdin]
+        lo, hi = self.u_min.tolist(), self.u_max.tolist()
+        return [lo[0], hi[0], lo[1], hi[1], self.wheelbase, self.v_max, *self.lim, self.dt, self.Qc, self.Ql,
+                self.Qv, self.Qo, self.Qin, self.Qdin]
 
     def maps(self):
         return [(self.obstacle_grid, float(self.cell_size[0]), float(self.origin[0][0]), float(self.origin[0][1])),
@@ -147,17 +147,77 @@ def racing_reference_path(state: torch.Tensor, path: torch.Tensor, cind: int, ho
     n = path.shape[0]
     # the reference accumulates `travel += interval` in fp64 and rounds half-to-even per row;
     # the running sum is kept (81 scalar adds) so that x.5 cases land on the same index
-    travel, dinds = float(lookahead_distance), []
-    for _ in range(horizon + 1):
-        travel += reference_path_interval
-        dinds.append(int(round(travel / DL)))
-    dind = torch.tensor(dinds, dtype=torch.long)
+    dind = torch.tensor(reference_index_offsets(horizon, DL, lookahead_distance, reference_path_interval),
+                        dtype=torch.long)
     idx = ind + dind
     beyond = idx >= n
     xref = torch.zeros(horizon + 1, 4, dtype=path.dtype, device=path.device)
     xref[:, :3] = path[idx.clamp(max=n - 1).to(path.device)]
     xref[:, 3] = 0.0 if bool(beyond.any()) else v_max
     return xref, ind
+
+
+def reference_index_offsets(horizon: int, DL: float = 0.1, lookahead_distance: float = 3.0,
+                            reference_path_interval: float = 0.85) -> List[int]:
+    """int(round(travel / DL)) per reference row, with the reference's running fp64 sum (racing.py:205-208)."""
+    travel, out = float(lookahead_distance), []
+    for _ in range(horizon + 1):
+        travel += reference_path_interval
+        out.append(int(round(travel / DL)))
+    return out
+
+
+class RacingReferencePath:
+    """Device-resident ``calc_ref_trajectory`` (example/racing.py:161-218): keeps the centre line and the
+    carried path index on the GPU; ``update(state)`` returns the [T+1,4] reference path for a device state
+    with one small kernel and no host synchronisation, ready to be handed to the solver."""
+
+    def __init__(self, center_path: torch.Tensor, horizon: int, v_max: float = 8.0, DL: float = 0.1,
+                 lookahead_distance: float = 3.0, reference_path_interval: float = 0.85, device=None):
+        import ctypes as C
+
+        self._lib = _capi.load()
+        self.device = torch.device(device if device is not None else "cuda")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.horizon = horizon
+        path = torch.as_tensor(center_path).detach().to("cpu", torch.float32).contiguous()
+        assert path.ndim == 2 and path.shape[1] == 3
+        offs = reference_index_offsets(horizon, DL, lookahead_distance, reference_path_interval)
+        arr = (C.c_int32 * len(offs))(*offs)
+        h = C.c_void_p()
+        _capi.check(self._lib.mppi_refpath_create(self.device.index, path.data_ptr(), path.shape[0], arr, len(offs),
+                                                  float(v_max), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self._lib.mppi_refpath_destroy(h)
+            except Exception:
+                pass
+
+    def update(self, state: torch.Tensor) -> torch.Tensor:
+        st = state.detach().to(self.device, torch.float32).contiguous()
+        out = torch.empty(self.horizon + 1, 4, device=self.device, dtype=torch.float32)
+        _capi.check(self._lib.mppi_refpath_update(self._h, st.data_ptr(), out.data_ptr(),
+                                                  torch.cuda.current_stream(self.device).cuda_stream))
+        return out
+
+    @property
+    def path_index(self) -> int:
+        import ctypes as C
+
+        v = C.c_int32()
+        _capi.check(self._lib.mppi_refpath_index(self._h, -1, C.byref(v),
+                                                 torch.cuda.current_stream(self.device).cuda_stream))
+        return v.value
+
+    @path_index.setter
+    def path_index(self, value: int) -> None:
+        _capi.check(self._lib.mppi_refpath_index(self._h, int(value), None,
+                                                 torch.cuda.current_stream(self.device).cuda_stream))
 
 
 # ---- bindings onto the reference's live objects -----------------------------------------
@@ -181,12 +241,15 @@ class _ReferenceRacing(Binding):
 
     def __init__(self, env, controller):
         self.env, self.ctl = env, controller
+        # env constants live in (possibly CUDA) tensors: read them ONCE - a float() of a device tensor is a
+        # device synchronisation, and these do not change after RacingEnv.__init__ (racing_env.py:37-42)
+        self._env_params = [float(env.u_min[0]), float(env.u_max[0]), float(env.u_min[1]), float(env.u_max[1]),
+                            float(env.L), float(env.V_MAX), *_lim4(env._obstacle_map),
+                            0.1]  # delta_t default, racing_env.py:328
 
     def params(self):
-        e, c = self.env, self.ctl
-        return [float(e.u_min[0]), float(e.u_max[0]), float(e.u_min[1]), float(e.u_max[1]), float(e.L),
-                float(e.V_MAX), *_lim4(e._obstacle_map), 0.1,  # delta_t default, racing_env.py:328
-                float(c.Qc), float(c.Ql), float(c.Qv), float(c.Qo), float(c.Qin), float(c.Qdin)]
+        c = self.ctl  # the cost weights are plain Python attributes, re-read every solve (racing.py:41-46)
+        return [*self._env_params, float(c.Qc), float(c.Ql), float(c.Qv), float(c.Qo), float(c.Qin), float(c.Qdin)]
 
     def maps(self):
         c = self.ctl
@@ -206,11 +269,13 @@ class _ReferenceNavigation2D(Binding):
 
     def __init__(self, env):
         self.env = env
+        e = env  # constants of Navigation2DEnv.__init__ (navigation_2d.py:53-71), read once (device tensors)
+        self._params = [float(e.u_min[0]), float(e.u_max[0]), float(e.u_min[1]), float(e.u_max[1]),
+                        float(e._goal_pos[0]), float(e._goal_pos[1]), *_lim4(e._obstacle_map), 0.1,
+                        10000.0]  # navigation_2d.py:219,277
 
     def params(self):
-        e = self.env
-        return [float(e.u_min[0]), float(e.u_max[0]), float(e.u_min[1]), float(e.u_max[1]), float(e._goal_pos[0]),
-                float(e._goal_pos[1]), *_lim4(e._obstacle_map), 0.1, 10000.0]  # navigation_2d.py:219,277
+        return list(self._params)
 
     def maps(self):
         return [_map_spec(self.env._obstacle_map)]

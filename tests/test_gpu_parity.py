@@ -478,3 +478,36 @@ def test_cost_weights_and_maps_are_reread_every_solve():
     solver.reset()
     oracle.reset()
     assert float(solver._previous_action_seq.abs().max()) == 0.0
+
+
+def test_device_reference_path_matches_host_twin():
+    """RacingReferencePath (device calc_ref_trajectory) against the host twin, which is itself checked
+    against the live reference (tests/test_reference_live.py) and the recorded golden paths."""
+    import mppi_playground_b200 as eng
+
+    env = fx.load_env_racing()
+    gen = eng.RacingReferencePath(env.center_path, 80, v_max=env.v_max)
+    state, cind = env.start_state.clone(), 0
+    g = torch.Generator().manual_seed(3)
+    for step in range(40):
+        want, cind = eng.racing_reference_path(state, env.center_path, cind, 80, v_max=env.v_max)
+        got = gen.update(state.cuda())
+        assert gen.path_index == cind
+        np.testing.assert_array_equal(got.cpu().numpy(), want.numpy())
+        # move along the track with some lateral scatter
+        j = min(len(env.center_path) - 1, cind + 40 + int(torch.randint(0, 60, (1,), generator=g)))
+        state = torch.tensor([env.center_path[j, 0] + 0.7 * float(torch.randn(1, generator=g)),
+                              env.center_path[j, 1] + 0.7 * float(torch.randn(1, generator=g)),
+                              float(env.center_path[j, 2]), 6.0])
+    # end of the course: target speeds drop to zero, rows clamp to the last point
+    gen.path_index = len(env.center_path) - 30
+    got = gen.update(state.cuda()).cpu()
+    want, _ = eng.racing_reference_path(state, env.center_path, len(env.center_path) - 30, 80, v_max=env.v_max)
+    np.testing.assert_array_equal(got.numpy(), want.numpy())
+    assert float(got[:, 3].abs().max()) == 0.0
+    # the generated path drives a solve directly (no host copy of the path)
+    model, solver = build_engine(dict(model="racing", horizon=80, num_samples=1024, sigmas=[0.5, 0.1], lambda_=1.0))
+    gen.path_index = 0
+    model.reference_path_tensor = gen.update(env.start_state.cuda())
+    a, s = solver.forward(env.start_state)
+    assert torch.isfinite(a).all() and torch.isfinite(s).all()
