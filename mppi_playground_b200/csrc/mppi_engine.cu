@@ -343,6 +343,14 @@ bool prove_exact_division(float c, float* rcp_out) {
   return bad == 0;
 }
 
+// every position inside the dynamics' clamp box maps to a cell index in [0, W] x [0, H] (the bordered
+// grid then answers without bounds logic); same fp32 arithmetic as the device (IEEE divide, add, rint)
+bool box_maps_inside(const SolveParams& b, int slot, float x_lo, float x_hi, float y_lo, float y_hi) {
+  auto cell = [&](float x, float o) { return (long long)nearbyintf(x / b.map_cell[slot] + o); };
+  return cell(x_lo, b.map_ox[slot]) >= 0 && cell(x_hi, b.map_ox[slot]) <= b.map_W[slot] &&
+         cell(y_lo, b.map_oy[slot]) >= 0 && cell(y_hi, b.map_oy[slot]) <= b.map_H[slot] && x_lo <= x_hi && y_lo <= y_hi;
+}
+
 void refresh_model_flags(MppiHandle* h) {
   SolveParams& b = h->base;
   int flags = 0;
@@ -368,13 +376,15 @@ void refresh_model_flags(MppiHandle* h) {
     const double smax = std::max(fabs((double)v[2]), fabs((double)v[3]));
     if (smax <= 0.78 && v[4] > 0.0f) {
       const double yaw = fabs((double)v[5]) * tan(smax) / (double)v[4] * fabs((double)v[10]);
-      if (yaw < 6.0 && clamp_redundant && (flags & kFlagSameMapGeometry) && b.map_fastdiv[0] && h->wheelbase_exact &&
+      if (yaw < 6.0 && clamp_redundant && (flags & kFlagSameMapGeometry) &&
+          box_maps_inside(b, 0, v[6], v[7], v[8], v[9]) && b.map_fastdiv[0] && h->wheelbase_exact &&
           fabsf(b.map_ox[0]) >= 1e-20f && fabsf(b.map_oy[0]) >= 1e-20f)
         flags |= kFlagBounded;
     }
   } else if (h->cfg.model == MPPI_MODEL_NAVIGATION2D) {
     const double wmax = std::max(fabs((double)v[2]), fabs((double)v[3]));
-    if (wmax * fabs((double)v[10]) < 6.0 && clamp_redundant && h->map_set[0] && b.map_fastdiv[0] && fabsf(b.map_ox[0]) >= 1e-20f &&
+    if (wmax * fabs((double)v[10]) < 6.0 && clamp_redundant && h->map_set[0] &&
+        box_maps_inside(b, 0, v[6], v[7], v[8], v[9]) && b.map_fastdiv[0] && fabsf(b.map_ox[0]) >= 1e-20f &&
         fabsf(b.map_oy[0]) >= 1e-20f)
       flags |= kFlagBounded;
   }
@@ -595,8 +605,8 @@ int mppi_set_map(MppiHandle* h, int32_t slot, const float* grid, int32_t on_devi
   if (slot < 0 || slot >= h->mi.maps) return fail(MPPI_ERR_INVALID, "model has %d map slots, got slot %d", h->mi.maps, slot);
   if (W < 1 || H < 1 || !(cell > 0.0f)) return fail(MPPI_ERR_INVALID, "bad map geometry");
   CUDA_TRY(cudaSetDevice(h->device));
-  const int words = (H + 31) / 32;
-  const size_t bytes = pad16((size_t)W * words * 4);
+  const int words = (H + 1 + 31) / 32;  // + the out-of-bounds border bit (see MapView)
+  const size_t bytes = pad16((size_t)(W + 1) * words * 4);
   const float* d_grid = grid;
   float* tmp = nullptr;
   if (!on_device) {
@@ -613,7 +623,7 @@ int mppi_set_map(MppiHandle* h, int32_t slot, const float* grid, int32_t on_devi
   cudaError_t e = cudaMalloc((void**)&h->d_map[slot], bytes);
   if (e == cudaSuccess) e = cudaMemset(h->d_map[slot], 0, bytes);
   if (e == cudaSuccess) {
-    int n = W * words;
+    int n = (W + 1) * words;
     pack_map_kernel<<<(n + 255) / 256, 256>>>(d_grid, W, H, words, h->d_map[slot]);
     e = cudaDeviceSynchronize();
   }

@@ -1157,13 +1157,15 @@ __global__ void selftest_kernel(unsigned long long* bad /*[3]*/) {
 }
 
 __global__ void pack_map_kernel(const float* __restrict__ grid, int W, int H, int words, uint32_t* __restrict__ bits) {
+  // (W + 1) rows x `words` words; row W and bit H of every row form the out-of-bounds border of ones
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= W * words) return;
+  if (idx >= (W + 1) * words) return;
   int ix = idx / words, wj = idx - ix * words;
   uint32_t v = 0;
   for (int b = 0; b < 32; ++b) {
     int iy = wj * 32 + b;
-    if (iy < H && grid[(size_t)ix * H + iy] != 0.0f) v |= (1u << b);
+    bool one = (iy == H) || (iy < H && (ix == W || grid[(size_t)ix * H + iy] != 0.0f));
+    if (one) v |= (1u << b);
   }
   bits[idx] = v;
 }

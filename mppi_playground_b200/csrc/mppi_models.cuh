@@ -42,7 +42,8 @@ __device__ __forceinline__ float div_exact(float x, const ExactDiv& d) {
   return x / d.c;
 }
 
-// Occupancy grid, bit-packed: bit (iy & 31) of word [ix * words + (iy >> 5)].
+// Occupancy grid, bit-packed: bit (iy & 31) of word [ix * words + (iy >> 5)]; (W + 1) rows of
+// words = ceil((H + 1) / 32) words: row W and bit H of every row are the out-of-bounds border (ones).
 struct MapView {
   const uint32_t* bits;
   int W, H, words;
@@ -73,6 +74,14 @@ __device__ __forceinline__ float map_value(const MapView& m, int ix, int iy) {
   uint32_t w = m.bits[ix * m.words + (iy >> 5)];  // :195
   float occ = (float)((w >> (iy & 31)) & 1u);
   return oob ? 1.0f : occ;  // :198
+}
+
+// The packed grid carries one extra row (ix == W) and one extra bit per row (iy == H) of ones, so a
+// cell index in [0, W] x [0, H] reads the out-of-bounds value 1.0 without any bounds logic. Only used
+// when the host proved that every rolled-out position maps into that range (kFlagBounded).
+__device__ __forceinline__ float map_value_bordered(const MapView& m, int ix, int iy) {
+  const uint32_t w = m.bits[ix * m.words + (iy >> 5)];
+  return (float)((w >> (iy & 31)) & 1u);
 }
 
 // src/envs/obstacle_map_2d.py:168-200 == src/envs/lane_map_2d.py:90-122.
@@ -218,8 +227,9 @@ struct Navigation2D {  // src/envs/navigation_2d.py:218-279
     s[1] = clampf(ny, p[8], p[9]);
     s[2] = nth;
   }
-  __device__ static __forceinline__ bool state_in_bounds(const Ctx&, const float* state) {
-    return fabsf(state[2]) < 9.0f && fabsf(state[0]) <= kFastDivMax && fabsf(state[1]) <= kFastDivMax;
+  __device__ static __forceinline__ bool state_in_bounds(const Ctx& c, const float* state) {
+    const float* p = c.p->v;  // heading range, position inside the dynamics' clamp box
+    return fabsf(state[2]) < 9.0f && state[0] >= p[6] && state[0] <= p[7] && state[1] >= p[8] && state[1] <= p[9];
   }
   template <bool kBounded = false>
   __device__ static __forceinline__ float cost(const Ctx& c, const float (&s)[DS], const float (&)[DU],
@@ -227,8 +237,8 @@ struct Navigation2D {  // src/envs/navigation_2d.py:218-279
     const float* p = c.p->v;
     float dx = s[0] - p[4], dy = s[1] - p[5];
     float goal = sqrtf(dx * dx + dy * dy);  // :269
-    float occ = kBounded ? map_value(c.map, map_cell_bounded(s[0], c.map.cell, c.map.ox),
-                                     map_cell_bounded(s[1], c.map.cell, c.map.oy))
+    float occ = kBounded ? map_value_bordered(c.map, map_cell_bounded(s[0], c.map.cell, c.map.ox),
+                                              map_cell_bounded(s[1], c.map.cell, c.map.oy))
                          : map_lookup(c.map, s[0], s[1]);
     return goal + p[11] * occ;  // :271-277
   }
@@ -326,8 +336,9 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
     s[3] = clampf(nv, -p[5], p[5]);
   }
   __device__ static __forceinline__ bool state_in_bounds(const Ctx& c, const float* state) {
-    return fabsf(state[2]) < 9.0f && fabsf(state[3]) <= c.p->v[5] && fabsf(state[0]) <= kFastDivMax &&
-           fabsf(state[1]) <= kFastDivMax;  // heading range, |v| <= v_max, finite position
+    const float* p = c.p->v;  // heading range, |v| <= v_max, position inside the dynamics' clamp box
+    return fabsf(state[2]) < 9.0f && fabsf(state[3]) <= p[5] && state[0] >= p[6] && state[0] <= p[7] &&
+           state[1] >= p[8] && state[1] <= p[9];
   }
   template <bool kBounded = false>
   __device__ static __forceinline__ float cost(const Ctx& c, const float (&s)[DS], const float (&u)[DU],
@@ -344,7 +355,7 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
     if (kBounded) {  // kFlagBounded implies: one shared geometry, proven exact division
       int ix = map_cell_bounded(s[0], c.obstacle.cell, c.obstacle.ox);
       int iy = map_cell_bounded(s[1], c.obstacle.cell, c.obstacle.oy);
-      occ = map_value(c.obstacle, ix, iy) + map_value(c.lane, ix, iy);
+      occ = map_value_bordered(c.obstacle, ix, iy) + map_value_bordered(c.lane, ix, iy);
     } else if (c.p->flags & kFlagSameMapGeometry) {  // one cell index serves both grids
       int ix = map_cell(s[0], c.obstacle.cell, c.obstacle.ox), iy = map_cell(s[1], c.obstacle.cell, c.obstacle.oy);
       occ = map_value(c.obstacle, ix, iy) + map_value(c.lane, ix, iy);
