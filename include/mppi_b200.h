@@ -214,8 +214,9 @@ int mppi_map_info(const MppiHandle* h, int32_t slot, int32_t* fast_division, uin
 int mppi_block_trace(MppiHandle* h, int32_t enable, uint64_t* h_out, int32_t max_blocks);
 /* Exhaustive device self-test of the bounded arithmetic helpers against the general ones, over every
  * fp32 input of their claimed range: mismatches[0] tan_quarter vs tanf (|x| <= 0.78), [1]
- * wrap_angle_bounded vs wrap_angle (|x| < 9), [2] floored_remainder vs the fmodf form. All must be 0. */
-int mppi_selftest(int32_t device, uint64_t mismatches[3]);
+ * wrap_angle_bounded vs wrap_angle (|x| < 9), [2] floored_remainder vs the fmodf form, [3] sincos_bounded
+ * vs sincosf (|x| <= 4). All must be 0. */
+int mppi_selftest(int32_t device, uint64_t mismatches[4]);
 /* ---- racing reference path on the device ("next" row: example/racing.py:161-218) ------------------
  * racing_controller.calc_ref_trajectory runs on the host before every solve in the reference (a Python
  * loop over the N centre-line points). MppiRefPath keeps the centre line [n,3] (x, y, yaw), the per-row

@@ -993,18 +993,18 @@ int mppi_block_trace(MppiHandle* h, int32_t enable, uint64_t* h_out, int32_t max
   return MPPI_OK;
 }
 
-int mppi_selftest(int32_t device, uint64_t mismatches[3]) {
+int mppi_selftest(int32_t device, uint64_t mismatches[4]) {
   if (!mismatches) return fail(MPPI_ERR_INVALID, "null argument");
   CUDA_TRY(cudaSetDevice(device));
   unsigned long long* d = nullptr;
-  CUDA_TRY(cudaMalloc((void**)&d, 24));
-  CUDA_TRY(cudaMemset(d, 0, 24));
+  CUDA_TRY(cudaMalloc((void**)&d, 32));
+  CUDA_TRY(cudaMemset(d, 0, 32));
   selftest_kernel<<<148 * 8, 256>>>(d);
-  unsigned long long hbad[3] = {1, 1, 1};
-  cudaError_t e = cudaMemcpy(hbad, d, 24, cudaMemcpyDeviceToHost);
+  unsigned long long hbad[4] = {1, 1, 1, 1};
+  cudaError_t e = cudaMemcpy(hbad, d, 32, cudaMemcpyDeviceToHost);
   cudaFree(d);
   if (e != cudaSuccess) return fail(MPPI_ERR_CUDA, "selftest: %s", cudaGetErrorString(e));
-  for (int i = 0; i < 3; ++i) mismatches[i] = hbad[i];
+  for (int i = 0; i < 4; ++i) mismatches[i] = hbad[i];
   return MPPI_OK;
 }
 

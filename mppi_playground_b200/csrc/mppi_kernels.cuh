@@ -1131,13 +1131,19 @@ __global__ void check_fastdiv_kernel(float c, float r, unsigned long long* misma
 
 // Exhaustive self-tests of the bounded helpers against the general ones (tests call these through
 // mppi_selftest): every float in the claimed range, bit-for-bit.
-__global__ void selftest_kernel(unsigned long long* bad /*[3]*/) {
-  unsigned b_tan = 0, b_wrap = 0, b_rem = 0;
+__global__ void selftest_kernel(unsigned long long* bad /*[4]*/) {
+  unsigned b_tan = 0, b_wrap = 0, b_rem = 0, b_sc = 0;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 32); i += stride) {
     const float x = __uint_as_float((unsigned)i);
     const float ax = fabsf(x);
     if (ax <= 0.78f) b_tan += (__float_as_uint(tan_quarter(x)) != __float_as_uint(tanf(x))) ? 1u : 0u;
+    if (ax <= 4.0f) {
+      float s0, c0, s1, c1;
+      sincos_bounded(x, &s0, &c0);
+      sincosf(x, &s1, &c1);
+      b_sc += (__float_as_uint(s0) != __float_as_uint(s1) || __float_as_uint(c0) != __float_as_uint(c1)) ? 1u : 0u;
+    }
     if (ax < 9.0f) b_wrap += (__float_as_uint(wrap_angle_bounded(x)) != __float_as_uint(wrap_angle(x))) ? 1u : 0u;
     if (ax < 1e30f) {  // lean floored remainder vs the textbook fmodf form
       const float b = 6.28318548202514648f;
@@ -1149,7 +1155,9 @@ __global__ void selftest_kernel(unsigned long long* bad /*[3]*/) {
   b_tan = __reduce_add_sync(kFullMask, b_tan);
   b_wrap = __reduce_add_sync(kFullMask, b_wrap);
   b_rem = __reduce_add_sync(kFullMask, b_rem);
+  b_sc = __reduce_add_sync(kFullMask, b_sc);
   if ((threadIdx.x & 31) == 0) {
+    if (b_sc) atomicAdd(bad + 3, (unsigned long long)b_sc);
     if (b_tan) atomicAdd(bad + 0, (unsigned long long)b_tan);
     if (b_wrap) atomicAdd(bad + 1, (unsigned long long)b_wrap);
     if (b_rem) atomicAdd(bad + 2, (unsigned long long)b_rem);

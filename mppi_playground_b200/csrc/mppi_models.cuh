@@ -219,7 +219,10 @@ struct Navigation2D {  // src/envs/navigation_2d.py:218-279
     float w = kBounded ? u[1] : clampf(u[1], p[2], p[3]);
     float th = kBounded ? wrap_angle_bounded(s[2]) : wrap_angle(s[2]);  // :237
     float st, ct;
-    sincosf(th, &st, &ct);
+    if (kBounded)
+      sincos_bounded(th, &st, &ct);
+    else
+      sincosf(th, &st, &ct);
     float nx = s[0] + v * ct * p[10];  // :239-241
     float ny = s[1] + v * st * p[10];
     float nth = kBounded ? wrap_angle_bounded(th + w * p[10]) : wrap_angle(th + w * p[10]);
@@ -322,7 +325,10 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
     float steer = kBounded ? u[1] : clampf(u[1], p[2], p[3]);
     float th = kBounded ? wrap_angle_bounded(s[2]) : wrap_angle(s[2]);  // :347
     float st, ct;
-    sincosf(th, &st, &ct);
+    if (kBounded)
+      sincos_bounded(th, &st, &ct);
+    else
+      sincosf(th, &st, &ct);
     float dx = s[3] * ct;  // :349-352
     float dy = s[3] * st;
     float dth = yaw_rate<kBounded>(*c.p, s[3], kBounded ? tan_quarter(steer) : tanf(steer));

@@ -257,9 +257,9 @@ def test_bounded_helpers_are_bit_identical_over_their_whole_range():
 
     from mppi_playground_b200 import _capi
 
-    bad = (C.c_uint64 * 3)()
+    bad = (C.c_uint64 * 4)()
     _capi.check(_capi.load().mppi_selftest(0, bad))
-    assert list(bad) == [0, 0, 0], f"mismatches tan/wrap/remainder = {list(bad)}"
+    assert list(bad) == [0, 0, 0, 0], f"mismatches tan/wrap/remainder/sincos = {list(bad)}"
 
 
 def test_bounded_and_general_rollouts_agree_bit_for_bit():
