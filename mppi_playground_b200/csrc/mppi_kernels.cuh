@@ -105,7 +105,7 @@ __host__ __device__ inline unsigned align_up(unsigned x, unsigned a) { return (x
 // floats of scratch finish_solve needs: N (doubles) | opt | y | scales | Combined | tail rollout
 __host__ __device__ inline unsigned finish_scratch_core(int E_pad, int T, int tail_per_step) {
   return align_up((unsigned)E_pad * 20 + 256 * 4 + 64 + (unsigned)E_pad * 8 * kMaxSegments +
-                      (unsigned)tail_per_step * (unsigned)(T + 1) * 4,
+                      (unsigned)tail_per_step * (unsigned)(T + 9) * 4,
                   16);
 }
 
@@ -1145,6 +1145,8 @@ __global__ void selftest_kernel(unsigned long long* bad /*[4]*/) {
       b_sc += (__float_as_uint(s0) != __float_as_uint(s1) || __float_as_uint(c0) != __float_as_uint(c1)) ? 1u : 0u;
     }
     if (ax < 9.0f) b_wrap += (__float_as_uint(wrap_angle_bounded(x)) != __float_as_uint(wrap_angle(x))) ? 1u : 0u;
+    if (x >= -3.14159274101257324f && x < 9.0f)
+      b_wrap += (__float_as_uint(wrap_angle_nonneg(x)) != __float_as_uint(wrap_angle(x))) ? 1u : 0u;
     if (ax < 1e30f) {  // lean floored remainder vs the textbook fmodf form
       const float b = 6.28318548202514648f;
       float m = fmodf(x, b);

@@ -89,24 +89,31 @@ __device__ __forceinline__ float map_lookup(const MapView& m, float x, float y) 
   return map_value(m, map_cell(x, m.cell, m.ox), map_cell(y, m.cell, m.oy));
 }
 
-// Heading recurrence of the unicycle / bicycle models, one thread; the per-stage increments inc(t)
-// do not depend on the heading, so they are evaluated eight at a time ahead of the dependent chain:
-// thw[t] = wrap(ths[t]); ths[t+1] = wrap(thw[t] + inc(t)).
-template <bool kBounded, class Inc>
-__device__ __forceinline__ void heading_chain(float th, Inc inc, float* thw, float* ths, int T) {
+// Heading recurrence of the unicycle / bicycle models, one thread; the per-stage increments inc[t] do
+// not depend on the heading, so they are fetched eight at a time ahead of the dependent chain:
+// thw[t] = wrap(ths[t]); ths[t+1] = wrap(thw[t] + inc[t]). Arrays are padded like serial_chain's.
+// kBounded: after the first stage every heading is itself a wrap output (>= -pi), so the inner wrap
+// only needs the upper fold (wrap_angle_nonneg).
+template <bool kBounded>
+__device__ __forceinline__ void heading_chain(float th, const float* inc, float* thw, float* ths, int T) {
   ths[0] = th;
+  bool first = true;
   for (int t0 = 0; t0 < T; t0 += 8) {
     float cc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) cc[j] = (t0 + j < T) ? inc(t0 + j) : 0.0f;
+    for (int j = 0; j < 8; ++j) cc[j] = inc[t0 + j];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (t0 + j < T) {
-        const float w = kBounded ? wrap_angle_bounded(th) : wrap_angle(th);
-        thw[t0 + j] = w;
-        th = kBounded ? wrap_angle_bounded(w + cc[j]) : wrap_angle(w + cc[j]);
-        ths[t0 + j + 1] = th;
-      }
+    for (int j = 0; j < 8; ++j) {
+      float w;
+      if (kBounded)
+        w = (first && j == 0) ? wrap_angle_bounded(th) : wrap_angle_nonneg(th);
+      else
+        w = wrap_angle(th);
+      thw[t0 + j] = w;
+      th = kBounded ? wrap_angle_bounded(w + cc[j]) : wrap_angle(w + cc[j]);
+      ths[t0 + j + 1] = th;
+    }
+    first = false;
   }
 }
 
@@ -248,13 +255,15 @@ struct Navigation2D {  // src/envs/navigation_2d.py:218-279
   // Optimal-trajectory rollout by one block (mppi.py:508-524). Same operations on the same values as
   // T calls of step(); only the schedule differs: the heading chain is the one serial part, the
   // sin/cos of every stage and the position increments are evaluated by T threads at once.
-  // scratch: 8 * (T + 1) floats.
+  // scratch: 8 * (T + 9) floats.
   __device__ static __noinline__ void rollout_block(const Ctx& c, const float* state, const float* opt, int T, float* out,
                                        float* scratch) {
     const float* p = c.p->v;
     const int tid = threadIdx.x, nt = blockDim.x;
-    float *wdt = scratch, *ths = wdt + (T + 1), *thw = ths + (T + 1), *dx = thw + (T + 1), *dy = dx + (T + 1),
-          *xs = dy + (T + 1), *ys = xs + (T + 1), *vc = ys + (T + 1);
+    const int S = T + 9;  // room for whole groups of 8 (see serial_chain)
+    float *wdt = scratch, *ths = wdt + S, *thw = ths + S, *dx = thw + S, *dy = dx + S, *xs = dy + S, *ys = xs + S,
+          *vc = ys + S;
+    for (int t = T + tid; t < S; t += nt) wdt[t] = dx[t] = dy[t] = 0.0f;
     for (int t = tid; t < T; t += nt) {
       vc[t] = clampf(opt[2 * t], p[0], p[1]);
       wdt[t] = clampf(opt[2 * t + 1], p[2], p[3]) * p[10];
@@ -262,9 +271,9 @@ struct Navigation2D {  // src/envs/navigation_2d.py:218-279
     __syncthreads();
     if (tid == 0) {  // heading: S[t+1].theta = wrap(wrap(S[t].theta) + c_t); thw keeps the inner wrap
       if ((c.p->flags & kFlagBounded) && state_in_bounds(c, state))
-        heading_chain<true>(state[2], [wdt](int t) { return wdt[t]; }, thw, ths, T);
+        heading_chain<true>(state[2], wdt, thw, ths, T);
       else
-        heading_chain<false>(state[2], [wdt](int t) { return wdt[t]; }, thw, ths, T);
+        heading_chain<false>(state[2], wdt, thw, ths, T);
     }
     __syncthreads();
     for (int t = tid; t < T; t += nt) {
@@ -378,14 +387,15 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
   // Optimal-trajectory rollout by one block (mppi.py:508-524): the same operations on the same values
   // as T calls of step(), rescheduled. Serial parts are only the three cheap recurrences (speed:
   // add+clamp; heading: two angle wraps; position: add+clamp); tan / sin / cos of all T stages run in
-  // parallel in between. scratch: 11 * (T + 1) floats.
+  // parallel in between. scratch: 11 * (T + 9) floats.
   __device__ static __noinline__ void rollout_block(const Ctx& c, const float* state, const float* opt, int T, float* out,
                                        float* scratch) {
     const float* p = c.p->v;
-    const int tid = threadIdx.x, nt = blockDim.x, S = T + 1;
+    const int tid = threadIdx.x, nt = blockDim.x, S = T + 9;  // room for whole groups of 8 (see serial_chain)
     float *adt = scratch, *tn = adt + S, *vs = tn + S, *cdt = vs + S, *ths = cdt + S, *thw = ths + S, *dx = thw + S,
           *dy = dx + S, *xs = dy + S, *ys = xs + S;
     const bool bounded = (c.p->flags & kFlagBounded) && state_in_bounds(c, state);
+    for (int t = T + tid; t < S; t += nt) adt[t] = cdt[t] = dx[t] = dy[t] = 0.0f;
     for (int t = tid; t < T; t += nt) {
       adt[t] = clampf(opt[2 * t], p[0], p[1]) * p[10];
       const float st = clampf(opt[2 * t + 1], p[2], p[3]);
@@ -402,9 +412,9 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
     __syncthreads();
     if (tid == 0) {  // heading: S[t+1].theta = wrap(wrap(S[t].theta) + c_t); thw keeps the inner wrap
       if (bounded)
-        heading_chain<true>(state[2], [cdt](int t) { return cdt[t]; }, thw, ths, T);
+        heading_chain<true>(state[2], cdt, thw, ths, T);
       else
-        heading_chain<false>(state[2], [cdt](int t) { return cdt[t]; }, thw, ths, T);
+        heading_chain<false>(state[2], cdt, thw, ths, T);
     }
     __syncthreads();
     for (int t = tid; t < T; t += nt) {
