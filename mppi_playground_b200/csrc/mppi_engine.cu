@@ -13,6 +13,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/mppi_b200.h"
@@ -156,6 +157,7 @@ struct MppiHandle {
   bool timing = false;
   unsigned long long* d_trace = nullptr;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+  std::unordered_map<const void*, unsigned> smem_opt_in;
 };
 
 namespace {
@@ -204,7 +206,13 @@ int launch_solve(MppiHandle* h, const SolveParams& p, int mode, bool inject, cud
   else
     PICK(kReduce);
 #undef PICK
-  CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+  {  // opt in to the large dynamic shared memory once per kernel instantiation (and again if it grows)
+    unsigned& have = h->smem_opt_in[(const void*)k];
+    if (have < h->smem) {
+      CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+      have = h->smem;
+    }
+  }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->timing && mode != kReduce) {
     CUDA_TRY(cudaEventCreate(&e0));
@@ -262,7 +270,19 @@ int launch_search(MppiHandle* h, const float* costs, long long n, cudaStream_t s
   q.lbps_delta = h->cfg.lbps_delta;
   q.essps_target = h->cfg.essps_target_ess;
   q.sc = h->d_sc;
-  lambda_search_kernel<<<1, 1024, 0, st>>>(q);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(kSearchCluster);
+  cfg.blockDim = dim3(1024);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kSearchCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, lambda_search_kernel, q));
   CUDA_TRY(cudaGetLastError());
   h->last_launches++;
   return MPPI_OK;

@@ -17,6 +17,7 @@
 // LBPS / ESSPS need every cost before lambda exists, so they run the same
 // kernel split in two (kCosts, kReduce) around lambda_search_kernel.
 #pragma once
+#include <cooperative_groups.h>
 #include <math.h>
 
 #include "mppi_models.cuh"
@@ -887,23 +888,57 @@ struct SearchStats {
   double S, S2, Sc;
 };
 
-__device__ inline SearchStats softmax_stats(const float* __restrict__ costs, long long n, double lambda, float cmin,
+constexpr int kSearchCluster = 8;  // CTAs of the lambda search (one thread-block cluster, portable size)
+
+// Cluster-wide sum of `v[N]`: block reduction, then every CTA stores its partial into every CTA's
+// exchange buffer through distributed shared memory and all add the kSearchCluster partials in rank
+// order (identical result everywhere). `phase` alternates the buffer half so that one cluster barrier
+// per call is enough.
+template <int N>
+__device__ __forceinline__ void cluster_sum(double (&v)[N], double* xchg /*[2][kSearchCluster][4]*/, int& phase,
                                             void* red) {
-  // w = softmax(-c / lambda) in fp32 like the reference; sums kept in fp64
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank(), nblk = cluster.num_blocks();
+  block_reduce_n(v, OpAddD(), 0.0, red);
+  if (threadIdx.x < nblk) {
+    double* remote = cluster.map_shared_rank(xchg, threadIdx.x) + ((size_t)phase * kSearchCluster + rank) * 4;
+#pragma unroll
+    for (int i = 0; i < N; ++i) remote[i] = v[i];
+  }
+  cluster.sync();
+  const double* mine = xchg + (size_t)phase * kSearchCluster * 4;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double a = 0.0;
+    for (unsigned r = 0; r < nblk; ++r) a += mine[r * 4 + i];
+    v[i] = a;
+  }
+  phase ^= 1;
+}
+
+__device__ inline SearchStats softmax_stats(const float* __restrict__ costs, long long n, double lambda, float cmin,
+                                            void* red, double* xchg, int& phase) {
+  // w = softmax(-c / lambda) in fp32 like the reference; sums kept in fp64. Each CTA of the cluster
+  // covers an interleaved slice of the costs.
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const long long stride = (long long)cluster.num_blocks() * blockDim.x;
   const float lam = (float)lambda;
   const float xmax = (-cmin) / lam;
-  double S = 0.0, S2 = 0.0, Sc = 0.0;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+  double v[3] = {0.0, 0.0, 0.0};
+  for (long long i = (long long)cluster.block_rank() * blockDim.x + threadIdx.x; i < n; i += stride) {
     float c = costs[i];
     float e = expf((-c) / lam - xmax);
-    S += (double)e;
-    S2 += (double)e * (double)e;
-    Sc += (double)e * (double)c;
+    v[0] += (double)e;
+    v[1] += (double)e * (double)e;
+    v[2] += (double)e * (double)c;
   }
+  cluster_sum(v, xchg, phase, red);
   SearchStats r;
-  r.S = block_reduce(S, OpAddD(), 0.0, red);
-  r.S2 = block_reduce(S2, OpAddD(), 0.0, red);
-  r.Sc = block_reduce(Sc, OpAddD(), 0.0, red);
+  r.S = v[0];
+  r.S2 = v[1];
+  r.Sc = v[2];
   return r;
 }
 
@@ -918,15 +953,38 @@ struct SearchParams {
 __device__ inline double dsign(double x) { return (x > 0.0) - (x < 0.0); }
 
 __global__ void __launch_bounds__(1024, 1) lambda_search_kernel(const SearchParams q) {
-  __shared__ double red[64];
+  // launched as ONE thread-block cluster of kSearchCluster CTAs (cudaLaunchAttributeClusterDimension)
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ double red[128];
+  __shared__ double xchg[2 * kSearchCluster * 4];
+  int phase = 0;
   float cmin = INFINITY, cmax = -INFINITY;
-  for (long long i = threadIdx.x; i < q.n; i += blockDim.x) {
-    float c = q.costs[i];
-    cmin = fminf(cmin, c);
-    cmax = fmaxf(cmax, c);
+  cluster.sync();  // every CTA of the cluster is resident before anyone touches remote shared memory
+  {
+    const long long stride = (long long)cluster.num_blocks() * blockDim.x;
+    for (long long i = (long long)cluster.block_rank() * blockDim.x + threadIdx.x; i < q.n; i += stride) {
+      float c = q.costs[i];
+      cmin = fminf(cmin, c);
+      cmax = fmaxf(cmax, c);
+    }
+    float mm[2] = {-cmin, cmax};
+    block_reduce_n(mm, OpMax(), -INFINITY, red);
+    if (threadIdx.x < cluster.num_blocks()) {
+      double* remote = cluster.map_shared_rank(xchg, threadIdx.x) + ((size_t)phase * kSearchCluster + cluster.block_rank()) * 4;
+      remote[0] = (double)mm[0];
+      remote[1] = (double)mm[1];
+    }
+    cluster.sync();
+    float a = -INFINITY, b = -INFINITY;
+    for (unsigned r = 0; r < cluster.num_blocks(); ++r) {
+      a = fmaxf(a, (float)xchg[(phase * kSearchCluster + r) * 4 + 0]);
+      b = fmaxf(b, (float)xchg[(phase * kSearchCluster + r) * 4 + 1]);
+    }
+    cmin = -a;
+    cmax = b;
+    phase ^= 1;
   }
-  cmin = block_reduce(cmin, OpMin(), INFINITY, red);
-  cmax = block_reduce(cmax, OpMax(), -INFINITY, red);
   int evals = 0;
   double result;
   if (q.mode == kLamLBPS) {
@@ -934,7 +992,7 @@ __global__ void __launch_bounds__(1024, 1) lambda_search_kernel(const SearchPara
     const double range = (double)(float)(cmax - cmin);
     const double pen = sqrt((1.0 - q.lbps_delta) / q.lbps_delta);
     auto J = [&](double lam) {
-      SearchStats s = softmax_stats(q.costs, q.n, lam, cmin, red);
+      SearchStats s = softmax_stats(q.costs, q.n, lam, cmin, red, xchg, phase);
       ++evals;
       double ess = 1.0 / (double)(float)(s.S2 / (s.S * s.S));
       double expected = (double)(float)(s.Sc / s.S);
@@ -1014,7 +1072,7 @@ __global__ void __launch_bounds__(1024, 1) lambda_search_kernel(const SearchPara
   } else {
     // ESS(lambda) = 1 / sum w^2  (mppi.py:526-532); root of ESS - target (mppi.py:351-370)
     auto F = [&](double lam) {
-      SearchStats s = softmax_stats(q.costs, q.n, lam, cmin, red);
+      SearchStats s = softmax_stats(q.costs, q.n, lam, cmin, red, xchg, phase);
       ++evals;
       return 1.0 / (double)(float)(s.S2 / (s.S * s.S)) - q.essps_target;
     };
@@ -1089,10 +1147,11 @@ __global__ void __launch_bounds__(1024, 1) lambda_search_kernel(const SearchPara
       }
     }
   }
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && cluster.block_rank() == 0) {
     q.sc->lambda = result;
     q.sc->search_evals = evals;
   }
+  cluster.sync();  // no CTA may exit while a peer can still address its shared memory
 }
 
 // ---------------------------------------------------------------------------

@@ -262,7 +262,7 @@ class MPPI(nn.Module):
             if tuple(noise.shape) == (self._num_samples, T, du) and self._world > 1:
                 noise = noise[lo:lo + self._local_samples].contiguous()
             assert tuple(noise.shape) == (self._local_samples, T, du)
-        self._noise_keepalive = (noise, st, ref)
+        self.__dict__["_noise_keepalive"] = (noise, st, ref)  # plain dict write: nn.Module.__setattr__ is slow
         action = torch.empty(T, du, device=self._device, dtype=torch.float32)
         states = torch.empty(T + 1, ds, device=self._device, dtype=torch.float32)
         s = _stream_ptr(self._device)
