@@ -44,6 +44,39 @@ H2D_BYTES = 4 * 4 + 16 * (HORIZON + 1)
 D2H_BYTES = 4 * HORIZON * 2 + 4 * (HORIZON + 1) * 4
 
 
+def load_racing_fixture():
+    """Racing workload data (occupancy grids, centre line, start state, cost weights) from
+    tests/golden/env_racing.npz - recorded from the reference's RacingEnv by oracle/gen_golden.py.
+    Plain numpy here: the measured GPU arm does not import anything from oracle/."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "env_racing.npz"))
+    shape = z["shape"]
+
+    def unpack(bits):
+        return np.unpackbits(bits, axis=1)[:, : int(shape[1])].astype(np.float32)
+
+    return dict(obstacle=unpack(z["obstacle_bits"]), lane=unpack(z["lane_bits"]), cell=[float(c) for c in z["cell"]],
+                origin=[[int(v) for v in o] for o in z["origin"]], lim=[float(v) for v in z["lim"]],
+                center_path=torch.from_numpy(z["center_path"].copy()),
+                start_state=torch.from_numpy(z["start_state"].copy()), u_min=z["u_min"].tolist(),
+                u_max=z["u_max"].tolist(), wheelbase=float(z["wheelbase"]), v_max=float(z["v_max"]),
+                Q=[float(q) for q in z["Q"]])
+
+
+def make_engine(env, device, **extra):
+    """(model descriptor, MPPI) for the bench workload through the public Python API."""
+    import mppi_playground_b200 as eng
+
+    q = env["Q"]
+    model = eng.RacingModel(env["obstacle"], env["lane"], cell_size=env["cell"], origin=env["origin"],
+                            u_min=env["u_min"], u_max=env["u_max"], wheelbase=env["wheelbase"], v_max=env["v_max"],
+                            lim=env["lim"], Qc=q[0], Ql=q[1], Qv=q[2], Qo=q[3], Qin=q[4], Qdin=q[5])
+    kw = {k: v for k, v in CFG.items() if k not in ("model", "sigmas")}
+    solver = eng.MPPI(dim_state=4, dim_control=2, dynamics=model.dynamics, cost_func=model.cost_func,
+                      u_min=model.u_min.clone(), u_max=model.u_max.clone(), sigmas=torch.tensor(CFG["sigmas"]),
+                      device=device, **kw, **extra)
+    return model, solver
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -105,16 +138,14 @@ def closed_loop_inputs(n_steps: int, device):
     """Run the engine's own closed loop once (untimed) and keep every step's
     state [4] and reference path [T+1,4] on the device."""
     import mppi_playground_b200 as eng
-    from engine_util import build_engine
-    from oracle import fixtures as fx  # env fixture loader only (maps, centre line)
 
-    env = fx.load_env_racing()
-    model, solver = build_engine(CFG, device=device)
+    env = load_racing_fixture()
+    model, solver = make_engine(env, device)
     states = torch.empty(n_steps, 4)
     refs = torch.empty(n_steps, HORIZON + 1, 4)
-    state, cind = env.start_state.clone(), 0
+    state, cind = env["start_state"].clone(), 0
     for s in range(n_steps):
-        ref, cind = eng.racing_reference_path(state, env.center_path, cind, HORIZON, v_max=env.v_max)
+        ref, cind = eng.racing_reference_path(state, env["center_path"], cind, HORIZON, v_max=env["v_max"])
         model.reference_path_tensor = ref
         states[s], refs[s] = state, ref
         _, seq = solver.forward(state)
@@ -126,8 +157,6 @@ def closed_loop_inputs(n_steps: int, device):
 def run_b200(args, rank, local_rank, world):
     import torch.distributed as dist
 
-    import mppi_playground_b200 as eng
-    from engine_util import build_engine
     from mppi_playground_b200 import _capi
 
     device = torch.device("cuda", local_rank)
@@ -147,7 +176,8 @@ def run_b200(args, rank, local_rank, world):
         dist.broadcast(refs_d, 0)
         states_h, refs_h = states_d.cpu(), refs_d.cpu()
 
-    model, solver = build_engine(CFG, device=device, process_group=pg) if world > 1 else build_engine(CFG, device=device)
+    env = load_racing_fixture()
+    model, solver = make_engine(env, device, process_group=pg) if world > 1 else make_engine(env, device)
     model.reference_path_tensor = refs_d[0]
     lib, h = solver._lib, solver._h
     solver._bind_maps(required=True)
