@@ -821,8 +821,8 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ S
   __syncthreads();
   if (!misc[0]) return;
   __threadfence();
-  // reuse the per-warp accumulators as scratch: N[E] doubles, opt[E], y[(2T-1)*du], scales[256]
-  // (n_warps * E_pad * 4 bytes are available; the host sizes it for this, see engine)
+  // the group-accumulator region doubles as the finish scratch (make_layout sizes it for both uses):
+  // N[E_pad] doubles | opt[E_pad] | y[2 E_pad] | rescale factors[256] | Combined | segment sums | tail rollout
   double* Nbuf = reinterpret_cast<double*>(smem + L.warpacc_off);
   float* opt = reinterpret_cast<float*>(Nbuf + p.E_pad);
   float* ybuf = opt + p.E_pad;

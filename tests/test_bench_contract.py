@@ -1,0 +1,36 @@
+"""bench.py contract on the CPU: the reference arm (`--impl reference`) runs without a GPU and prints
+one JSON line with the keys the driver reads; the GPU arm's static pieces are importable."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_the_contract_line():
+    out = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "3"],
+                         cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "solves/s" and line["higher_is_better"] is True
+    assert line["metric"].startswith("MPPI solves/sec") and line["n_gpus"] == 1 and line["gpu_launches"] == 0
+    assert line["value"] > 0 and abs(line["ms_per_step"] - 1e3 / line["value"]) < 1e-6 * line["ms_per_step"]
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and "65536/65536" in cb["sample"] and cb["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "solves/s", "h2d_bytes_per_step": 0,
+                           "d2h_bytes_per_step": 0}
+    assert "K=65536" in line["config"]["workload"] and "T=80" in line["config"]["workload"]
+
+
+def test_gpu_arm_constants_and_fixture():
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert bench.FLOPS_PER_SOLVE == 65536 * 80 * 97 + 65536 * 61
+    assert bench.BYTES_PER_SOLVE == 4 * 65536 + 4 * 80 * 2 * 2 + 16 * 81 + 4 * 81 * 4 + 2 * 800 * 25 * 4
+    assert (bench.H2D_BYTES, bench.D2H_BYTES) == (1312, 1936)
+    env = bench.load_racing_fixture()
+    assert env["obstacle"].shape == (800, 800) and int(env["obstacle"].sum()) == 18602
+    assert int(env["lane"].sum()) == 445529 and tuple(env["center_path"].shape) == (3678, 3)
+    assert bench.ncu_traffic() is None or bench.ncu_traffic() > 0
