@@ -81,13 +81,18 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
-def ncu_traffic():
-    """DRAM bytes per launch of the solve kernel from the committed ncu capture (null if absent)."""
+def ncu_capture():
+    """Numbers of the committed ncu --set full capture of the solve kernel (profiles/), or {}."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            return json.load(f)["dram_bytes_per_launch"]
+            return json.load(f)
     except Exception:
-        return None
+        return {}
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the solve kernel from the committed ncu capture (null if absent)."""
+    return ncu_capture().get("dram_bytes_per_launch")
 
 
 def measured_peaks():
@@ -325,6 +330,7 @@ def run_b200(args, rank, local_rank, world):
                          "frac": (ach / fp32_peak) if ach else None, "traffic": ncu_traffic() if world == 1 else None,
                          "kernel": "solve_kernel<Racing,false,kFused>", "kernel_ms": kern_ms, "kernel_launches": kern_n,
                          "algorithmic_flops_per_launch": FLOPS_PER_SOLVE / share,
+                         "ncu_pipes": ncu_capture().get("pipes") if world == 1 else None,
                          "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz ({peak_src} MEASURED_PEAKS.json has no "
                                         "fp32 figure; the path is fp32-issue/latency bound, not HBM or tensor)",
                          "hbm": {"achieved": hbm_ach, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
