@@ -564,7 +564,8 @@ def test_full_size_solves_by_size_independent_properties(cfg):
     assert rel.max() <= TOL["cost_rel"], rel.max()
     # (2) weighted mean in fp64 from the engine's own costs / noise (first solve: nominal is zero)
     u = torch.clamp(noise.double(), solver._u_min.double(), solver._u_max.double())
-    w = torch.softmax(-costs.double() / lam, dim=0)
+    x32 = (-costs) / torch.tensor(lam, dtype=torch.float32, device=costs.device)  # fp32 like mppi.py:376
+    w = torch.softmax(x32.double(), dim=0)
     want = (w.view(K, 1, 1) * u).sum(dim=0)
     np.testing.assert_allclose(action.double().cpu().numpy(), want.cpu().numpy(), rtol=0, atol=2e-6)
     assert abs(float(solver._weights.double().sum()) - 1.0) < 2e-5
