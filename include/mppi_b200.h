@@ -51,7 +51,9 @@ typedef enum MppiModel {
   MPPI_MODEL_CARTPOLE = 1,     /* example/cartpole.py:17-81 */
   MPPI_MODEL_MOUNTAINCAR = 2,  /* example/mountaincar.py:17-55 */
   MPPI_MODEL_NAVIGATION2D = 3, /* src/envs/navigation_2d.py:218-279 */
-  MPPI_MODEL_RACING = 4        /* src/envs/racing_env.py:327-372 + example/racing.py:110-159 */
+  MPPI_MODEL_RACING = 4,       /* src/envs/racing_env.py:327-372 + example/racing.py:110-159 */
+  MPPI_MODEL_CARTPOLE_CONTINUOUS = 5, /* example/mujoco_cartpole.py:20-80 */
+  MPPI_MODEL_GOAL_IN_DANGER_ZONE = 6  /* src/envs/goal_in_danger_zone.py:113-156 */
 } MppiModel;
 
 /* lambda_ argument of the constructor (src/pi_mpc/mppi.py:183-210). */
@@ -66,9 +68,12 @@ typedef enum MppiLambdaMode {
  *   PENDULUM / CARTPOLE / MOUNTAINCAR: none (the reference hard-codes them).
  *   NAVIGATION2D (12): v_min v_max w_min w_max  goal_x goal_y  x_lo x_hi y_lo y_hi  dt  obstacle_weight
  *   RACING (17):       a_min a_max s_min s_max  wheelbase v_max  x_lo x_hi y_lo y_hi  dt  Qc Ql Qv Qo Qin Qdin
+ *   CARTPOLE_CONTINUOUS: none.
+ *   GOAL_IN_DANGER_ZONE (11): v_min v_max w_min w_max  dt  goal_x goal_y  centre_x centre_y  radius  collision_cost
  */
 #define MPPI_NAV2D_NUM_PARAMS 12
 #define MPPI_RACING_NUM_PARAMS 17
+#define MPPI_GOAL_ZONE_NUM_PARAMS 11
 
 /* Mirrors the keyword arguments of MPPI.__init__ (src/pi_mpc/mppi.py:24-47). */
 typedef struct MppiConfig {

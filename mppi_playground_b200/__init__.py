@@ -13,8 +13,8 @@ model resolution). Importing it does not load CUDA; constructing ``MPPI`` does
 and raises if libmppi_b200.so or a CUDA device is missing - there is no CPU path.
 """
 from .mppi import MPPI, shard_bounds  # noqa: F401
-from .models import (CartpoleModel, MountainCarModel, Navigation2DModel, PendulumModel,  # noqa: F401
+from .models import (CartpoleContinuousModel, CartpoleModel, GoalInDangerZoneModel, MountainCarModel, Navigation2DModel, PendulumModel,  # noqa: F401
                      RacingModel, RacingReferencePath, racing_reference_path)
 
-__all__ = ["MPPI", "PendulumModel", "CartpoleModel", "MountainCarModel", "Navigation2DModel", "RacingModel",
+__all__ = ["MPPI", "PendulumModel", "CartpoleModel", "MountainCarModel", "CartpoleContinuousModel", "GoalInDangerZoneModel", "Navigation2DModel", "RacingModel",
            "racing_reference_path", "RacingReferencePath", "shard_bounds"]

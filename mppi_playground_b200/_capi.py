@@ -14,9 +14,10 @@ LIB_PATH = os.path.join(_HERE, "libmppi_b200.so")
 ABI_VERSION = 1
 MAX_DU, MAX_SG, MAX_PARAMS = 4, 33, 32
 
-MODEL_PENDULUM, MODEL_CARTPOLE, MODEL_MOUNTAINCAR, MODEL_NAVIGATION2D, MODEL_RACING = range(5)
+(MODEL_PENDULUM, MODEL_CARTPOLE, MODEL_MOUNTAINCAR, MODEL_NAVIGATION2D, MODEL_RACING, MODEL_CARTPOLE_CONTINUOUS,
+ MODEL_GOAL_IN_DANGER_ZONE) = range(7)
 LAMBDA_FIXED, LAMBDA_MPO, LAMBDA_LBPS, LAMBDA_ESSPS = range(4)
-NAV2D_NUM_PARAMS, RACING_NUM_PARAMS = 12, 17
+NAV2D_NUM_PARAMS, RACING_NUM_PARAMS, GOAL_ZONE_NUM_PARAMS = 12, 17, 11
 
 
 class MppiConfig(C.Structure):

@@ -56,6 +56,9 @@ ModelInfo model_info(int model) {
     case MPPI_MODEL_MOUNTAINCAR: return {MountainCar::DS, MountainCar::DU, 0, 0, false, 0};
     case MPPI_MODEL_NAVIGATION2D: return {Navigation2D::DS, Navigation2D::DU, 1, MPPI_NAV2D_NUM_PARAMS, false, tail_per_step<Navigation2D>()};
     case MPPI_MODEL_RACING: return {Racing::DS, Racing::DU, 2, MPPI_RACING_NUM_PARAMS, true, tail_per_step<Racing>()};
+    case MPPI_MODEL_CARTPOLE_CONTINUOUS: return {CartpoleContinuous::DS, CartpoleContinuous::DU, 0, 0, false, 0};
+    case MPPI_MODEL_GOAL_IN_DANGER_ZONE:
+      return {GoalInDangerZone::DS, GoalInDangerZone::DU, 0, MPPI_GOAL_ZONE_NUM_PARAMS, false, 0};
     default: return {0, 0, 0, 0, false, 0};
   }
 }
@@ -236,6 +239,8 @@ int dispatch_solve(MppiHandle* h, const SolveParams& p, int mode, bool inject, c
     case MPPI_MODEL_MOUNTAINCAR: return launch_solve<MountainCar>(h, p, mode, inject, st);
     case MPPI_MODEL_NAVIGATION2D: return launch_solve<Navigation2D>(h, p, mode, inject, st);
     case MPPI_MODEL_RACING: return launch_solve<Racing>(h, p, mode, inject, st);
+    case MPPI_MODEL_CARTPOLE_CONTINUOUS: return launch_solve<CartpoleContinuous>(h, p, mode, inject, st);
+    case MPPI_MODEL_GOAL_IN_DANGER_ZONE: return launch_solve<GoalInDangerZone>(h, p, mode, inject, st);
   }
   return fail(MPPI_ERR_INVALID, "unknown model %d", h->cfg.model);
 }
@@ -256,6 +261,8 @@ int dispatch_finish(MppiHandle* h, const SolveParams& p, const float* parts, int
     case MPPI_MODEL_MOUNTAINCAR: return launch_finish<MountainCar>(h, p, parts, n, st);
     case MPPI_MODEL_NAVIGATION2D: return launch_finish<Navigation2D>(h, p, parts, n, st);
     case MPPI_MODEL_RACING: return launch_finish<Racing>(h, p, parts, n, st);
+    case MPPI_MODEL_CARTPOLE_CONTINUOUS: return launch_finish<CartpoleContinuous>(h, p, parts, n, st);
+    case MPPI_MODEL_GOAL_IN_DANGER_ZONE: return launch_finish<GoalInDangerZone>(h, p, parts, n, st);
   }
   return fail(MPPI_ERR_INVALID, "unknown model %d", h->cfg.model);
 }
@@ -923,6 +930,8 @@ int mppi_top_samples(MppiHandle* h, int32_t n, float* d_traj, float* d_w, void* 
     case MPPI_MODEL_MOUNTAINCAR: return launch_reroll<MountainCar>(h, p, n, d_traj, d_w, st);
     case MPPI_MODEL_NAVIGATION2D: return launch_reroll<Navigation2D>(h, p, n, d_traj, d_w, st);
     case MPPI_MODEL_RACING: return launch_reroll<Racing>(h, p, n, d_traj, d_w, st);
+    case MPPI_MODEL_CARTPOLE_CONTINUOUS: return launch_reroll<CartpoleContinuous>(h, p, n, d_traj, d_w, st);
+    case MPPI_MODEL_GOAL_IN_DANGER_ZONE: return launch_reroll<GoalInDangerZone>(h, p, n, d_traj, d_w, st);
   }
   return fail(MPPI_ERR_INVALID, "unknown model");
 }
@@ -940,6 +949,8 @@ int mppi_rollout_actions(MppiHandle* h, const float* d_state, const float* d_act
     case MPPI_MODEL_MOUNTAINCAR: return launch_rollout_actions<MountainCar>(h, p, d_actions, n, d_traj, st);
     case MPPI_MODEL_NAVIGATION2D: return launch_rollout_actions<Navigation2D>(h, p, d_actions, n, d_traj, st);
     case MPPI_MODEL_RACING: return launch_rollout_actions<Racing>(h, p, d_actions, n, d_traj, st);
+    case MPPI_MODEL_CARTPOLE_CONTINUOUS: return launch_rollout_actions<CartpoleContinuous>(h, p, d_actions, n, d_traj, st);
+    case MPPI_MODEL_GOAL_IN_DANGER_ZONE: return launch_rollout_actions<GoalInDangerZone>(h, p, d_actions, n, d_traj, st);
   }
   return fail(MPPI_ERR_INVALID, "unknown model");
 }

@@ -198,6 +198,12 @@ __device__ __forceinline__ float perturbed_entry(const SolveParams& p, const flo
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void stamp(const SolveParams& p, int slot);
 
+// models whose Ctx carries the parameter block pointer `p`
+template <class M>
+__host__ __device__ constexpr bool uses_params() {
+  return M::kUsesParams;
+}
+
 // state / reference path of this solve: device buffers, or the copies inside the parameter block
 __device__ __forceinline__ const float* state_of(const SolveParams& p) {
   return p.inline_inputs ? p.state_inline : p.state;
@@ -400,7 +406,7 @@ __device__ __noinline__ void finish_solve(const SolveParams& p, const Combined& 
   // the rollout of the optimal sequence only needs the model parameters (dynamics never read the maps
   // or the reference path); a local context keeps the caller's register-resident one from escaping
   typename M::Ctx ctx{};
-  if constexpr (M::kMaps >= 1) ctx.p = &p.mp;
+  if constexpr (uses_params<M>()) ctx.p = &p.mp;
   constexpr int DS = M::DS, DU = M::DU;
   const int tid = threadIdx.x, nt = blockDim.x, T = p.T, E = p.E;
   const int H = (T - 1) * DU;
@@ -679,8 +685,8 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ S
       ctx.obstacle = mv[0];
       ctx.lane = mv[1];
     }
-    ctx.p = &p.mp;
   }
+  if constexpr (uses_params<M>()) ctx.p = &p.mp;
   if constexpr (M::kRefPath) {
     // per-stage reference row: (x, y, sin yaw, cos yaw), v_target (racing.py:127-143)
     float4* ref4 = reinterpret_cast<float4*>(smem + L.ref4_off);
@@ -1269,7 +1275,7 @@ __global__ void reroll_kernel(SolveParams p, const int* __restrict__ order, int 
   const uint32_t k_lo = (uint32_t)kg, k_hi = (uint32_t)((unsigned long long)kg >> 32);
   const bool zero_mean = kg >= p.explore_threshold;
   typename M::Ctx ctx{};
-  if constexpr (M::kMaps >= 1) ctx.p = &p.mp;
+  if constexpr (uses_params<M>()) ctx.p = &p.mp;
   float s[DS], seen[DS], u[DU];
   for (int d = 0; d < DS; ++d) s[d] = p.state[d];
   float* out = traj + (size_t)i * (p.T + 1) * DS;
@@ -1303,7 +1309,7 @@ __global__ void rollout_actions_kernel(SolveParams p, const float* __restrict__ 
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   typename M::Ctx ctx{};
-  if constexpr (M::kMaps >= 1) ctx.p = &p.mp;
+  if constexpr (uses_params<M>()) ctx.p = &p.mp;
   float s[DS], seen[DS], u[DU];
   for (int d = 0; d < DS; ++d) s[d] = p.state[d];
   float* out = traj + (size_t)i * (p.T + 1) * DS;

@@ -135,7 +135,7 @@ constexpr int kFlagBounded = 4;
 // ---------------------------------------------------------------------------
 struct Pendulum {  // example/pendulum.py:17-47
   static constexpr int DS = 2, DU = 1, kMaps = 0;
-  static constexpr bool kRefPath = false, kParallelTail = false, kHasBounded = false;
+  static constexpr bool kRefPath = false, kParallelTail = false, kHasBounded = false, kUsesParams = false;
   struct Ctx {};
   __device__ static __forceinline__ void step(const Ctx&, float (&s)[DS], const float (&u)[DU], float (&seen)[DS]) {
     seen[0] = s[0];
@@ -157,7 +157,7 @@ struct Pendulum {  // example/pendulum.py:17-47
 // ---------------------------------------------------------------------------
 struct Cartpole {  // example/cartpole.py:17-81
   static constexpr int DS = 4, DU = 1, kMaps = 0;
-  static constexpr bool kRefPath = false, kParallelTail = false, kHasBounded = false;
+  static constexpr bool kRefPath = false, kParallelTail = false, kHasBounded = false, kUsesParams = false;
   struct Ctx {};
   __device__ static __forceinline__ void step(const Ctx&, float (&s)[DS], const float (&u)[DU], float (&seen)[DS]) {
 #pragma unroll
@@ -188,7 +188,7 @@ struct Cartpole {  // example/cartpole.py:17-81
 // ---------------------------------------------------------------------------
 struct MountainCar {  // example/mountaincar.py:17-55
   static constexpr int DS = 2, DU = 1, kMaps = 0;
-  static constexpr bool kRefPath = false, kParallelTail = false, kHasBounded = false;
+  static constexpr bool kRefPath = false, kParallelTail = false, kHasBounded = false, kUsesParams = false;
   struct Ctx {};
   __device__ static __forceinline__ void step(const Ctx&, float (&s)[DS], const float (&u)[DU], float (&seen)[DS]) {
     float force = clampf(u[0], -1.0f, 1.0f);                          // :32
@@ -210,7 +210,7 @@ struct MountainCar {  // example/mountaincar.py:17-55
 // ---------------------------------------------------------------------------
 struct Navigation2D {  // src/envs/navigation_2d.py:218-279
   static constexpr int DS = 3, DU = 2, kMaps = 1;
-  static constexpr bool kRefPath = false, kParallelTail = true, kHasBounded = true;
+  static constexpr bool kRefPath = false, kParallelTail = true, kHasBounded = true, kUsesParams = true;
   struct Ctx {
     MapView map;
     const ModelParams* p;  // v_min v_max w_min w_max goal_x goal_y x_lo x_hi y_lo y_hi dt w_obst
@@ -304,7 +304,7 @@ struct Navigation2D {  // src/envs/navigation_2d.py:218-279
 // ---------------------------------------------------------------------------
 struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
   static constexpr int DS = 4, DU = 2, kMaps = 2;
-  static constexpr bool kRefPath = true, kParallelTail = true, kHasBounded = true;
+  static constexpr bool kRefPath = true, kParallelTail = true, kHasBounded = true, kUsesParams = true;
   struct Ctx {
     MapView obstacle, lane;
     const ModelParams* p;  // a_min a_max s_min s_max L v_max x_lo x_hi y_lo y_hi dt Qc Ql Qv Qo Qin Qdin
@@ -441,6 +441,72 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
     }
   }
   static constexpr int kTailScratchPerStep = 11;
+};
+
+// ---------------------------------------------------------------------------
+struct CartpoleContinuous {  // example/mujoco_cartpole.py:20-80 (pole mass 1.0, continuous force, |x| <= 1)
+  static constexpr int DS = 4, DU = 1, kMaps = 0;
+  static constexpr bool kRefPath = false, kParallelTail = false, kHasBounded = false, kUsesParams = false;
+  struct Ctx {};
+  __device__ static __forceinline__ void step(const Ctx&, float (&s)[DS], const float (&u)[DU], float (&seen)[DS]) {
+#pragma unroll
+    for (int i = 0; i < DS; ++i) seen[i] = s[i];
+    const float total_mass = 2.0f, pml = 0.5f, masspole = 1.0f;  // :35-40
+    const float force = u[0];                                    // :33 (no bang-bang here)
+    float st, ct;
+    sincosf(s[2], &st, &ct);
+    float temp = (force + pml * (s[3] * s[3]) * st) / total_mass;  // :46
+    float thacc = (9.8f * st - ct * temp) / (0.5f * (1.33333337306976318f - masspole * (ct * ct) / total_mass));  // :47-49
+    float xacc = temp - pml * thacc * ct / total_mass;  // :50
+    float nx = s[0] + 0.02f * s[1];                     // :52-55
+    float nxd = s[1] + 0.02f * xacc;
+    float nth = s[2] + 0.02f * s[3];
+    float nthd = s[3] + 0.02f * thacc;
+    s[0] = clampf(nx, -1.0f, 1.0f);                                  // :57-62
+    s[2] = clampf(nth, -0.20943951606750488f, 0.20943951606750488f);
+    s[1] = nxd;
+    s[3] = nthd;
+  }
+  __device__ static __forceinline__ float cost(const Ctx&, const float (&s)[DS], const float (&)[DU],
+                                               const float (&)[DU], int) {
+    float a = wrap_angle(s[2]);
+    return a * a + 0.1f * (s[3] * s[3]) + 0.1f * (s[0] * s[0]);  // :68-80
+  }
+};
+
+// ---------------------------------------------------------------------------
+struct GoalInDangerZone {  // src/envs/goal_in_danger_zone.py:113-156 (obs = x y theta, vec to goal, vec to centre)
+  static constexpr int DS = 7, DU = 2, kMaps = 0;
+  static constexpr bool kRefPath = false, kParallelTail = false, kHasBounded = false, kUsesParams = true;
+  struct Ctx {
+    const ModelParams* p;  // v_min v_max w_min w_max dt goal_x goal_y centre_x centre_y radius collision_cost
+  };
+  __device__ static __forceinline__ void step(const Ctx& c, float (&s)[DS], const float (&u)[DU], float (&seen)[DS]) {
+    const float* p = c.p->v;
+#pragma unroll
+    for (int i = 0; i < DS; ++i) seen[i] = s[i];
+    float v = clampf(u[0], p[0], p[1]);  // :118-119
+    float w = clampf(u[1], p[2], p[3]);
+    float th = wrap_angle(s[2] + w * p[4]);  // :124
+    float st, ct;
+    sincosf(th, &st, &ct);
+    float nx = s[0] + v * ct * p[4];  // :126-127
+    float ny = s[1] + v * st * p[4];
+    s[0] = nx;
+    s[1] = ny;
+    s[2] = th;
+    s[3] = p[5] - nx;  // :129-134
+    s[4] = p[6] - ny;
+    s[5] = p[7] - nx;
+    s[6] = p[8] - ny;
+  }
+  __device__ static __forceinline__ float cost(const Ctx& c, const float (&s)[DS], const float (&)[DU],
+                                               const float (&)[DU], int) {
+    const float* p = c.p->v;
+    float dist = sqrtf(s[3] * s[3] + s[4] * s[4]);                   // :145
+    float collided = (sqrtf(s[5] * s[5] + s[6] * s[6]) < p[9]) ? 1.0f : 0.0f;  // :153
+    return dist + collided * p[10];                                  // :154
+  }
 };
 
 }  // namespace mppi

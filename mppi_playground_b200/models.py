@@ -81,6 +81,31 @@ class MountainCarModel(_Descriptor):
     model_id, name, dim_state, dim_control = _capi.MODEL_MOUNTAINCAR, "mountaincar", 2, 1
 
 
+class CartpoleContinuousModel(_Descriptor):
+    """example/mujoco_cartpole.py:20-80 (pole mass 1.0, continuous force, |x| <= 1)."""
+
+    model_id, name, dim_state, dim_control = _capi.MODEL_CARTPOLE_CONTINUOUS, "cartpole_continuous", 4, 1
+
+
+class GoalInDangerZoneModel(_Descriptor):
+    """src/envs/goal_in_danger_zone.py:113-156: unicycle, 7-dim observation (x, y, theta, vector to the goal,
+    vector to the danger-zone centre); cost = distance to goal + 1000 inside the zone. ``goal`` may be
+    reassigned between solves (the env draws a new one at every reset)."""
+
+    model_id, name, dim_state, dim_control = _capi.MODEL_GOAL_IN_DANGER_ZONE, "goal_in_danger_zone", 7, 2
+
+    def __init__(self, goal, center=(0.0, 0.0), radius: float = 10.0, v_lim=(-1.0, 1.0), w_lim=(-1.0, 1.0),
+                 dt: float = 0.1, collision_cost: float = 1000.0):
+        self.goal, self.center, self.radius = list(goal), list(center), float(radius)
+        self.v_lim, self.w_lim, self.dt, self.collision_cost = tuple(v_lim), tuple(w_lim), dt, collision_cost
+        self.u_min = torch.tensor([v_lim[0], w_lim[0]], dtype=torch.float32)
+        self.u_max = torch.tensor([v_lim[1], w_lim[1]], dtype=torch.float32)
+
+    def params(self):
+        return [self.v_lim[0], self.v_lim[1], self.w_lim[0], self.w_lim[1], self.dt, float(self.goal[0]),
+                float(self.goal[1]), float(self.center[0]), float(self.center[1]), self.radius, self.collision_cost]
+
+
 class Navigation2DModel(_Descriptor):
     """src/envs/navigation_2d.py:218-279: unicycle, goal distance + occupancy cost."""
 
@@ -284,6 +309,19 @@ class _ReferenceNavigation2D(Binding):
         return (id(self.env._obstacle_map),)
 
 
+class _ReferenceGoalInDangerZone(Binding):
+    model_id, name, dim_state, dim_control = _capi.MODEL_GOAL_IN_DANGER_ZONE, "goal_in_danger_zone", 7, 2
+
+    def __init__(self, env):
+        self.env = env
+
+    def params(self):
+        e = self.env  # plain Python / numpy attributes; the goal changes at every env.reset()
+        return [float(e._v_min), float(e._v_max), float(e._omega_min), float(e._omega_max), float(e._dt),
+                float(e._goal[0]), float(e._goal[1]), float(e._danger_zone.center[0]),
+                float(e._danger_zone.center[1]), float(e._danger_zone.radius), 1000.0]  # goal_in_danger_zone.py:154
+
+
 # ---- behavioural fingerprints of the example closures -------------------------------------
 
 
@@ -317,6 +355,18 @@ def _cartpole_host(s, a):
     return nxt, _wrap(th) ** 2 + 0.1 * thd**2 + 0.1 * x**2
 
 
+def _cartpole_continuous_host(s, a):
+    x, xd, th, thd = s.unbind(1)
+    ct, st = torch.cos(th), torch.sin(th)
+    temp = (a[:, 0] + 0.5 * thd**2 * st) / 2.0
+    thacc = (9.8 * st - ct * temp) / (0.5 * (4.0 / 3.0 - ct**2 / 2.0))
+    xacc = temp - 0.5 * thacc * ct / 2.0
+    lim = 12 * 2 * math.pi / 360
+    nxt = torch.stack([(x + 0.02 * xd).clamp(-1.0, 1.0), xd + 0.02 * xacc, (th + 0.02 * thd).clamp(-lim, lim),
+                       thd + 0.02 * thacc], 1)
+    return nxt, _wrap(th) ** 2 + 0.1 * thd**2 + 0.1 * x**2
+
+
 def _mountaincar_host(s, a):
     p, v = s[:, 0], s[:, 1]
     v2 = (v + a[:, 0].clamp(-1, 1) * 0.0015 - 0.0025 * torch.cos(3 * p)).clamp(-0.07, 0.07)
@@ -326,6 +376,7 @@ def _mountaincar_host(s, a):
 _CLOSURE_TWINS = [
     (PendulumModel, _pendulum_host),
     (CartpoleModel, _cartpole_host),
+    (CartpoleContinuousModel, _cartpole_continuous_host),
     (MountainCarModel, _mountaincar_host),
 ]
 
@@ -364,6 +415,10 @@ def resolve(dynamics: Callable, cost_func: Callable, dim_state: int, dim_control
         if c_self is None or not all(hasattr(c_self, a) for a in need):
             raise NotImplementedError("RacingEnv.dynamics is only supported with racing_controller.cost_function")
         binding = _ReferenceRacing(d_self, c_self)
+    elif d_self is not None and type(d_self).__name__ == "GoalInDangerZoneEnv":
+        if c_self is not d_self or getattr(dynamics, "__name__", "") != "parallel_step":
+            raise NotImplementedError("GoalInDangerZoneEnv is supported through parallel_step / parallel_cost")
+        binding = _ReferenceGoalInDangerZone(d_self)
     elif d_self is not None and type(d_self).__name__ == "Navigation2DEnv":
         if c_self is not d_self:
             raise NotImplementedError("Navigation2DEnv.dynamics is only supported with Navigation2DEnv.cost_function")
@@ -373,7 +428,7 @@ def resolve(dynamics: Callable, cost_func: Callable, dim_state: int, dim_control
     if binding is None:
         raise NotImplementedError(
             "dynamics/cost_func do not match a built-in device model (pendulum, cartpole, mountaincar, "
-            "navigation2d, racing). mppi_playground_b200 runs the rollout in a CUDA kernel and has no CPU "
+            "mujoco-cartpole, navigation2d, racing, goal-in-danger-zone). mppi_playground_b200 runs the rollout in a CUDA kernel and has no CPU "
             "fallback for arbitrary Python callables.")
     if (binding.dim_state, binding.dim_control) != (dim_state, dim_control):
         raise ValueError(f"model {binding.name} has dim_state={binding.dim_state}, dim_control={binding.dim_control};"

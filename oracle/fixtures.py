@@ -66,6 +66,10 @@ def oracle_model(name: str):
         return mo.CartpoleModel()
     if name == "mountaincar":
         return mo.MountainCarModel()
+    if name == "mujoco_cartpole":
+        return mo.CartpoleContinuousModel()
+    if name == "goal_in_danger_zone":
+        return mo.GoalInDangerZoneModel()
     if name == "navigation2d":
         return oracle_navigation2d_model()
     if name == "racing":
@@ -73,7 +77,7 @@ def oracle_model(name: str):
     raise KeyError(name)
 
 
-GOLDEN_CASES = ["pendulum_c1", "pendulum_essps", "cartpole", "cartpole_mpo", "mountaincar", "navigation2d_lbps",
+GOLDEN_CASES = ["mujoco_cartpole", "goal_in_danger_zone", "pendulum_c1", "pendulum_essps", "cartpole", "cartpole_mpo", "mountaincar", "navigation2d_lbps",
                 "navigation2d_essps", "navigation2d_mpo_expl", "racing_sg", "racing_example"]
 
 
@@ -99,6 +103,8 @@ def bounds_for(case_cfg: dict, model) -> tuple:
 
 def build_oracle(case: SimpleNamespace):
     model = oracle_model(case.cfg["model"])
+    if case.cfg["model"] == "goal_in_danger_zone":
+        model = mo.GoalInDangerZoneModel(goal=case.cfg["goal"], center=case.cfg["center"], radius=case.cfg["radius"])
     u_min, u_max = bounds_for(case.cfg, model)
     solver = mo.OracleMPPI(dim_state=model.dim_state, dim_control=model.dim_control, dynamics=model.dynamics,
                            cost_func=model.cost, u_min=u_min, u_max=u_max, sigmas=case.cfg["sigmas"],

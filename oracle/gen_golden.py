@@ -132,6 +132,37 @@ def racing_case(name, cfg, n_solves=3):
              pre_solve=pre_solve, extra_cfg=dict(cfg, model="racing"))
 
 
+def goal_zone_case(name, cfg, goal, state0, n_solves=3):
+    """GoalInDangerZoneEnv needs gymnasium to be constructed; its two batch methods are plain torch code,
+    so they are compiled from the reference file where it lies (src/envs/goal_in_danger_zone.py:113-156)
+    and bound to an object that carries exactly the attributes they read."""
+    import ast
+    import types
+
+    ns = rh.load_reference()
+    path = os.path.join(rh.REFERENCE_ROOT, "src", "envs", "goal_in_danger_zone.py")
+    tree = ast.parse(open(path).read(), filename=path)
+    env_ns = {"torch": torch, "np": np}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name in ("parallel_step", "parallel_cost"):
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), env_ns)
+    env = types.SimpleNamespace(_v_min=-1.0, _v_max=1.0, _omega_min=-1.0, _omega_max=1.0, _dt=0.1,
+                                _goal=np.array(goal), _danger_zone=types.SimpleNamespace(center=[0.0, 0.0], radius=10.0))
+    step = types.MethodType(env_ns["parallel_step"], env)
+    cost = types.MethodType(env_ns["parallel_cost"], env)
+    recorder = CostRecorder(cost)
+    kw = dict(cfg)
+    solver = ns.MPPI(dim_state=7, dim_control=2, dynamics=step, cost_func=recorder, u_min=torch.tensor([-1.0, -1.0]),
+                     u_max=torch.tensor([1.0, 1.0]), sigmas=torch.tensor(kw.pop("sigmas")), **kw)
+
+    def advance(state, a):
+        return step(state.view(1, -1), a[0].view(1, -1)).view(-1)
+
+    run_case(name, solver, recorder, cfg["horizon"], torch.tensor(state0, dtype=torch.float32), advance, n_solves,
+             extra_cfg=dict(cfg, model="goal_in_danger_zone", goal=list(goal), center=[0.0, 0.0], radius=10.0,
+                            state0=state0))
+
+
 def env_fixtures():
     env, ctl, _ = rh.make_racing()
     om, lm = env._obstacle_map, env._lane_map
@@ -158,11 +189,20 @@ def env_fixtures():
     print("env fixtures written")
 
 
-def main():
+def main(only=None):
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    env_fixtures()
+    if only is None:
+        env_fixtures()
     # BASELINE.json config 1, verbatim: the reference's own CPU-runnable case
+    if only in (None, "extra"):
+        closure_case("mujoco_cartpole", "mujoco_cartpole", ["dynamics", "cost_func"],
+                     dict(horizon=50, num_samples=512, dim_state=4, dim_control=1, u_min=[-3.0], u_max=[3.0],
+                          sigmas=[1.0], lambda_=1.0), [0.0, 0.0, 0.05, 0.0])  # example/mujoco_cartpole.py:95-106
+        goal_zone_case("goal_in_danger_zone", dict(horizon=30, num_samples=768, sigmas=[0.5, 0.5], lambda_=1.0),
+                       goal=(3.2, -4.1), state0=[12.0, 9.0, -2.4, 3.2 - 12.0, -4.1 - 9.0, -12.0, -9.0])
+    if only == "extra":
+        return
     closure_case("pendulum_c1", "pendulum", ["dynamics", "cost_function"],
                  dict(horizon=50, num_samples=1000, dim_state=2, dim_control=1, u_min=[-2.0], u_max=[2.0],
                       sigmas=[1.0], lambda_=1.0), [3.14, 0.0])
@@ -188,4 +228,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else None)  # `extra`: only the later-added models

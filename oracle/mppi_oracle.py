@@ -276,6 +276,75 @@ class RacingModel:
         return path_cost + velocity_cost + occ + input_cost  # :157
 
 
+class CartpoleContinuousModel:
+    """example/mujoco_cartpole.py:20-80: the cartpole equations with pole mass 1.0, the continuous
+    action as the force (no bang-bang) and |x| <= 1."""
+
+    name = "cartpole_continuous"
+    dim_state, dim_control = 4, 1
+
+    def dynamics(self, state, action):
+        x = state[:, 0].view(-1, 1)
+        x_dt = state[:, 1].view(-1, 1)
+        theta = state[:, 2].view(-1, 1)
+        theta_dt = state[:, 3].view(-1, 1)
+        force = action[:, 0].view(-1, 1)  # :33
+        total_mass = 1.0 + 1.0  # :38
+        polemass_length = 1.0 * 0.5  # :40
+        costheta = torch.cos(theta)
+        sintheta = torch.sin(theta)
+        temp = (force + polemass_length * theta_dt**2 * sintheta) / total_mass  # :46
+        thetaacc = (9.8 * sintheta - costheta * temp) / (0.5 * (4.0 / 3.0 - 1.0 * costheta**2 / total_mass))  # :47-49
+        xacc = temp - polemass_length * thetaacc * costheta / total_mass  # :50
+        newx = x + 0.02 * x_dt  # :52-55
+        newx_dt = x_dt + 0.02 * xacc
+        newtheta = theta + 0.02 * theta_dt
+        newtheta_dt = theta_dt + 0.02 * thetaacc
+        newx = torch.clamp(newx, -1.0, 1.0)  # :57-62
+        lim = 12 * 2 * torch.pi / 360
+        newtheta = torch.clamp(newtheta, -lim, lim)
+        return torch.cat((newx, newx_dt, newtheta, newtheta_dt), dim=1)
+
+    def cost(self, state, action, info):
+        x, theta, theta_dt = state[:, 0], state[:, 2], state[:, 3]
+        return wrap_angle(theta) ** 2 + 0.1 * theta_dt**2 + 0.1 * x**2  # :68-80
+
+
+class GoalInDangerZoneModel:
+    """src/envs/goal_in_danger_zone.py:113-156 (parallel_step / parallel_cost): unicycle whose 7-dim
+    observation carries the vectors to the goal and to the danger-zone centre."""
+
+    name = "goal_in_danger_zone"
+    dim_state, dim_control = 7, 2
+
+    def __init__(self, goal=(3.0, -4.0), center=(0.0, 0.0), radius=10.0, v_lim=(-1.0, 1.0), w_lim=(-1.0, 1.0),
+                 dt=0.1, collision_cost=1000.0):
+        self.goal, self.center, self.radius = list(goal), list(center), radius
+        self.v_lim, self.w_lim, self.dt, self.collision_cost = v_lim, w_lim, dt, collision_cost
+        self.u_min = torch.tensor([v_lim[0], w_lim[0]])
+        self.u_max = torch.tensor([v_lim[1], w_lim[1]])
+
+    def dynamics(self, obs, action):
+        x = obs[:, 0].view(-1, 1)
+        y = obs[:, 1].view(-1, 1)
+        theta = obs[:, 2].view(-1, 1)
+        v = torch.clamp(action[:, 0].view(-1, 1), self.v_lim[0], self.v_lim[1])  # :118-119
+        omega = torch.clamp(action[:, 1].view(-1, 1), self.w_lim[0], self.w_lim[1])
+        theta = wrap_angle(theta + omega * self.dt)  # :124
+        new_x = x + v * torch.cos(theta) * self.dt  # :126-127
+        new_y = y + v * torch.sin(theta) * self.dt
+        pos = torch.cat((new_x, new_y), dim=-1)
+        vec_to_goal = torch.tensor(self.goal, dtype=obs.dtype) - pos  # :129-134
+        vec_to_center = torch.tensor(self.center, dtype=obs.dtype) - pos
+        return torch.cat((new_x, new_y, theta, vec_to_goal, vec_to_center), dim=-1)
+
+    def cost(self, obs, action, info):
+        cost = torch.norm(obs[:, 3:5], dim=-1)  # :145
+        is_collided = torch.norm(obs[:, 5:7], dim=-1) < self.radius  # :153
+        cost += is_collided.float() * self.collision_cost  # :154
+        return cost
+
+
 def racing_reference_path(state: torch.Tensor, path: torch.Tensor, cind: int, horizon: int, v_max: float = 8.0,
                           DL: float = 0.1, lookahead_distance: float = 3.0,
                           reference_path_interval: float = 0.85) -> Tuple[torch.Tensor, int]:

@@ -8,7 +8,11 @@ import mppi_playground_b200 as eng
 from oracle import fixtures as fx
 
 
-def engine_model(name: str):
+def engine_model(name: str, cfg=None):
+    if name == "mujoco_cartpole":
+        return eng.CartpoleContinuousModel()
+    if name == "goal_in_danger_zone":
+        return eng.GoalInDangerZoneModel(goal=cfg["goal"], center=cfg["center"], radius=cfg["radius"])
     if name == "pendulum":
         return eng.PendulumModel()
     if name == "cartpole":
@@ -35,7 +39,7 @@ def bounds(cfg: dict, model):
 
 def build_engine(cfg: dict, **overrides):
     """(model descriptor, MPPI) for a golden-style cfg dict."""
-    model = engine_model(cfg["model"])
+    model = engine_model(cfg["model"], cfg)
     u_min, u_max = bounds(cfg, model)
     kw = fx.solver_kwargs(cfg)
     kw.update(overrides)
@@ -48,6 +52,8 @@ def build_oracle(cfg: dict, **overrides):
     from oracle import mppi_oracle as mo
 
     model = fx.oracle_model(cfg["model"])
+    if cfg["model"] == "goal_in_danger_zone":
+        model = mo.GoalInDangerZoneModel(goal=cfg["goal"], center=cfg["center"], radius=cfg["radius"])
     u_min, u_max = (cfg["u_min"], cfg["u_max"]) if "u_min" in cfg else (model.u_min.tolist(), model.u_max.tolist())
     kw = fx.solver_kwargs(cfg)
     kw.update(overrides)

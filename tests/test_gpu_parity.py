@@ -12,7 +12,7 @@ from engine_util import ParityStats, TOL, assert_parity, build_engine, build_ora
 from oracle import fixtures as fx
 
 pytestmark = pytest.mark.gpu
-SMOOTH = {"pendulum", "cartpole", "mountaincar"}
+SMOOTH = {"pendulum", "cartpole", "mountaincar", "mujoco_cartpole"}
 REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_report.jsonl")
 
 
@@ -72,6 +72,11 @@ def test_top_samples_match_reference(name):
 
 
 CLOSED_LOOP = [
+    dict(model="mujoco_cartpole", horizon=50, num_samples=1000, u_min=[-3.0], u_max=[3.0], sigmas=[1.0], lambda_=1.0,
+         state0=[0.0, 0.0, 0.05, 0.0]),  # example/mujoco_cartpole.py:95-106
+    dict(model="goal_in_danger_zone", horizon=30, num_samples=3000, u_min=[-1.0, -1.0], u_max=[1.0, 1.0],
+         sigmas=[0.5, 0.5], lambda_=1.0, goal=[-2.5, 6.0], center=[0.0, 0.0], radius=10.0,
+         state0=[-14.0, 3.0, 0.4, -2.5 + 14.0, 6.0 - 3.0, 14.0, -3.0]),  # example/goal_in_danger_zone.py:30-41
     dict(model="pendulum", horizon=50, num_samples=1000, u_min=[-2.0], u_max=[2.0], sigmas=[1.0], lambda_=1.0,
          state0=[3.14, 0.0]),  # BASELINE.json config 1
     dict(model="cartpole", horizon=50, num_samples=2048, u_min=[-3.0], u_max=[3.0], sigmas=[1.0], lambda_=0.001,

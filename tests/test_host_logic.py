@@ -11,7 +11,8 @@ from oracle import mppi_oracle as mo
 
 
 @pytest.mark.parametrize("oracle_cls,want", [(mo.PendulumModel, "pendulum"), (mo.CartpoleModel, "cartpole"),
-                                             (mo.MountainCarModel, "mountaincar")])
+                                             (mo.MountainCarModel, "mountaincar"),
+                                             (mo.CartpoleContinuousModel, "cartpole_continuous")])
 def test_example_closures_are_fingerprinted(oracle_cls, want):
     m = oracle_cls()  # same arithmetic as the example closures (pinned by the golden tests)
     b = models.resolve(m.dynamics, m.cost, m.dim_state, m.dim_control)
@@ -133,3 +134,25 @@ def test_shard_bounds_partition_the_samples(K, world):
     assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         eng.shard_bounds(K, world, world)
+
+
+def test_goal_in_danger_zone_env_is_recognised_and_goal_is_reread():
+    class Zone:
+        center, radius = [0.0, 0.0], 10.0
+
+    class GoalInDangerZoneEnv:  # attribute names of src/envs/goal_in_danger_zone.py:79-99
+        _v_min, _v_max, _omega_min, _omega_max, _dt = -1.0, 1.0, -1.0, 1.0, 0.1
+        _danger_zone = Zone()
+        _goal = np.array([1.0, 2.0])
+
+        def parallel_step(self, obs, action):
+            raise AssertionError("never called on the host")
+
+        def parallel_cost(self, obs, action, info):
+            raise AssertionError("never called on the host")
+
+    env = GoalInDangerZoneEnv()
+    b = models.resolve(env.parallel_step, env.parallel_cost, 7, 2)
+    assert b.model_id == _capi.MODEL_GOAL_IN_DANGER_ZONE and len(b.params()) == _capi.GOAL_ZONE_NUM_PARAMS
+    env._goal = np.array([-3.0, 4.0])  # env.reset() draws a new goal
+    assert b.params()[5:7] == [-3.0, 4.0]

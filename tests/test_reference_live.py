@@ -43,12 +43,14 @@ def test_navigation2d_objects_resolve():
 
 @pytest.mark.parametrize("example,names,want", [("pendulum", ["dynamics", "cost_function"], "pendulum"),
                                                 ("cartpole", ["dynamics", "stage_cost"], "cartpole"),
-                                                ("mountaincar", ["dynamics", "cost_func"], "mountaincar")])
+                                                ("mountaincar", ["dynamics", "cost_func"], "mountaincar"),
+                                                ("mujoco_cartpole", ["dynamics", "cost_func"],
+                                                 "cartpole_continuous")])
 def test_example_closures_resolve(example, names, want):
     from mppi_playground_b200 import models
 
     dyn, cost = rh.extract_closures(example, names)
-    ds = {"pendulum": 2, "cartpole": 4, "mountaincar": 2}[example]
+    ds = {"pendulum": 2, "cartpole": 4, "mountaincar": 2, "mujoco_cartpole": 4}[example]
     assert models.resolve(dyn, cost, ds, 1).name == want
 
 
