@@ -130,8 +130,7 @@ int mppi_set_model_params(MppiHandle* h, const float* params, int32_t n);
 /* Occupancy grid for slot 0 (obstacle map; NAVIGATION2D and RACING) or slot 1
  * (lane map; RACING). `grid` is the reference's [W,H] fp32 0/1 map, x on the
  * slow axis (src/envs/obstacle_map_2d.py:195), on the device if on_device != 0.
- * It is bit-packed once (with a one-cell border of ones = the out-of-bounds value) into the layout the
- * kernels stage into shared memory; grids too large for shared memory stay in global memory.
+ * It is bit-packed once into the layout the kernels stage into shared memory.
  * Synchronous. */
 int mppi_set_map(MppiHandle* h, int32_t slot, const float* grid, int32_t on_device, int32_t width, int32_t height,
                  float cell_size, float origin_x, float origin_y);

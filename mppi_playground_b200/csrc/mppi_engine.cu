@@ -420,20 +420,11 @@ void refresh_model_flags(MppiHandle* h) {
 
 void refresh_launch_geometry(MppiHandle* h) {
   unsigned mb[2] = {h->base.map_bytes[0], h->base.map_bytes[1]};
-  // stage the grids into shared memory when they fit next to everything else; otherwise they stay in
-  // global memory (same lookups through L1/L2) and the blocks need only the small buffers
-  int n_staged = h->mi.maps;
-  {
-    SmemLayout L = make_layout(n_staged, mb, h->cfg.horizon, h->E_pad, h->base.prev_action_bytes, h->mi.refpath, 2,
-                               h->mi.tail_per_step);
-    if (L.total > kMaxSmem) n_staged = 0;
-  }
-  h->base.maps_in_smem = n_staged > 0 ? 1 : 0;
-  int bs = h->cfg.block_size > 0 ? h->cfg.block_size : pick_block(h, n_staged, mb, h->base.prev_action_bytes);
-  if (bs <= 0) bs = 64;
+  int bs = h->cfg.block_size > 0 ? h->cfg.block_size : pick_block(h, h->mi.maps, mb, h->base.prev_action_bytes);
+  if (bs <= 0) bs = 64;  // nothing fits (oversized grids): the shared-memory check below reports it
   h->block = bs;
   h->grid = (h->cfg.num_samples + bs - 1) / bs;
-  h->smem = make_layout(n_staged, mb, h->cfg.horizon, h->E_pad, h->base.prev_action_bytes, h->mi.refpath, bs / 32,
+  h->smem = make_layout(h->mi.maps, mb, h->cfg.horizon, h->E_pad, h->base.prev_action_bytes, h->mi.refpath, bs / 32,
                         h->mi.tail_per_step)
                 .total;
 }

@@ -55,7 +55,6 @@ struct SolveParams {
   const uint32_t* map_bits[2];
   int map_W[2], map_H[2], map_words[2];
   unsigned map_bytes[2];  // padded to 16 B
-  int maps_in_smem;       // 0: the grids are too large for shared memory and are read from global memory (L1/L2)
   float map_cell[2], map_rcp[2], map_ox[2], map_oy[2];
   int map_fastdiv[2];  // (cell, rcp) passed the exhaustive exact-division check
   const float* state;    // [ds]
@@ -638,8 +637,7 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ S
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
   const SmemLayout L =
-      make_layout(p.maps_in_smem ? M::kMaps : 0, p.map_bytes, p.T, p.E_pad, p.prev_action_bytes, M::kRefPath, n_warps,
-                  tail_per_step<M>());
+      make_layout(M::kMaps, p.map_bytes, p.T, p.E_pad, p.prev_action_bytes, M::kRefPath, n_warps, tail_per_step<M>());
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   float* nominal = reinterpret_cast<float*>(smem + L.nominal_off);
   float* warp_acc = reinterpret_cast<float*>(smem + L.warpacc_off);
@@ -656,14 +654,13 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ S
   if (tid == 0) {
     unsigned bytes = p.prev_action_bytes;
     if (kMode != kReduce) {
-      for (int i = 0; i < (p.maps_in_smem ? M::kMaps : 0); ++i) bytes += p.map_bytes[i];
+      for (int i = 0; i < M::kMaps; ++i) bytes += p.map_bytes[i];
       if (M::kRefPath && p.ref_bulk_ok && !p.inline_inputs) bytes += (unsigned)(p.T + 1) * 16;
     }
     mbar_expect_tx(bar, bytes);
     bulk_g2s(nominal, p.prev_action, p.prev_action_bytes, bar);
     if (kMode != kReduce) {
-      for (int i = 0; i < (p.maps_in_smem ? M::kMaps : 0); ++i)
-        bulk_g2s(smem + L.map_off[i], p.map_bits[i], p.map_bytes[i], bar);
+      for (int i = 0; i < M::kMaps; ++i) bulk_g2s(smem + L.map_off[i], p.map_bits[i], p.map_bytes[i], bar);
       if (M::kRefPath && p.ref_bulk_ok && !p.inline_inputs)
         bulk_g2s(smem + L.refraw_off, p.refpath, (unsigned)(p.T + 1) * 16, bar);
     }
@@ -680,8 +677,7 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ S
   if constexpr (M::kMaps >= 1) {
     MapView mv[2];
     for (int i = 0; i < M::kMaps; ++i)
-      mv[i] = MapView{p.maps_in_smem ? reinterpret_cast<const uint32_t*>(smem + L.map_off[i]) : p.map_bits[i],
-                      p.map_W[i], p.map_H[i], p.map_words[i],
+      mv[i] = MapView{reinterpret_cast<const uint32_t*>(smem + L.map_off[i]), p.map_W[i], p.map_H[i], p.map_words[i],
                       ExactDiv{p.map_cell[i], p.map_rcp[i], p.map_fastdiv[i]}, p.map_ox[i], p.map_oy[i]};
     if constexpr (M::kMaps == 1) {
       ctx.map = mv[0];

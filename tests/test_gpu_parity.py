@@ -583,33 +583,3 @@ def test_full_size_solves_by_size_independent_properties(cfg):
     # (4) determinism
     a2, s2 = twin.forward(state)
     assert torch.equal(a2, action) and torch.equal(s2, states) and torch.equal(twin._costs, costs)
-
-
-def test_grids_too_large_for_shared_memory_are_read_from_global_memory():
-    """A 1600 x 1600 occupancy grid (325 kB bit-packed) cannot be staged into shared memory; the engine
-    keeps it in global memory and must give the same solve as the oracle."""
-    import mppi_playground_b200 as eng
-    from oracle import mppi_oracle as mo
-
-    g = torch.Generator().manual_seed(11)
-    grid = (torch.rand(1600, 1600, generator=g) < 0.02).float()
-    grid[700:760, 820:900] = 1.0
-    kw = dict(u_min=(0.0, -1.0), u_max=(2.0, 1.0), goal=(9.0, 9.0), lim=(-10.0, 10.0, -10.0, 10.0))
-    model = eng.Navigation2DModel(grid, 0.0125, (800, 800), **kw)
-    omodel = mo.Navigation2DModel(mo.GridMap(grid, 0.0125, (800, 800)), **kw)
-    args = dict(horizon=40, num_samples=2048, dim_state=3, dim_control=2, u_min=torch.tensor([0.0, -1.0]),
-                u_max=torch.tensor([2.0, 1.0]), sigmas=torch.tensor([0.5, 0.5]), lambda_=2.0)
-    solver = eng.MPPI(dynamics=model.dynamics, cost_func=model.cost_func, **args)
-    oracle = mo.OracleMPPI(dynamics=omodel.dynamics, cost_func=omodel.cost, burn_constructor_draw=False,
-                           **{k: (v.tolist() if torch.is_tensor(v) else v) for k, v in args.items()})
-    state = torch.tensor([-1.0, 0.5, 0.3])
-    for _ in range(2):
-        noise = solver.sampler_noise().cpu()
-        action, states = solver.forward(state)
-        assert solver.launch_info()["smem_bytes"] < 100 * 1024  # the grid was not staged
-        tr = oracle.forward(state, noise=noise)
-        st = ParityStats(solver._costs.cpu().numpy(), tr.costs.numpy(), action.cpu().numpy(), tr.action_seq.numpy(),
-                         states.cpu().numpy(), tr.state_seq.numpy(), 2.0, 2.0)
-        assert_parity(st)
-        oracle.prev_action_seq = action.cpu().clone()
-        state = states[0, 1].cpu().clone()
