@@ -564,11 +564,70 @@ __device__ __forceinline__ float model_cost(const typename M::Ctx& ctx, const fl
     return M::cost(ctx, s, u, pu, t);
 }
 
+// Loop constants held in ordinary registers: ptxas otherwise re-materialises kernel parameters from the
+// constant bank inside the pass-1 loop (one LDCU issue slot each, ~17 per step on the racing model).
+// A warp shuffle of the (warp-uniform) value is opaque to ptxas, so it has to stay live in a register;
+// values are unchanged.
+__device__ __forceinline__ float pin(float v) {  // all lanes hold the same v; must be called by the full warp
+  return __shfl_sync(kFullMask, v, 0);
+}
+__device__ __forceinline__ int pin(int v) {
+  return __shfl_sync(kFullMask, v, 0);
+}
+__device__ __forceinline__ void pin_map(MapView& m) {
+  m.saddr = (unsigned)pin((int)__cvta_generic_to_shared(m.bits));
+  m.words = pin(m.words);
+  m.cell.c = pin(m.cell.c);
+  m.cell.r = pin(m.cell.r);
+  m.ox = pin(m.ox);
+  m.oy = pin(m.oy);
+}
+
+// Loop constants of one thread, pinned by the whole warp before the per-sample branch.
+template <class M>
+struct LoopConsts {
+  typename M::Ctx ctx;
+  float sigma[M::DU], lo[M::DU], hi[M::DU];
+  int T, zero_mean;
+};
+template <class M>
+__device__ __forceinline__ void pin_loop_consts(const SolveParams& p, const typename M::Ctx& ctx, bool zero_mean,
+                                                LoopConsts<M>& lc) {
+  lc.ctx = ctx;
+  constexpr int kHot = sizeof(lc.ctx.hv) / sizeof(float);
+#pragma unroll
+  for (int i = 0; i < kHot; ++i) lc.ctx.hv[i] = pin(ctx.p->v[i]);
+  if constexpr (M::kMaps == 1) pin_map(lc.ctx.map);
+  if constexpr (M::kMaps == 2) {
+    pin_map(lc.ctx.obstacle);
+    pin_map(lc.ctx.lane);
+  }
+#pragma unroll
+  for (int d = 0; d < M::DU; ++d) {
+    lc.sigma[d] = pin(p.sigma[d]);
+    lc.lo[d] = pin(p.u_min[d]);
+    lc.hi[d] = pin(p.u_max[d]);
+  }
+  lc.T = pin(p.T);
+  lc.zero_mean = __shfl_sync(kFullMask, zero_mean ? 1 : 0, (int)(threadIdx.x & 31));  // per lane, opaque
+}
+
 template <class M, bool kInject, bool kBounded>
-__device__ __forceinline__ float rollout_cost(const SolveParams& p, const typename M::Ctx& ctx, const float* nominal,
-                                           bool zero_mean, uint32_t k_lo, uint32_t k_hi, long long k_local) {
+__device__ __forceinline__ float rollout_cost(const SolveParams& p, const typename M::Ctx& ctx_in, const float* nominal,
+                                           bool zero_mean_in, uint32_t k_lo, uint32_t k_hi, long long k_local,
+                                           const LoopConsts<M>& lc) {
   constexpr int DS = M::DS, DU = M::DU, SPC = Chunking<DU>::kStepsPerChunk;
-  const int T = p.T;
+  // bounded: every loop constant comes from the pinned register copies (lc), see pin_loop_consts
+  const typename M::Ctx& ctx = kBounded ? lc.ctx : ctx_in;
+  const bool zero_mean = kBounded ? (lc.zero_mean != 0) : zero_mean_in;
+  const int T = kBounded ? lc.T : p.T;
+  float sigma_r[DU], lo_r[DU], hi_r[DU];
+#pragma unroll
+  for (int d = 0; d < DU; ++d) {
+    sigma_r[d] = kBounded ? lc.sigma[d] : p.sigma[d];
+    lo_r[d] = kBounded ? lc.lo[d] : p.u_min[d];
+    hi_r[d] = kBounded ? lc.hi[d] : p.u_max[d];
+  }
   float s[DS], seen[DS];
   {
     const float* state = state_of(p);
@@ -580,6 +639,38 @@ __device__ __forceinline__ float rollout_cost(const SolveParams& p, const typena
   for (int d = 0; d < DU; ++d) up[d] = upp[d] = 0.0f;
   float total = 0.0f;
   const float* nz = kInject ? (p.noise + (size_t)k_local * T * DU) : nullptr;
+  if constexpr (kBounded && !kInject && M::kHasBounded) {
+    // whole sampler chunks without the per-step `t < T` guard; a trailing partial chunk keeps it
+    auto one_step = [&](int t, const float* ez) {
+#pragma unroll
+      for (int d = 0; d < DU; ++d)
+        u[d] = clampf((zero_mean ? 0.0f : nominal[t * DU + d]) + sigma_r[d] * ez[d], lo_r[d], hi_r[d]);
+      float pu[DU];
+#pragma unroll
+      for (int d = 0; d < DU; ++d) pu[d] = (t == 0) ? u[d] : up[d];
+      model_step<M, kBounded>(ctx, s, u, seen);
+      total = total + model_cost<M, kBounded>(ctx, seen, u, pu, t);
+#pragma unroll
+      for (int d = 0; d < DU; ++d) {
+        upp[d] = up[d];
+        up[d] = u[d];
+      }
+    };
+    int t0 = 0, chunk = 0;
+    for (; t0 + SPC <= T; t0 += SPC, ++chunk) {
+      float z[4];
+      normal4(p.key, k_lo, k_hi, (uint32_t)chunk, z);
+#pragma unroll
+      for (int j = 0; j < SPC; ++j) one_step(t0 + j, z + j * DU);
+    }
+    if (t0 < T) {
+      float z[4];
+      normal4(p.key, k_lo, k_hi, (uint32_t)chunk, z);
+#pragma unroll
+      for (int j = 0; j < SPC; ++j)
+        if (t0 + j < T) one_step(t0 + j, z + j * DU);
+    }
+  } else
   for (int t0 = 0, chunk = 0; t0 < T; t0 += SPC, ++chunk) {
     float z[4];
     if (!kInject) normal4(p.key, k_lo, k_hi, (uint32_t)chunk, z);
@@ -589,8 +680,8 @@ __device__ __forceinline__ float rollout_cost(const SolveParams& p, const typena
       if (t < T) {
 #pragma unroll
         for (int d = 0; d < DU; ++d) {
-          float eps = kInject ? nz[t * DU + d] : p.sigma[d] * z[j * DU + d];
-          u[d] = perturbed_entry<DU>(p, nominal, zero_mean, t, d, eps);
+          float eps = kInject ? nz[t * DU + d] : sigma_r[d] * z[j * DU + d];
+          u[d] = clampf((zero_mean ? 0.0f : nominal[t * DU + d]) + eps, lo_r[d], hi_r[d]);  // == perturbed_entry
         }
         float pu[DU];  // info["prev_action"]: U[:, max(t-1, 0)]  (mppi.py:299-304)
 #pragma unroll
@@ -716,12 +807,18 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ S
   float cost = INFINITY;
   if (kMode == kReduce) {
     if (active) cost = p.costs[k_local];
-  } else if (active) {
+  } else {
     bool bounded = false;  // uniform over the block: model flag + the solve's initial state
     if constexpr (M::kHasBounded) bounded = (p.mp.flags & kFlagBounded) && M::state_in_bounds(ctx, state_of(p));
-    cost = bounded ? rollout_cost<M, kInject, true>(p, ctx, nominal, zero_mean, k_lo, k_hi, k_local)
-                   : rollout_cost<M, kInject, false>(p, ctx, nominal, zero_mean, k_lo, k_hi, k_local);
-    p.costs[k_local] = cost;
+    LoopConsts<M> lc;
+    if constexpr (M::kHasBounded) {
+      if (bounded) pin_loop_consts<M>(p, ctx, zero_mean, lc);  // whole warps: before the per-sample branch
+    }
+    if (active) {
+      cost = bounded ? rollout_cost<M, kInject, true>(p, ctx, nominal, zero_mean, k_lo, k_hi, k_local, lc)
+                     : rollout_cost<M, kInject, false>(p, ctx, nominal, zero_mean, k_lo, k_hi, k_local, lc);
+      p.costs[k_local] = cost;
+    }
   }
   if (kMode == kCosts) return;
   __syncthreads();

@@ -49,6 +49,7 @@ struct MapView {
   int W, H, words;
   ExactDiv cell;
   float ox, oy;
+  unsigned saddr;  // shared-window address of `bits`, held in a register by the bounded loop (pin_map)
 };
 
 // cell index of a world coordinate: round(x / cell + origin) half-to-even, as integer
@@ -80,7 +81,8 @@ __device__ __forceinline__ float map_value(const MapView& m, int ix, int iy) {
 // cell index in [0, W] x [0, H] reads the out-of-bounds value 1.0 without any bounds logic. Only used
 // when the host proved that every rolled-out position maps into that range (kFlagBounded).
 __device__ __forceinline__ float map_value_bordered(const MapView& m, int ix, int iy) {
-  const uint32_t w = m.bits[ix * m.words + (iy >> 5)];
+  uint32_t w;  // the staged grid is read-only for the whole loop
+  asm("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(m.saddr + 4u * (unsigned)(ix * m.words + (iy >> 5))));
   return (float)((w >> (iy & 31)) & 1u);
 }
 
@@ -214,12 +216,18 @@ struct Navigation2D {  // src/envs/navigation_2d.py:218-279
   struct Ctx {
     MapView map;
     const ModelParams* p;  // v_min v_max w_min w_max goal_x goal_y x_lo x_hi y_lo y_hi dt w_obst
+    float hv[12];          // register copy of p->v[0..11] for the bounded pass-1 loop (pin_loop_consts)
   };
+  template <bool kBounded>
+  __device__ static __forceinline__ const float* params(const Ctx& c) {
+    if (kBounded) return c.hv;
+    return c.p->v;
+  }
   // kBounded: the host proved |omega dt| < 6 and the kernel checked the initial heading, so every
   // heading stays within the exact range of wrap_angle_bounded (same values, no slow path).
   template <bool kBounded = false>
   __device__ static __forceinline__ void step(const Ctx& c, float (&s)[DS], const float (&u)[DU], float (&seen)[DS]) {
-    const float* p = c.p->v;
+    const float* p = params<kBounded>(c);
 #pragma unroll
     for (int i = 0; i < DS; ++i) seen[i] = s[i];
     float v = kBounded ? u[0] : clampf(u[0], p[0], p[1]);  // :235-236 (identity under kFlagBounded)
@@ -244,7 +252,7 @@ struct Navigation2D {  // src/envs/navigation_2d.py:218-279
   template <bool kBounded = false>
   __device__ static __forceinline__ float cost(const Ctx& c, const float (&s)[DS], const float (&)[DU],
                                                const float (&)[DU], int) {
-    const float* p = c.p->v;
+    const float* p = params<kBounded>(c);
     float dx = s[0] - p[4], dy = s[1] - p[5];
     float goal = sqrtf(dx * dx + dy * dy);  // :269
     float occ = kBounded ? map_value_bordered(c.map, map_cell_bounded(s[0], c.map.cell, c.map.ox),
@@ -310,7 +318,13 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
     const ModelParams* p;  // a_min a_max s_min s_max L v_max x_lo x_hi y_lo y_hi dt Qc Ql Qv Qo Qin Qdin
     const float4* ref;     // per stage t: (x, y, sin yaw, cos yaw) of reference_path[t]
     const float* ref_v;    // per stage t: target speed reference_path[t, 3]
+    float hv[18];          // register copy of p->v[0..17] for the bounded pass-1 loop (pin_loop_consts)
   };
+  template <bool kBounded>
+  __device__ static __forceinline__ const float* params(const Ctx& c) {
+    if (kBounded) return c.hv;
+    return c.p->v;
+  }
   template <bool kBounded = false>
   __device__ static __forceinline__ float yaw_rate(const ModelParams& mp, float v, float tan_steer) {
     // racing_env.py:352  v * tan(steer) / L ; the division by the wheelbase goes through the proven
@@ -324,10 +338,17 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
     }
     return div_exact(r, ExactDiv{mp.v[4], mp.v[17], mp.flags & kFlagUnitWheelbase});
   }
+  // yaw_rate<true> on the register copy of the parameters
+  __device__ static __forceinline__ float yaw_rate_hot(const float* pv, float v, float tan_steer) {
+    const float r = v * tan_steer;
+    float q = r * pv[17];
+    q = fmaf(fmaf(-q, pv[4], r), pv[17], q);
+    return (fabsf(r) >= kFastDivMin) ? q : r;
+  }
   // kBounded: host-proved steering / yaw bounds + kernel-checked initial state, see kFlagBounded.
   template <bool kBounded = false>
   __device__ static __forceinline__ void step(const Ctx& c, float (&s)[DS], const float (&u)[DU], float (&seen)[DS]) {
-    const float* p = c.p->v;
+    const float* p = params<kBounded>(c);
 #pragma unroll
     for (int i = 0; i < DS; ++i) seen[i] = s[i];
     float accel = kBounded ? u[0] : clampf(u[0], p[0], p[1]);  // :345-346 (identity under kFlagBounded)
@@ -340,7 +361,7 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
       sincosf(th, &st, &ct);
     float dx = s[3] * ct;  // :349-352
     float dy = s[3] * st;
-    float dth = yaw_rate<kBounded>(*c.p, s[3], kBounded ? tan_quarter(steer) : tanf(steer));
+    float dth = kBounded ? yaw_rate_hot(p, s[3], tan_quarter(steer)) : yaw_rate<false>(*c.p, s[3], tanf(steer));
     float nx = s[0] + dx * p[10];  // :354-357
     float ny = s[1] + dy * p[10];
     float nth = kBounded ? wrap_angle_bounded(th + dth * p[10]) : wrap_angle(th + dth * p[10]);
@@ -358,7 +379,7 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
   template <bool kBounded = false>
   __device__ static __forceinline__ float cost(const Ctx& c, const float (&s)[DS], const float (&u)[DU],
                                                const float (&pu)[DU], int t) {
-    const float* p = c.p->v;
+    const float* p = params<kBounded>(c);
     const float4 r = c.ref[t];
     float sx = s[0] - r.x, sy = s[1] - r.y;
     float ec = r.z * sx - r.w * sy;                         // racing.py:127-131
