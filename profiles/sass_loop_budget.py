@@ -5,7 +5,7 @@
 
 Finds solve_kernel<Racing, inject=false, mode=fused>, takes its first long backward branch (the bounded pass-1
 loop: one Philox4x32-10 call = 4 normals = 2 time steps per iteration) and counts instructions by opcode. With
-the kernel issue-bound (profiles/r01_solve_kernel_ncu.md: issue active 78 %, no pipe above 46 %), instructions per
+the kernel issue/latency-bound (profiles/r01_solve_kernel_ncu.md: issue active 73 %, no pipe above 48 %), instructions per
 step x steps x warps per scheduler / clock is the floor for pass 1 at this instruction mix.
 """
 import collections
@@ -58,17 +58,19 @@ def main():
     slots = per_step * T * warps_per_sched
     print(f"Issue floor: {per_step:.0f} instr/step x T={T} x {warps_per_sched} warps per scheduler (512-thread block, "
           f"1 block per SM) = {slots:,.0f} issue slots per scheduler = **{slots / mhz:.1f} us at {mhz:.0f} MHz**. "
-          "Measured pass 1 (in-kernel `%globaltimer`, `profiles/block_trace_r01.txt`, median block): 40.9 us at the same "
+          "Measured pass 1 (in-kernel `%globaltimer`, `profiles/block_trace_r01.txt`, median block): 38.2 us at the same "
           "clock (`profiles/bench_r01_n1.json` `clocks`), i.e. the loop runs at "
-          f"~{100.0 * slots / mhz / 40.9:.0f} % of one instruction per cycle per scheduler. The rest of the 70 us launch "
+          f"~{100.0 * slots / mhz / 38.2:.0f} % of one instruction per cycle per scheduler. The rest of the 70 us launch "
           "is staging, the weight/combine phases and the block-parallel tail rollout (same file).\n")
     print("What the count is made of: the arithmetic follows the reference's fp32 operation order without FMA "
           "contraction (`-fmad=false`; every FFMA here is an explicit `fmaf` of the `sinf`/`cosf`/`tanf` polynomials "
-          "or of the exact-division step), so ~60 % of the slots are fixed by bit-parity. Reclaimable without touching "
-          "results: the constant-bank reloads (uniform registers spill across the unrolled pair of steps), the "
-          "per-step 64-bit exploration compare, and the two separate map-word loads (a merged 2-bit grid makes "
-          "them one) - about 25 of the per-step slots, DESIGN.md section 8.")
-
+          "or of the exact-division step), so about two thirds of the slots are fixed by bit-parity; Philox4x32-10 is "
+          "another 21 per step. History: 212 per step before the loop constants were pinned in registers (17 `LDCU` "
+          "constant-bank reloads per step, the per-step 64-bit exploration compare, the shared-window address "
+          "arithmetic of the grids and the `t < T` guards of the unrolled pair of steps); measured pass 1 went from "
+          "40.9 us to 38.2 us. Still reclaimable without touching results: the two separate map-word loads (a merged "
+          "2-bit grid makes them one), the lower fold of the second heading wrap, the `t == 0` select - DESIGN.md "
+          "section 8.")
 
 if __name__ == "__main__":
     main()

@@ -1,9 +1,12 @@
 #!/usr/bin/env python
 """Turn gpurun_out/prof_<tag>.ncu-rep + launches_<tag>.csv into the committed summaries
-   profiles/<tag>_solve_kernel.md and profiles/<tag>_launches.md  (run in the build container)."""
+   profiles/r01_solve_kernel_ncu.md, profiles/r01_launches_ncu.md and profiles/ncu_traffic.json (the
+   DRAM bytes and pipe figures bench.py reports as roofline.traffic / ncu_pipes). Run in the build container:
+   python profiles/summarize_ncu.py <tag>"""
 import collections
 import csv
 import io
+import json
 import subprocess
 import sys
 
@@ -72,7 +75,27 @@ out += ["", "## SASS evidence", "",
         f"`UBLKCP` (cp.async.bulk, TMA engine) occurrences in libmppi_b200.so: {sass.count('UBLKCP')}; "
         f"`SYNCS` (mbarrier): {sass.count('SYNCS')}; tensor-core mnemonics (`UTC*MMA`, `HMMA`): "
         f"{sass.count('UTCHMMA') + sass.count('HMMA')} (none by design: the path has no contraction)."]
-open(f"profiles/{tag}_solve_kernel.md", "w").write("\n".join(out) + "\n")
+open("profiles/r01_solve_kernel_ncu.md", "w").write("\n".join(out) + "\n")
+
+
+def _num(name, row=rows[2]):
+    v = float(row[hdr.index(name)].replace(",", ""))
+    u = units[hdr.index(name)]
+    return v * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1.0)
+
+
+rd, wr = _num("dram__bytes_read.sum"), _num("dram__bytes_write.sum")
+json.dump({"dram_bytes_per_launch": int(rd + wr), "dram_read": int(rd), "dram_write": int(wr),
+           "source": f"profiles/r01_solve_kernel_ncu.md (ncu --set full capture {tag}, dram__bytes_read.sum + "
+                     "dram__bytes_write.sum, launch 0)",
+           "pipes": {"issue_active_pct": _num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                     "fma_pipe_pct": _num("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+                     "alu_pipe_pct": _num("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"),
+                     "xu_pipe_pct": _num("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+                     "tensor_pipe_pct": _num("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+                     "warp_instructions_per_launch": _num("smsp__inst_executed.sum"),
+                     "registers_per_thread": _num("launch__registers_per_thread")}},
+          open("profiles/ncu_traffic.json", "w"), indent=1)
 
 lrows = [r for r in csv.reader(open(launches)) if len(r) > 10]
 lh = lrows[0]
@@ -89,5 +112,5 @@ for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
     lo.append(f"| `{k[:100]}` | {len(v)} | {sum(v) / len(v) / 1e3:.1f} | {sum(v) / 1e3:.1f} | {100 * sum(v) / tot_t:.1f}% |")
 lo += ["", "The memset (`FillFunctor`) launches are bench.py's L2 flush between timed steps, the `pack_map` / "
        "`check_fastdiv` launches are one-time set-up (`mppi_set_map`). Within a solve the only kernel is `solve_kernel` (100%)."]
-open(f"profiles/{tag}_launches.md", "w").write("\n".join(lo) + "\n")
+open("profiles/r01_launches_ncu.md", "w").write("\n".join(lo) + "\n")
 print("ok")
