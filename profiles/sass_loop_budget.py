@@ -27,19 +27,25 @@ GROUPS = [
 ]
 
 
-def main():
-    here = os.path.dirname(os.path.abspath(__file__))
-    lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(here, "..", "mppi_playground_b200", "libmppi_b200.so")
+def loop_body(lib):
+    """SASS instructions (predicates stripped) of the bounded pass-1 loop of the headline kernel, and its bounds."""
     sass = subprocess.run(["cuobjdump", "-sass", "-fun", SYMBOL, lib], capture_output=True, text=True, check=True).stdout
     ins = [(int(m.group(1), 16), re.sub(r"^@!?U?P\d\s+", "", m.group(2)))
            for m in re.finditer(r"/\*([0-9a-f]{4,5})\*/\s+(.*?);", sass)]
-    loop = None
     for addr, text in ins:
         m = re.search(r"BRA\s+0x([0-9a-f]+)", text)
         if m and addr - int(m.group(1), 16) > 0x1000:
             loop = (int(m.group(1), 16), addr)
-            break
-    body = [t for a, t in ins if loop[0] <= a <= loop[1]]
+            return [t for a, t in ins if loop[0] <= a <= loop[1]], loop
+    raise RuntimeError("pass-1 loop not found in " + lib)
+
+
+DEFAULT_LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "mppi_playground_b200", "libmppi_b200.so")
+
+
+def main():
+    lib = sys.argv[1] if len(sys.argv) > 1 else DEFAULT_LIB
+    body, loop = loop_body(lib)
     ops = collections.Counter(t.split()[0].split(".")[0] for t in body)
     steps_per_iter, T, warps_per_sched, mhz = 2, 80, 4, 1965.0
     per_step = len(body) / steps_per_iter

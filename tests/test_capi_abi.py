@@ -91,3 +91,22 @@ def test_product_never_imports_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), os.path.join(d, f)
     code = "import sys; import mppi_playground_b200; assert not any(m.split('.')[0]=='oracle' for m in sys.modules)"
     subprocess.check_call([sys.executable, "-c", code], cwd=ROOT)
+
+
+def test_pass1_loop_issue_budget_does_not_regress():
+    """Static guard on the headline kernel's hot loop (profiles/sass_loop_budget.py): instructions per
+    sample-timestep, and no local-memory traffic or constant-bank reloads inside it."""
+    import importlib.util
+    import shutil
+
+    lib = os.path.join(ROOT, "mppi_playground_b200", "libmppi_b200.so")
+    if not os.path.exists(lib) or shutil.which("cuobjdump") is None:
+        pytest.skip("needs the built library and cuobjdump")
+    spec = importlib.util.spec_from_file_location("sass_loop_budget", os.path.join(ROOT, "profiles", "sass_loop_budget.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    body, _ = mod.loop_body(lib)
+    ops = [t.split()[0].split(".")[0] for t in body]
+    assert len(body) / 2 <= 190, f"{len(body) / 2} SASS instructions per step (round-1 level: 184)"
+    assert not {"LDL", "STL", "LD", "ST"} & set(ops), "local/generic memory traffic inside the pass-1 loop"
+    assert ops.count("LDCU") + ops.count("LDC") <= 2, "loop constants are being re-read from the constant bank"
