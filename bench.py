@@ -1,16 +1,17 @@
 #!/usr/bin/env python
-"""bench.py - MPPI solves/sec (control-loop Hz) of the racing kinematic-bicycle
-solve, K=65536 samples, T=80 steps, SG filter on, lambda=1.0 (BASELINE.json
-configs[3], the configuration `metric` is quoted on).
+"""bench.py - MPPI solves/sec (control-loop Hz).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config c4|c5]
 
-One "step" = one whole MPPI solve (sample -> clamp -> 80-step rollout of 65536
-samples -> costs -> softmax -> weighted mean -> SG filter -> optimal-trajectory
-rollout) on the closed-loop sequence of states / reference paths recorded once,
-before the timed region, so the timed solves run on inputs resident in HBM.
-N > 1: the K samples are sharded over the ranks (strong scaling: the solve is
-the unit, K is fixed); launch with torch.distributed.run as the contract says.
+Default workload (`--config c4`, BASELINE.json configs[3], the configuration `metric` is quoted on): racing
+kinematic-bicycle solve, K=65536 samples, T=80 steps, SG filter on, lambda=1.0. `--config c5` is BASELINE.json
+configs[4]: cartpole K=1 048 576, T=50, sample-sharded over the ranks.
+
+One "step" = one whole MPPI solve (sample -> clamp -> T-step rollout of K samples -> costs -> softmax ->
+weighted mean -> SG filter -> optimal-trajectory rollout) on a closed-loop sequence of states (and reference
+paths) recorded once, before the timed region, so the timed solves run on inputs resident in HBM.
+N > 1: the K samples are sharded over the ranks (strong scaling: the solve is the unit, K is fixed); launch
+with torch.distributed.run as the contract says.
 
 Prints ONE JSON line (rank 0). See DESIGN.md "measurement" for every field.
 """
@@ -33,15 +34,45 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-K_SAMPLES, HORIZON = 65536, 80
-CFG = dict(model="racing", horizon=HORIZON, num_samples=K_SAMPLES, sigmas=[0.5, 0.1], lambda_=1.0, use_sg_filter=True,
-           sg_window_size=5, sg_poly_order=3, exploration=0.0, seed=42)
-# F_step(racing) = 97 fp32 flop per sample-timestep, 61 per sample for terminal + softmax
-FLOPS_PER_SOLVE = K_SAMPLES * HORIZON * 97 + K_SAMPLES * 61
-MAP_BYTES = 2 * 800 * 25 * 4
-BYTES_PER_SOLVE = 4 * K_SAMPLES + 4 * HORIZON * 2 * 2 + 16 * (HORIZON + 1) + 4 * (HORIZON + 1) * 4 + MAP_BYTES
-H2D_BYTES = 4 * 4 + 16 * (HORIZON + 1)
-D2H_BYTES = 4 * HORIZON * 2 + 4 * (HORIZON + 1) * 4
+# ---- workloads ----------------------------------------------------------------------------------------------
+# algorithmic fp32 flop per sample-timestep and per sample (terminal + softmax)
+WORKLOADS = {
+    "c4": dict(
+        cfg=dict(model="racing", horizon=80, num_samples=65536, sigmas=[0.5, 0.1], lambda_=1.0, use_sg_filter=True,
+                 sg_window_size=5, sg_poly_order=3, exploration=0.0, seed=42),
+        ds=4, du=2, flop_step=97, flop_sample=61, map_bytes=2 * 800 * 25 * 4, refpath=True,
+        metric="MPPI solves/sec (control Hz) at K=65536,T=80 racing",
+        workload="racing kinematic-bicycle MPPI solve, K=65536 T=80 ds=4 du=2, SG filter on, lambda=1.0 "
+                 "(BASELINE.json configs[3])",
+        kernel="solve_kernel<Racing,false,kFused>"),
+    "c5": dict(
+        cfg=dict(model="cartpole", horizon=50, num_samples=1048576, u_min=[-3.0], u_max=[3.0], sigmas=[1.0],
+                 lambda_=0.001, exploration=0.0, seed=42),
+        ds=4, du=1, flop_step=52, flop_sample=20, map_bytes=0, refpath=False, state0=[0.0, 0.0, 0.05, 0.0],
+        metric="MPPI solves/sec (control Hz) at K=1048576,T=50 cartpole",
+        workload="cartpole MPPI solve, K=1048576 T=50 ds=4 du=1, lambda=0.001, samples sharded over the ranks "
+                 "(BASELINE.json configs[4])",
+        kernel="solve_kernel<Cartpole,false,kFused>"),
+}
+THREADS_CACHE = "/tmp/mppi_bench_cpu_threads.json"
+# the headline workload's constants under their round-1 names (tools/, tests/)
+CFG = WORKLOADS["c4"]["cfg"]
+K_SAMPLES, HORIZON = CFG["num_samples"], CFG["horizon"]
+
+
+def wl_numbers(wl):
+    cfg = wl["cfg"]
+    K, T, ds, du = cfg["num_samples"], cfg["horizon"], wl["ds"], wl["du"]
+    flops = K * T * wl["flop_step"] + K * wl["flop_sample"]
+    bytes_ = 4 * K + 4 * T * du * 2 + (16 * (T + 1) if wl["refpath"] else 0) + 4 * (T + 1) * ds + wl["map_bytes"]
+    h2d = 4 * ds + (16 * (T + 1) if wl["refpath"] else 0)
+    d2h = 4 * T * du + 4 * (T + 1) * ds
+    return K, T, ds, du, flops, bytes_, h2d, d2h
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the solve kernel from the committed ncu capture (null if absent)."""
+    return ncu_capture().get("dram_bytes_per_launch")
 
 
 def load_racing_fixture():
@@ -62,19 +93,29 @@ def load_racing_fixture():
                 Q=[float(q) for q in z["Q"]])
 
 
-def make_engine(env, device, **extra):
-    """(model descriptor, MPPI) for the bench workload through the public Python API."""
+def make_engine(wl, device, **extra):
+    """(model descriptor, MPPI) for a bench workload through the public Python API."""
     import mppi_playground_b200 as eng
 
-    q = env["Q"]
-    model = eng.RacingModel(env["obstacle"], env["lane"], cell_size=env["cell"], origin=env["origin"],
-                            u_min=env["u_min"], u_max=env["u_max"], wheelbase=env["wheelbase"], v_max=env["v_max"],
-                            lim=env["lim"], Qc=q[0], Ql=q[1], Qv=q[2], Qo=q[3], Qin=q[4], Qdin=q[5])
-    kw = {k: v for k, v in CFG.items() if k not in ("model", "sigmas")}
-    solver = eng.MPPI(dim_state=4, dim_control=2, dynamics=model.dynamics, cost_func=model.cost_func,
-                      u_min=model.u_min.clone(), u_max=model.u_max.clone(), sigmas=torch.tensor(CFG["sigmas"]),
-                      device=device, **kw, **extra)
+    cfg = wl["cfg"]
+    kw = {k: v for k, v in cfg.items() if k not in ("model", "sigmas", "u_min", "u_max")}
+    if cfg["model"] == "racing":
+        env = load_racing_fixture()
+        q = env["Q"]
+        model = eng.RacingModel(env["obstacle"], env["lane"], cell_size=env["cell"], origin=env["origin"],
+                                u_min=env["u_min"], u_max=env["u_max"], wheelbase=env["wheelbase"],
+                                v_max=env["v_max"], lim=env["lim"], Qc=q[0], Ql=q[1], Qv=q[2], Qo=q[3], Qin=q[4],
+                                Qdin=q[5])
+        u_min, u_max = model.u_min.clone(), model.u_max.clone()
+    else:
+        model = eng.CartpoleModel()
+        u_min, u_max = torch.tensor(cfg["u_min"]), torch.tensor(cfg["u_max"])
+    solver = eng.MPPI(dim_state=wl["ds"], dim_control=wl["du"], dynamics=model.dynamics, cost_func=model.cost_func,
+                      u_min=u_min, u_max=u_max, sigmas=torch.tensor(cfg["sigmas"]), device=device, **kw, **extra)
     return model, solver
+
+
+_, _, _, _, FLOPS_PER_SOLVE, BYTES_PER_SOLVE, H2D_BYTES, D2H_BYTES = wl_numbers(WORKLOADS["c4"])
 
 
 def dist_env():
@@ -90,11 +131,6 @@ def ncu_capture():
         return {}
 
 
-def ncu_traffic():
-    """DRAM bytes per launch of the solve kernel from the committed ncu capture (null if absent)."""
-    return ncu_capture().get("dram_bytes_per_launch")
-
-
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -104,7 +140,7 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons while the GPU is under load (spin-up + warm-up + timed region)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -113,12 +149,11 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.rows, self.proc = index, [], None
-        self.t_mark = None
 
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
@@ -130,33 +165,51 @@ class ClockSampler(threading.Thread):
             self.proc.terminate()
 
     def summary(self, t0, t1):
-        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows]
+        inside = [r for t, r in self.rows if t0 <= t <= t1]
+        rows = inside or [r for _, r in self.rows]
         sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(rows)}
+                "reasons": reasons, "samples": len(inside),
+                "window": "spin-up + warm-up + timed region + end-to-end loop (GPU under load throughout)"}
 
 
-def closed_loop_inputs(n_steps: int, device):
-    """Run the engine's own closed loop once (untimed) and keep every step's
-    state [4] and reference path [T+1,4] on the device."""
+def closed_loop_inputs(wl, n_steps: int, device):
+    """Run the engine's own closed loop once (untimed) and keep every step's state [ds] (and reference path
+    [T+1,4]) for replay."""
     import mppi_playground_b200 as eng
 
-    env = load_racing_fixture()
-    model, solver = make_engine(env, device)
-    states = torch.empty(n_steps, 4)
-    refs = torch.empty(n_steps, HORIZON + 1, 4)
-    state, cind = env["start_state"].clone(), 0
+    cfg = wl["cfg"]
+    T, ds = cfg["horizon"], wl["ds"]
+    model, solver = make_engine(wl, device)
+    states = torch.empty(n_steps, ds)
+    refs = torch.zeros(n_steps, T + 1, 4)
+    if cfg["model"] == "racing":
+        env = load_racing_fixture()
+        state, cind = env["start_state"].clone(), 0
+    else:
+        state = torch.tensor(wl["state0"])
     for s in range(n_steps):
-        ref, cind = eng.racing_reference_path(state, env["center_path"], cind, HORIZON, v_max=env["v_max"])
-        model.reference_path_tensor = ref
-        states[s], refs[s] = state, ref
+        if cfg["model"] == "racing":
+            ref, cind = eng.racing_reference_path(state, env["center_path"], cind, T, v_max=env["v_max"])
+            model.reference_path_tensor = ref
+            refs[s] = ref
+        states[s] = state
         _, seq = solver.forward(state)
         state = seq[0, 1].cpu()
     del solver
     return states, refs
+
+
+def fp32_peak(device_index: int):
+    """Measured fp32 pipe peaks through the C ABI (csrc/mppi_microbench.cu)."""
+    from mppi_playground_b200 import _capi
+
+    rep = _capi.MppiFp32Report()
+    _capi.check(_capi.load().mppi_fp32_microbench(device_index, C.byref(rep)))
+    return {n: getattr(rep, n) for n, _ in rep._fields_ if n != "reserved"}
 
 
 def run_b200(args, rank, local_rank, world):
@@ -164,6 +217,9 @@ def run_b200(args, rank, local_rank, world):
 
     from mppi_playground_b200 import _capi
 
+    wl = WORKLOADS[args.config]
+    K, T, ds, du, FLOPS, BYTES, H2D, D2H = wl_numbers(wl)
+    use_ref = wl["refpath"]
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     pg = None
@@ -171,23 +227,25 @@ def run_b200(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=device)
         pg = dist.group.WORLD
     n_total = args.warmup + args.steps
-    # distinct inputs per step would be 5000 closed-loop python iterations; cycle through a recorded loop instead
-    n_rec = min(n_total, 256)
-    states_h, refs_h = closed_loop_inputs(n_rec, device) if rank == 0 else (torch.empty(n_rec, 4),
-                                                                           torch.empty(n_rec, HORIZON + 1, 4))
+    # distinct inputs per step would be thousands of closed-loop python iterations; cycle through a recorded loop
+    n_rec = min(n_total, 256 if args.config == "c4" else 32)
+    if rank == 0:
+        states_h, refs_h = closed_loop_inputs(wl, n_rec, device)
+    else:
+        states_h, refs_h = torch.empty(n_rec, ds), torch.empty(n_rec, T + 1, 4)
     states_d, refs_d = states_h.to(device), refs_h.to(device)
     if world > 1:
         dist.broadcast(states_d, 0)
         dist.broadcast(refs_d, 0)
         states_h, refs_h = states_d.cpu(), refs_d.cpu()
 
-    env = load_racing_fixture()
-    model, solver = make_engine(env, device, process_group=pg) if world > 1 else make_engine(env, device)
-    model.reference_path_tensor = refs_d[0]
+    model, solver = make_engine(wl, device, process_group=pg) if world > 1 else make_engine(wl, device)
+    if use_ref:
+        model.reference_path_tensor = refs_d[0]
     lib, h = solver._lib, solver._h
     solver._bind_maps(required=True)
-    action = torch.empty(HORIZON, 2, device=device)
-    seq = torch.empty(HORIZON + 1, 4, device=device)
+    action = torch.empty(T, du, device=device)
+    seq = torch.empty(T + 1, ds, device=device)
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
     stream = torch.cuda.current_stream(device)
     sp = stream.cuda_stream
@@ -197,10 +255,11 @@ def run_b200(args, rank, local_rank, world):
     def solve(i):
         j = i % n_rec
         if fused:
-            _capi.check(lib.mppi_solve(h, states_d[j].data_ptr(), refs_d[j].data_ptr(), None, action.data_ptr(),
-                                       seq.data_ptr(), sp))
+            _capi.check(lib.mppi_solve(h, states_d[j].data_ptr(), refs_d[j].data_ptr() if use_ref else None, None,
+                                       action.data_ptr(), seq.data_ptr(), sp))
         else:
-            model.reference_path_tensor = refs_d[j]
+            if use_ref:
+                model.reference_path_tensor = refs_d[j]
             solver.forward(states_d[j])
 
     def barrier():
@@ -208,24 +267,46 @@ def run_b200(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize(device)
 
+    def check_exchange(where):
+        """A timed-out peer exchange leaves NaN outputs and a sticky flag: never report numbers from it."""
+        if world > 1 and fused:
+            flag = C.c_int32()
+            _capi.check(lib.mppi_p2p_status(h, C.byref(flag)))
+            if flag.value:
+                raise SystemExit(f"bench: fused shard exchange timed out on rank {rank} ({where}); no number reported")
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for i in range(args.warmup):
+    # ---- spin-up (untimed, part of the warm-up): at least W solves and at least ~0.4 s of load, so that the
+    #      clocks are up and the nvidia-smi sampler has rows from a loaded GPU even at --steps 20
+    barrier()
+    t_load0 = time.perf_counter()
+    n_spin = torch.tensor([0], device=device)
+    i = 0
+    while True:
         solve(i)
         flush.zero_()
+        i += 1
+        if i >= args.warmup and i % 16 == 0:
+            torch.cuda.synchronize(device)
+            n_spin[0] = 1 if time.perf_counter() - t_load0 > 0.4 else 0
+            if world > 1:
+                dist.broadcast(n_spin, 0)
+            if int(n_spin.item()):
+                break
+    n_warm_run = i
+    check_exchange("warm-up")
     # ---- timed region: K solves, L2 flushed between them, each bracketed by CUDA events on the launch stream
     solver.kernel_timing(True)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
-    t0 = time.perf_counter()
     for i in range(args.steps):
         ev[i][0].record(stream)
         solve(args.warmup + i)
         ev[i][1].record(stream)
         flush.zero_()
     barrier()
-    t1 = time.perf_counter()
     per_step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = torch.tensor([sum(per_step_ms)], device=device, dtype=torch.float64)
     kern_ms, kern_n = solver.kernel_time_ms()
@@ -234,6 +315,7 @@ def run_b200(args, rank, local_rank, world):
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     ms_per_step = total_ms.item() / args.steps
+    check_exchange("timed region")
     # back-to-back (no flush, one bracket) for context
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -247,29 +329,35 @@ def run_b200(args, rank, local_rank, world):
     # ---- end to end through the C ABI with HOST buffers (H2D + solve + D2H + sync every step)
     e2e = None
     if fused:
-        a_h = np.empty((HORIZON, 2), np.float32)
-        s_h = np.empty((HORIZON + 1, 4), np.float32)
+        a_h = np.empty((T, du), np.float32)
+        s_h = np.empty((T + 1, ds), np.float32)
         st_np, rf_np = states_h.numpy(), refs_h.numpy()
         n_e2e = min(args.steps, 2000)
-        for i in range(min(args.warmup, 20)):
-            _capi.check(lib.mppi_solve_host(h, st_np[i % n_rec].ctypes.data, rf_np[i % n_rec].ctypes.data,
+
+        def solve_host(j):
+            _capi.check(lib.mppi_solve_host(h, st_np[j].ctypes.data, rf_np[j].ctypes.data if use_ref else None,
                                             a_h.ctypes.data, s_h.ctypes.data))
+
+        for i in range(min(args.warmup, 20)):
+            solve_host(i % n_rec)
         torch.cuda.synchronize(device)
         spent = 0.0
         for i in range(n_e2e):
             flush.zero_()
             torch.cuda.synchronize(device)
+            if world > 1:
+                dist.barrier()
             j = (args.warmup + i) % n_rec
             c0 = time.perf_counter()
-            _capi.check(lib.mppi_solve_host(h, st_np[j].ctypes.data, rf_np[j].ctypes.data, a_h.ctypes.data,
-                                            s_h.ctypes.data))
+            solve_host(j)
             spent += time.perf_counter() - c0
         if world > 1:
             t_max = torch.tensor([spent], device=device, dtype=torch.float64)
             dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
             spent = t_max.item()
-        e2e = {"value": n_e2e / spent, "unit": "solves/s", "h2d_bytes_per_step": H2D_BYTES,
-               "d2h_bytes_per_step": D2H_BYTES, "steps": n_e2e,
+        check_exchange("end-to-end loop")
+        e2e = {"value": n_e2e / spent, "unit": "solves/s", "h2d_bytes_per_step": H2D, "d2h_bytes_per_step": D2H,
+               "steps": n_e2e,
                "api": "mppi_solve_host (C ABI, host buffers): state + reference path travel host->device inside the "
                       "kernel parameter block, the finishing block stores action_seq / state_seq into mapped pinned "
                       "host memory, stream sync, copy to the caller's buffers - every step"}
@@ -280,62 +368,77 @@ def run_b200(args, rank, local_rank, world):
             j = (args.warmup + i) % n_rec
             barrier()
             c0 = time.perf_counter()
-            model.reference_path_tensor = refs_h[j]  # host tensors: forward() uploads them
+            if use_ref:
+                model.reference_path_tensor = refs_h[j]  # host tensors: forward() uploads them
             a, sq = solver.forward(states_h[j])
             a_host, s_host = a.cpu(), sq.cpu()
             spent += time.perf_counter() - c0
         dist.all_reduce(spent, op=dist.ReduceOp.MAX)
-        e2e = {"value": n_e2e / spent.item(), "unit": "solves/s", "h2d_bytes_per_step": H2D_BYTES,
-               "d2h_bytes_per_step": D2H_BYTES, "steps": n_e2e,
+        e2e = {"value": n_e2e / spent.item(), "unit": "solves/s", "h2d_bytes_per_step": H2D,
+               "d2h_bytes_per_step": D2H, "steps": n_e2e,
                "api": "MPPI.forward with host tensors in, .cpu() out (sharded solve, NCCL all-gather of partials)"}
+    t_load1 = time.perf_counter()
 
     clocks = None
     if rank == 0:
         sampler.stop()
-        clocks = sampler.summary(t0, t1)
+        clocks = sampler.summary(t_load0, t_load1)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = time_oracle(n_timed=6, n_warm=1, states=states_h, refs=refs_h, k_samples=K_SAMPLES)
+        cpu_baseline = time_oracle(wl, n_timed=6 if args.config == "c4" else 2, n_warm=1, states=states_h,
+                                   refs=refs_h)
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
         info = solver.launch_info()
         sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
-        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12  # TFLOP/s, FMA counted as 2
+        fp32_derived = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12  # TFLOP/s, FMA counted as 2
+        try:
+            micro = fp32_peak(local_rank)
+        except Exception as e:  # the roofline then falls back to the derived figure, and says so
+            micro = {"error": str(e)}
+        fp32_measured = micro.get("ffma_tflops")
         kern_s = kern_ms / 1e3
         share = world  # each rank runs 1/world of the samples
-        ach = FLOPS_PER_SOLVE / share / kern_s / 1e12 if kern_s > 0 else None
-        hbm_ach = BYTES_PER_SOLVE / kern_s / 1e9 if kern_s > 0 else None
+        ach = FLOPS / share / kern_s / 1e12 if kern_s > 0 else None
+        hbm_ach = BYTES / kern_s / 1e9 if kern_s > 0 else None
+        peak = fp32_measured or fp32_derived
+        cap = ncu_capture() if (world == 1 and args.config == "c4") else {}
         line = {
-            "metric": "MPPI solves/sec (control Hz) at K=65536,T=80 racing",
+            "metric": wl["metric"],
             "value": 1e3 / ms_per_step, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "racing kinematic-bicycle MPPI solve, K=65536 T=80 ds=4 du=2, SG filter on, "
-                                   "lambda=1.0 (BASELINE.json configs[3])",
-                       "inputs": f"closed loop of {n_rec} recorded (state, reference path) pairs, device resident; "
-                                 "800x800 obstacle + lane occupancy grids, circuit centre line from tests/golden",
-                       "l2": "flushed between timed steps (192 MiB memset outside the per-step CUDA events)",
-                       "ms_per_step_back_to_back_no_flush": b2b_ms,
-                       "parallelism": (f"K sharded over {world} GPUs, one fused kernel per GPU, shard partials exchanged by "
-                                       "peer stores over NVLink inside the kernel" if fused else
-                                       f"K sharded over {world} GPUs, NCCL all-gather of the partials + finish kernel")
-                       if world > 1 else "single GPU, one fused kernel",
-                       "launch": info},
+            "config": {"workload": wl["workload"]},
+            "details": {"inputs": f"closed loop of {n_rec} recorded states"
+                                  + (" + reference paths" if use_ref else "") + ", device resident",
+                        "l2": "flushed between timed steps (192 MiB memset outside the per-step CUDA events)",
+                        "warmup_solves_run": n_warm_run,
+                        "ms_per_step_back_to_back_no_flush": b2b_ms,
+                        "parallelism": (f"K sharded over {world} GPUs, one fused kernel per GPU, shard partials "
+                                        "exchanged by peer stores over NVLink inside the kernel" if fused else
+                                        f"K sharded over {world} GPUs, NCCL all-gather of the partials + finish "
+                                        "kernel") if world > 1 else "single GPU, one fused kernel",
+                        "launch": info},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": launches,
-            "roofline": {"bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": (ach / fp32_peak) if ach else None, "traffic": ncu_traffic() if world == 1 else None,
-                         "kernel": "solve_kernel<Racing,false,kFused>", "kernel_ms": kern_ms, "kernel_launches": kern_n,
-                         "algorithmic_flops_per_launch": FLOPS_PER_SOLVE / share,
-                         "ncu_pipes": ncu_capture().get("pipes") if world == 1 else None,
-                         "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz ({peak_src} MEASURED_PEAKS.json has no "
-                                        "fp32 figure; the path is fp32-issue/latency bound, not HBM or tensor)",
+            "roofline": {"bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                         "frac": (ach / peak) if ach else None, "traffic": cap.get("dram_bytes_per_launch"),
+                         "traffic_source": "committed ncu --set full capture (profiles/ncu_traffic.json), not this run"
+                         if cap else None,
+                         "kernel": wl["kernel"], "kernel_ms": kern_ms, "kernel_launches": kern_n,
+                         "algorithmic_flops_per_launch": FLOPS / share,
+                         "ncu_pipes": cap.get("pipes"),
+                         "peak_source": ("measured in this run: full-chip 3-register FFMA throughput "
+                                         "(mppi_fp32_microbench, csrc/mppi_microbench.cu)" if fp32_measured else
+                                         "derived 148 SM x 128 lanes x 2 x sm_max_mhz (microbenchmark failed)"),
+                         "peak_derived": fp32_derived, "frac_of_derived": (ach / fp32_derived) if ach else None,
+                         "fp32_microbench": micro,
                          "hbm": {"achieved": hbm_ach, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                                  "frac": (hbm_ach / peaks["hbm_gbs"]) if hbm_ach and peaks.get("hbm_gbs") else None,
-                                 "algorithmic_bytes_per_launch": BYTES_PER_SOLVE, "peak_source": peak_src}},
+                                 "algorithmic_bytes_per_launch": BYTES, "peak_source": peak_src}},
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))
@@ -343,91 +446,112 @@ def run_b200(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-def best_thread_count(states, refs):
-    """The reference's CPU path is thousands of small ATen ops: on a many-core host all cores is
-    NOT the fastest setting. Probe one full-size solve per candidate thread count and keep the best,
-    so the baseline is the reference at its best on this box (all probes are reported)."""
+# ---- the reference's CPU path (oracle port) --------------------------------------------------------------------
+def pick_threads(wl, states, refs):
+    """Thread count of the CPU arm. The reference's CPU path is thousands of small ATen ops: on a many-core
+    host all cores is NOT the fastest setting (128 threads ran minutes per solve in round 1). Candidates are
+    bounded (<= 32), the probe is bounded (<= 30 s in total; a candidate slower than 5 s ends it), and the
+    choice is cached for this box so that `--impl reference` and the GPU arm's cpu_baseline use the same count."""
     from engine_util import build_oracle
 
     ncpu = os.cpu_count() or 1
-    cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
-    probes = {}
-    omodel, oracle = build_oracle(CFG, emulate_dead_work=True)
-    omodel.reference_path = refs[0]
+    key = f"{wl['cfg']['model']}-{wl['cfg']['num_samples']}-{ncpu}"
+    try:
+        with open(THREADS_CACHE) as f:
+            c = json.load(f)
+        if c.get("key") == key:
+            return int(c["threads"]), c.get("probes"), "cached"
+    except Exception:
+        pass
+    cands = sorted({c for c in (8, 16, 32) if c <= ncpu} or {ncpu})
+    probes, t_begin = {}, time.perf_counter()
+    omodel, oracle = build_oracle(wl["cfg"], emulate_dead_work=True)
+    if wl["refpath"]:
+        omodel.reference_path = refs[0]
     for c in cands:
         torch.set_num_threads(c)
         oracle.forward(states[0])  # warm (thread pool spin-up)
         c0 = time.perf_counter()
         oracle.forward(states[0])
         probes[c] = time.perf_counter() - c0
-        if probes[c] > 4 * min(probes.values()):
-            break  # more threads only get slower from here
-    return min(probes, key=probes.get), probes
+        if probes[c] > 5.0 and len(probes) > 1 or time.perf_counter() - t_begin > 30.0:
+            break
+    best = min(probes, key=probes.get)
+    probes_s = {str(k): round(v, 3) for k, v in probes.items()}
+    try:
+        with open(THREADS_CACHE, "w") as f:
+            json.dump({"key": key, "threads": best, "probes": probes_s}, f)
+    except Exception:
+        pass
+    return best, probes_s, "probed"
 
 
-def time_oracle(n_timed, n_warm, states, refs, k_samples, threads=None):
-    """The reference's algorithm on the host cores: oracle/mppi_oracle.py (a torch-CPU
-    restatement pinned bit-exact to the reference) on the same racing workload."""
+def time_oracle(wl, n_timed, n_warm, states, refs):
+    """The reference's algorithm on the host cores: oracle/mppi_oracle.py (a torch-CPU restatement pinned
+    bit-exact to the reference) on the same workload, full K per solve."""
     from engine_util import build_oracle
 
-    probes = None
-    if threads is None:
-        threads, probes = best_thread_count(states, refs)
+    threads, probes, how = pick_threads(wl, states, refs)
     torch.set_num_threads(threads)
-    cfg = dict(CFG, num_samples=k_samples)
+    cfg = wl["cfg"]
     omodel, oracle = build_oracle(cfg, emulate_dead_work=True)
     times = []
     for i in range(n_warm + n_timed):
-        omodel.reference_path = refs[i % len(refs)]
+        if wl["refpath"]:
+            omodel.reference_path = refs[i % len(refs)]
         c0 = time.perf_counter()
         oracle.forward(states[i % len(states)])
         dt = time.perf_counter() - c0
         if i >= n_warm:
             times.append(dt)
     med = statistics.median(times)
-    out = {"value": (k_samples / K_SAMPLES) / med, "unit": "solves/s", "cores": threads, "kind": "port",
-           "sample": f"{n_timed} solves (median) of {k_samples}/{K_SAMPLES} samples x T={HORIZON}, after {n_warm} "
-                     f"warm-up, torch CPU fp32 with {threads} threads of {os.cpu_count()} host cpus",
-           "seconds_per_sample_solve": med}
-    if probes:
-        out["thread_probe_seconds_per_solve"] = {str(k): round(v, 3) for k, v in probes.items()}
-    return out
+    return {"value": 1.0 / med, "unit": "solves/s", "cores": threads, "kind": "port",
+            "sample": f"{n_timed} full solves (median) of K={cfg['num_samples']} x T={cfg['horizon']}, after "
+                      f"{n_warm} warm-up, torch CPU fp32 with {threads} threads of {os.cpu_count()} host cpus "
+                      f"(thread count {how}, candidates <= 32)",
+            "seconds_per_solve": med, "thread_probe_seconds_per_solve": probes}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU algorithm (oracle port; the reference is
-    pure Python/torch and does not exist on the GPU box) on the host cores."""
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference is pure Python/torch and
+    does not exist on the GPU box) on the host cores. Same config / metric / warm-up as the GPU arm."""
     if rank != 0:
         return
     from oracle import fixtures as fx
     from oracle import mppi_oracle as mo
 
-    env = fx.load_env_racing()
+    wl = WORKLOADS[args.config]
+    cfg = wl["cfg"]
+    T = cfg["horizon"]
     n_rec = 8
-    states, refs = torch.empty(n_rec, 4), torch.empty(n_rec, HORIZON + 1, 4)
-    state, cind = env.start_state.clone(), 0
-    for s in range(n_rec):  # inputs only; advance along the centre line
-        ref, cind = mo.racing_reference_path(state, env.center_path, cind, HORIZON, v_max=env.v_max)
-        states[s], refs[s] = state, ref
-        state = torch.tensor([ref[0, 0], ref[0, 1], ref[0, 2], min(8.0, 1.0 + s)])
-    # Sub-sampling K would flatter the GPU (the CPU path's per-op overhead makes small K slower per
-    # sample), so every timed step is a FULL K=65536 solve and the bound is on how many are run:
-    # as many of the requested steps as fit in ~150 s of CPU time, at least 3.
-    threads, probes = best_thread_count(states, refs)
-    n_timed = int(max(3, min(args.steps, 150.0 // max(probes[threads], 1e-3))))
-    n_warm = min(args.warmup, 2)
-    res = time_oracle(n_timed, n_warm, states, refs, K_SAMPLES, threads=threads)
-    res["thread_probe_seconds_per_solve"] = {str(k): round(v, 3) for k, v in probes.items()}
+    states, refs = torch.empty(n_rec, wl["ds"]), torch.zeros(n_rec, T + 1, 4)
+    if cfg["model"] == "racing":
+        env = fx.load_env_racing()
+        state, cind = env.start_state.clone(), 0
+        for s in range(n_rec):  # inputs only; advance along the centre line
+            ref, cind = mo.racing_reference_path(state, env.center_path, cind, T, v_max=env.v_max)
+            states[s], refs[s] = state, ref
+            state = torch.tensor([ref[0, 0], ref[0, 1], ref[0, 2], min(8.0, 1.0 + s)])
+    else:
+        for s in range(n_rec):
+            states[s] = torch.tensor(wl["state0"]) * (1.0 + 0.1 * s)
+    # Sub-sampling K would flatter the GPU (the CPU path's per-op overhead makes small K slower per sample), so
+    # every timed step is a FULL-K solve and the bound is on how many are run: as many of the requested steps
+    # as fit in ~120 s of CPU time, at least 3.
+    threads, probes, how = pick_threads(wl, states, refs)
+    per = probes.get(str(threads), 1.0) if probes else 1.0
+    n_timed = int(max(3, min(args.steps, 120.0 // max(per, 1e-3))))
+    n_warm = int(max(1, min(args.warmup, 30.0 // max(per, 1e-3))))
+    res = time_oracle(wl, n_timed, n_warm, states, refs)
     res["sample"] += f"; {n_timed} of the requested {args.steps} steps were run to bound the CPU time"
     value = res["value"]
-    line = {"impl": "reference", "metric": "MPPI solves/sec (control Hz) at K=65536,T=80 racing", "value": value,
+    line = {"impl": "reference", "metric": wl["metric"], "value": value,
             "unit": "solves/s", "n_gpus": world, "steps": n_timed, "warmup": n_warm,
             "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "racing kinematic-bicycle MPPI solve, K=65536 T=80 ds=4 du=2, SG filter on, "
-                                   "lambda=1.0 (BASELINE.json configs[3])",
-                       "implementation": "oracle/mppi_oracle.py: op-for-op torch-CPU restatement of "
-                                         "pi_mpc.MPPI.forward, bit-exact to the reference on tests/golden"},
+            "config": {"workload": wl["workload"]},
+            "details": {"implementation": "oracle/mppi_oracle.py: op-for-op torch-CPU restatement of "
+                                          "pi_mpc.MPPI.forward, bit-exact to the reference on tests/golden"},
             "cpu_baseline": {k2: res[k2] for k2 in ("value", "unit", "cores", "kind", "sample",
                                                       "thread_probe_seconds_per_solve")},
             "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -441,6 +565,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -241,6 +241,20 @@ int mppi_refpath_index(MppiRefPath* r, int32_t set_value, int32_t* current, void
 int mppi_kernel_timing(MppiHandle* h, int32_t enable);
 int mppi_kernel_time_ms(MppiHandle* h, double* mean_ms, int32_t* launches);
 
+/* Measured fp32 denominators of the roofline (csrc/mppi_microbench.cu): full-chip throughput of FFMA
+ * (3-register form, 8 independent chains per thread, 2 x 1024 threads per SM), of the packed FFMA2, of the
+ * never-contracted FMUL+FADD pair the reference's op order leaves (-fmad=false) and of its packed form, in
+ * TFLOP/s (an FMA counts 2); dependent-issue latencies in SM cycles; the SM clock during the run
+ * (clock64 / globaltimer). Synchronous, a few ms. MEASURED_PEAKS.json has no fp32 figure, hence this. */
+typedef struct MppiFp32Report {
+  double ffma_tflops, ffma2_tflops, fmul_fadd_tflops, fmul2_fadd2_tflops;
+  double lat_ffma, lat_ffma2, lat_fadd2, lat_fmnmx, lat_fadd, lat_fmul2;
+  double sm_clock_mhz;
+  int32_t sms;
+  int32_t reserved;
+} MppiFp32Report;
+int mppi_fp32_microbench(int32_t device, MppiFp32Report* out);
+
 /* Philox4x32-10 known-answer hook for tests: out[4] = block(counter, key). Host code. */
 void mppi_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);
 /* Index the NEXT solve will key its sampler with (== number of solves so far). */

@@ -39,6 +39,14 @@ class MppiConfig(C.Structure):
     ]
 
 
+class MppiFp32Report(C.Structure):
+    """struct MppiFp32Report of include/mppi_b200.h (csrc/mppi_microbench.cu)."""
+
+    _fields_ = [(n, C.c_double) for n in ("ffma_tflops", "ffma2_tflops", "fmul_fadd_tflops", "fmul2_fadd2_tflops",
+                                          "lat_ffma", "lat_ffma2", "lat_fadd2", "lat_fmnmx", "lat_fadd", "lat_fmul2",
+                                          "sm_clock_mhz")] + [("sms", C.c_int32), ("reserved", C.c_int32)]
+
+
 # name -> (restype, argtypes); every symbol include/mppi_b200.h declares
 _P = C.c_void_p
 _FP = C.c_void_p  # float* passed as raw address
@@ -83,6 +91,7 @@ PROTOTYPES = {
     "mppi_refpath_index": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), _P]),
     "mppi_kernel_timing": (C.c_int, [_P, C.c_int32]),
     "mppi_kernel_time_ms": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
+    "mppi_fp32_microbench": (C.c_int, [C.c_int32, C.POINTER(MppiFp32Report)]),
     "mppi_philox4x32_10": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "mppi_solve_index": (C.c_uint64, [_P]),
     "mppi_sample_noise": (C.c_int, [_P, C.c_uint64, _FP, _P]),

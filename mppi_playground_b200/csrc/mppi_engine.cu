@@ -44,6 +44,26 @@ int fail(int code, const char* fmt, ...) {
 constexpr int kNumSMs = 148;
 constexpr unsigned kMaxSmem = 227 * 1024;
 
+// Every entry point runs on the handle's device and leaves the caller's current device as it found it
+// (torch reads cudaGetDevice: a solve or a destructor on cuda:1 must not move later `device="cuda"` work).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) err = cudaSetDevice(device);
+  }
+  ~DeviceGuard() {
+    int now = -1;
+    if (prev >= 0 && cudaGetDevice(&now) == cudaSuccess && now != prev) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define ON_DEVICE(dev)                                                                              \
+  DeviceGuard _guard(dev);                                                                          \
+  if (_guard.err != cudaSuccess) return fail(MPPI_ERR_CUDA, "cudaSetDevice(%d): %s", (dev), cudaGetErrorString(_guard.err))
+
 struct ModelInfo {
   int ds, du, maps, n_params;
   bool refpath;
@@ -115,8 +135,12 @@ struct MppiHandle {
   ModelInfo mi{};
   int device = 0;
   int E = 0, E_pad = 0, P = 0;
-  int block = 0, grid = 0;
-  unsigned smem = 0;
+  // launch geometry of the rollout kernel: [0] the in-kernel sampler (two samples per thread when the model's
+  // bounded loop applies), [1] injected noise (always one sample per thread)
+  struct Geometry {
+    int spt = 1, block = 0, grid = 0;
+    unsigned smem = 0, stage_bytes = 0;
+  } geo[2];
   SolveParams base{};  // everything that does not change between solves
   // device buffers
   float* d_prev_action = nullptr;
@@ -170,17 +194,21 @@ size_t pad16(size_t bytes) { return (bytes + 15) / 16 * 16; }
 // Launch geometry for the rollout kernel. The path is latency bound at the
 // sizes MPPI runs (K/32 warps spread over 592 schedulers), so the model is:
 // time ~ waves * w / ipc(w) with w = max warps on one scheduler.
-int pick_block(const MppiHandle* h, int n_maps, const unsigned* map_bytes, unsigned pa_bytes) {
-  const int K = h->cfg.num_samples;
+int pick_block(const MppiHandle* h, int n_maps, const unsigned* map_bytes, unsigned pa_bytes, int spt) {
+  const long long K = (h->cfg.num_samples + spt - 1) / spt;  // threads needed
   int best = 0;
   double best_t = 1e300;
-  const int cands[] = {512, 256, 128, 64};
-  for (int bs : cands) {
+  const int cands1[] = {512, 256, 128, 64}, cands2[] = {256, 128, 64, 0};  // paired kernel: <= 256 threads
+  const int* cands = spt == 2 ? cands2 : cands1;
+  for (int ci = 0; ci < 4; ++ci) {
+    const int bs = cands[ci];
+    if (bs == 0) continue;
     SmemLayout L = make_layout(n_maps, map_bytes, h->cfg.horizon, h->E_pad, pa_bytes, h->mi.refpath, bs / 32,
-                               h->mi.tail_per_step);
+                               h->mi.tail_per_step, spt, 0);
     if (L.total > kMaxSmem) continue;
-    long long blocks = ((long long)K + bs - 1) / bs;
-    int per_sm = std::min<long long>({2048 / bs, (long long)(kMaxSmem / L.total), 65536 / (128LL * bs)});
+    long long blocks = (K + bs - 1) / bs;
+    const long long regs = spt == 2 ? 200 : 128;
+    int per_sm = (int)std::min<long long>({2048 / bs, (long long)(kMaxSmem / L.total), 65536 / (regs * bs)});
     if (per_sm < 1) per_sm = 1;
     long long conc = (long long)kNumSMs * per_sm;
     long long waves = (blocks + conc - 1) / conc;
@@ -198,10 +226,18 @@ int pick_block(const MppiHandle* h, int n_maps, const unsigned* map_bytes, unsig
 
 template <class M>
 int launch_solve(MppiHandle* h, const SolveParams& p, int mode, bool inject, cudaStream_t st) {
+  const MppiHandle::Geometry& g = h->geo[inject ? 1 : 0];
   void (*k)(SolveParams) = nullptr;
-#define PICK(MODE)                                                     \
-  k = inject ? (void (*)(SolveParams))solve_kernel<M, true, MODE>      \
-             : (void (*)(SolveParams))solve_kernel<M, false, MODE>
+#define PICK(MODE)                                                                   \
+  do {                                                                               \
+    if (inject) {                                                                    \
+      k = (void (*)(SolveParams))solve_kernel<M, true, MODE, 1>;                     \
+    } else if (g.spt == 2) {                                                         \
+      if constexpr (M::kHasBounded) k = (void (*)(SolveParams))solve_kernel<M, false, MODE, 2>; \
+    } else {                                                                         \
+      k = (void (*)(SolveParams))solve_kernel<M, false, MODE, 1>;                    \
+    }                                                                                \
+  } while (0)
   if (mode == kFused)
     PICK(kFused);
   else if (mode == kCosts)
@@ -209,11 +245,12 @@ int launch_solve(MppiHandle* h, const SolveParams& p, int mode, bool inject, cud
   else
     PICK(kReduce);
 #undef PICK
+  if (!k) return fail(MPPI_ERR_STATE, "no kernel for this launch geometry");
   {  // opt in to the large dynamic shared memory once per kernel instantiation (and again if it grows)
     unsigned& have = h->smem_opt_in[(const void*)k];
-    if (have < h->smem) {
-      CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-      have = h->smem;
+    if (have < g.smem) {
+      CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+      have = g.smem;
     }
   }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -222,7 +259,7 @@ int launch_solve(MppiHandle* h, const SolveParams& p, int mode, bool inject, cud
     CUDA_TRY(cudaEventCreate(&e1));
     CUDA_TRY(cudaEventRecord(e0, st));
   }
-  k<<<h->grid, h->block, h->smem, st>>>(p);
+  k<<<g.grid, g.block, g.smem, st>>>(p);
   if (e0) {
     CUDA_TRY(cudaEventRecord(e1, st));
     h->events.emplace_back(e0, e1);
@@ -312,6 +349,7 @@ int make_params(MppiHandle* h, const float* d_state, const float* d_refpath, con
   p.refpath = d_refpath;
   p.ref_bulk_ok = d_refpath && (((uintptr_t)d_refpath & 15) == 0);
   p.noise = d_noise;
+  p.stage_bytes = h->geo[d_noise ? 1 : 0].stage_bytes;
   p.action_out = d_action;
   p.state_seq_out = d_state_seq;
   p.key.solve_lo = (uint32_t)h->solve_count;
@@ -420,13 +458,30 @@ void refresh_model_flags(MppiHandle* h) {
 
 void refresh_launch_geometry(MppiHandle* h) {
   unsigned mb[2] = {h->base.map_bytes[0], h->base.map_bytes[1]};
-  int bs = h->cfg.block_size > 0 ? h->cfg.block_size : pick_block(h, h->mi.maps, mb, h->base.prev_action_bytes);
-  if (bs <= 0) bs = 64;  // nothing fits (oversized grids): the shared-memory check below reports it
-  h->block = bs;
-  h->grid = (h->cfg.num_samples + bs - 1) / bs;
-  h->smem = make_layout(h->mi.maps, mb, h->cfg.horizon, h->E_pad, h->base.prev_action_bytes, h->mi.refpath, bs / 32,
-                        h->mi.tail_per_step)
-                .total;
+  const bool pair_model = h->cfg.model == MPPI_MODEL_RACING || h->cfg.model == MPPI_MODEL_NAVIGATION2D;
+  for (int v = 0; v < 2; ++v) {
+    MppiHandle::Geometry& g = h->geo[v];
+    // two samples per thread: the model's bounded loop is available (host-verified flags) and the noise
+    // comes from the in-kernel sampler; the kernel re-checks the solve's initial state
+    g.spt = (v == 0 && pair_model && (h->base.mp.flags & kFlagBounded)) ? 2 : 1;
+    int bs = h->cfg.block_size > 0 ? h->cfg.block_size : pick_block(h, h->mi.maps, mb, h->base.prev_action_bytes, g.spt);
+    if (bs <= 0) bs = 64;  // nothing fits (oversized grids): the shared-memory check below reports it
+    if (g.spt == 2 && bs > 256) bs = 256;
+    g.block = bs;
+    const long long per_block = (long long)bs * g.spt;
+    g.grid = (int)((h->cfg.num_samples + per_block - 1) / per_block);
+    // landing zone for the block partials in the last block: all of them if that fits beside the rest
+    const unsigned want = (unsigned)std::min<long long>((long long)g.grid * h->P * 4, (long long)kMaxSmem);
+    SmemLayout L = make_layout(h->mi.maps, mb, h->cfg.horizon, h->E_pad, h->base.prev_action_bytes, h->mi.refpath,
+                               bs / 32, h->mi.tail_per_step, g.spt, want);
+    g.stage_bytes = want;
+    if (L.total > kMaxSmem) {  // does not fit: combine straight from global memory
+      g.stage_bytes = 0;
+      L = make_layout(h->mi.maps, mb, h->cfg.horizon, h->E_pad, h->base.prev_action_bytes, h->mi.refpath, bs / 32,
+                      h->mi.tail_per_step, g.spt, 0);
+    }
+    g.smem = L.total;
+  }
 }
 
 }  // namespace
@@ -478,7 +533,7 @@ int mppi_create(const MppiConfig* cfg, MppiHandle** out) {
   if (prop.major != 10)
     return fail(MPPI_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device,
                 prop.major, prop.minor);
-  CUDA_TRY(cudaSetDevice(cfg->device));
+  ON_DEVICE(cfg->device);
 
   MppiHandle* h = new (std::nothrow) MppiHandle();
   if (!h) return fail(MPPI_ERR_INVALID, "out of host memory");
@@ -568,7 +623,9 @@ int mppi_create(const MppiConfig* cfg, MppiHandle** out) {
   b.E_pad = h->E_pad;
   b.P = h->P;
   refresh_launch_geometry(h);
-  if (h->smem > kMaxSmem) return cleanup(fail(MPPI_ERR_UNSUPPORTED, "shared memory budget exceeded (%u B)", h->smem));
+  if (std::max(h->geo[0].smem, h->geo[1].smem) > kMaxSmem)
+    return cleanup(fail(MPPI_ERR_UNSUPPORTED, "shared memory budget exceeded (%u B)",
+                        std::max(h->geo[0].smem, h->geo[1].smem)));
   // block partials: sized for the smallest block the engine may pick later (maps change smem)
   ALLOC(h->d_block_partials, (size_t)((K + 63) / 64) * h->P * 4);
   b.block_partials = h->d_block_partials;
@@ -579,7 +636,7 @@ int mppi_create(const MppiConfig* cfg, MppiHandle** out) {
 
 void mppi_destroy(MppiHandle* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   for (auto& ev : h->events) {
     cudaEventDestroy(ev.first);
     cudaEventDestroy(ev.second);
@@ -605,7 +662,7 @@ void mppi_destroy(MppiHandle* h) {
     if (h->peer_opened[r]) cudaIpcCloseMemHandle(h->peer_mailbox[r]);
   cudaFree(h->d_mailbox);
   cudaFree(h->d_gather_scratch);
-  cudaFree(h->d_error_flag);
+  if (h->d_error_flag) cudaFreeHost(h->d_error_flag);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -622,8 +679,10 @@ int mppi_reset(MppiHandle* h, void* stream) {
 int mppi_set_model_params(MppiHandle* h, const float* params, int32_t n) {
   if (!h || (!params && n > 0)) return fail(MPPI_ERR_INVALID, "null argument");
   if (n != h->mi.n_params) return fail(MPPI_ERR_INVALID, "model takes %d parameters, got %d", h->mi.n_params, n);
+  ON_DEVICE(h->device);
   for (int i = 0; i < n; ++i) h->base.mp.v[i] = params[i];
   refresh_model_flags(h);
+  refresh_launch_geometry(h);  // the flags decide between one and two samples per thread
   return MPPI_OK;
 }
 
@@ -632,7 +691,7 @@ int mppi_set_map(MppiHandle* h, int32_t slot, const float* grid, int32_t on_devi
   if (!h || !grid) return fail(MPPI_ERR_INVALID, "null argument");
   if (slot < 0 || slot >= h->mi.maps) return fail(MPPI_ERR_INVALID, "model has %d map slots, got slot %d", h->mi.maps, slot);
   if (W < 1 || H < 1 || !(cell > 0.0f)) return fail(MPPI_ERR_INVALID, "bad map geometry");
-  CUDA_TRY(cudaSetDevice(h->device));
+  ON_DEVICE(h->device);
   const int words = (H + 1 + 31) / 32;  // + the out-of-bounds border bit (see MapView)
   const size_t bytes = pad16((size_t)(W + 1) * words * 4);
   const float* d_grid = grid;
@@ -676,8 +735,9 @@ int mppi_set_map(MppiHandle* h, int32_t slot, const float* grid, int32_t on_devi
   h->map_set[slot] = true;
   refresh_model_flags(h);
   refresh_launch_geometry(h);
-  if (h->smem > kMaxSmem)
-    return fail(MPPI_ERR_UNSUPPORTED, "occupancy maps need %u B of shared memory (> %u)", h->smem, kMaxSmem);
+  if (std::max(h->geo[0].smem, h->geo[1].smem) > kMaxSmem)
+    return fail(MPPI_ERR_UNSUPPORTED, "occupancy maps need %u B of shared memory (> %u)",
+                std::max(h->geo[0].smem, h->geo[1].smem), kMaxSmem);
   return MPPI_OK;
 }
 
@@ -686,7 +746,7 @@ static int solve_impl(MppiHandle* h, const float* d_state, const float* d_refpat
   int rc = check_ready(h);
   if (rc) return rc;
   if (!d_action || !d_state_seq) return fail(MPPI_ERR_INVALID, "output pointer is null");
-  CUDA_TRY(cudaSetDevice(h->device));
+  ON_DEVICE(h->device);
   SolveParams p;
   const bool lam_search = h->cfg.lambda_mode == MPPI_LAMBDA_LBPS || h->cfg.lambda_mode == MPPI_LAMBDA_ESSPS;
   const bool fused_shards = h->p2p_world > 1 && !lam_search;
@@ -720,7 +780,7 @@ int mppi_solve_host(MppiHandle* h, const float* h_state, const float* h_refpath,
                     float* h_state_seq) {
   if (!h || !h_state || !h_action_seq || !h_state_seq) return fail(MPPI_ERR_INVALID, "null argument");
   if (h->mi.refpath && !h_refpath) return fail(MPPI_ERR_INVALID, "this model needs a reference path [T+1,4]");
-  CUDA_TRY(cudaSetDevice(h->device));
+  ON_DEVICE(h->device);
   const int T = h->cfg.horizon, DS = h->mi.ds;
   const size_t n_state = 8, n_ref = (size_t)(T + 1) * 4, n_act = (size_t)h->E_pad, n_seq = (size_t)(T + 1) * DS;
   float* hp = h->h_pinned;
@@ -760,7 +820,7 @@ int mppi_shard_rollout(MppiHandle* h, const float* d_state, const float* d_refpa
                        void* stream) {
   int rc = check_ready(h);
   if (rc) return rc;
-  CUDA_TRY(cudaSetDevice(h->device));
+  ON_DEVICE(h->device);
   SolveParams p;
   // outputs are written by mppi_shard_finish; n_shards = 2 only means "stop at the shard partial"
   rc = make_params(h, d_state, d_refpath, d_noise, nullptr, nullptr, 2, &p);
@@ -777,7 +837,7 @@ int mppi_shard_lambda(MppiHandle* h, const float* d_costs_all, void* stream) {
   if (!h || !d_costs_all) return fail(MPPI_ERR_INVALID, "null argument");
   if (!(h->cfg.lambda_mode == MPPI_LAMBDA_LBPS || h->cfg.lambda_mode == MPPI_LAMBDA_ESSPS))
     return fail(MPPI_ERR_STATE, "mppi_shard_lambda is for LBPS / ESSPS handles");
-  CUDA_TRY(cudaSetDevice(h->device));
+  ON_DEVICE(h->device);
   int rc = launch_search(h, d_costs_all, h->cfg.total_samples, (cudaStream_t)stream);
   if (rc) return rc;
   SolveParams p;
@@ -792,7 +852,7 @@ int mppi_shard_finish(MppiHandle* h, const float* d_partials, int32_t n_shards, 
                       float* d_action_seq, float* d_state_seq, void* stream) {
   if (!h || !d_partials || !d_state || !d_action_seq || !d_state_seq || n_shards < 1)
     return fail(MPPI_ERR_INVALID, "bad argument");
-  CUDA_TRY(cudaSetDevice(h->device));
+  ON_DEVICE(h->device);
   SolveParams p;
   int rc = make_params(h, d_state, h->mi.refpath ? d_state : nullptr, nullptr, d_action_seq, d_state_seq, n_shards, &p);
   if (rc) return rc;
@@ -805,15 +865,17 @@ int mppi_shard_finish(MppiHandle* h, const float* d_partials, int32_t n_shards, 
 
 int mppi_p2p_export(MppiHandle* h, uint8_t handle_out[64]) {
   if (!h || !handle_out) return fail(MPPI_ERR_INVALID, "null argument");
-  CUDA_TRY(cudaSetDevice(h->device));
+  ON_DEVICE(h->device);
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
   if (!h->d_mailbox) {
     const size_t bytes = mailbox_floats(h->P) * 4;
     CUDA_TRY(cudaMalloc((void**)&h->d_mailbox, bytes));
     CUDA_TRY(cudaMemset(h->d_mailbox, 0, bytes));
     CUDA_TRY(cudaMalloc((void**)&h->d_gather_scratch, (size_t)kMaxPeers * h->P * 4));
-    CUDA_TRY(cudaMalloc((void**)&h->d_error_flag, 16));
-    CUDA_TRY(cudaMemset(h->d_error_flag, 0, 16));
+    // the timeout flag lives in mapped pinned host memory: the finishing block stores the sequence number of
+    // the failed solve there and the host reads it without a copy or a synchronisation (mppi_p2p_status)
+    CUDA_TRY(cudaHostAlloc((void**)&h->d_error_flag, 16, cudaHostAllocMapped));
+    memset(h->d_error_flag, 0, 16);
     CUDA_TRY(cudaDeviceSynchronize());
   }
   cudaIpcMemHandle_t ipc;
@@ -827,7 +889,7 @@ int mppi_p2p_connect(MppiHandle* h, const uint8_t* handles, int32_t world, int32
   if (world < 2 || world > kMaxPeers || rank < 0 || rank >= world)
     return fail(MPPI_ERR_INVALID, "p2p world must be in [2, %d]", kMaxPeers);
   if (!h->d_mailbox) return fail(MPPI_ERR_STATE, "call mppi_p2p_export first");
-  CUDA_TRY(cudaSetDevice(h->device));
+  ON_DEVICE(h->device);
   for (int r = 0; r < world; ++r) {
     if (r == rank) {
       h->peer_mailbox[r] = h->d_mailbox;
@@ -866,7 +928,11 @@ int mppi_p2p_mailbox_ptr(MppiHandle* h, uint64_t* ptr) {
 int mppi_p2p_status(MppiHandle* h, int32_t* timed_out) {
   if (!h || !timed_out) return fail(MPPI_ERR_INVALID, "null argument");
   *timed_out = 0;
-  if (h->d_error_flag) CUDA_TRY(cudaMemcpy(timed_out, h->d_error_flag, 4, cudaMemcpyDeviceToHost));
+  if (h->d_error_flag) {  // mapped host memory, written by the kernel with a system-scope fence
+    volatile int* f = h->d_error_flag;
+    *timed_out = *f;  // sequence number (>= 1) of the solve whose exchange timed out, 0 if none
+    *f = 0;           // reported once
+  }
   return MPPI_OK;
 }
 
@@ -892,7 +958,7 @@ int mppi_prev_action_ptr(MppiHandle* h, const float** p) {
 int mppi_weights(MppiHandle* h, float* d_weights, void* stream) {
   if (!h || !d_weights) return fail(MPPI_ERR_INVALID, "null argument");
   if (!h->solved) return fail(MPPI_ERR_STATE, "no solve has run yet");
-  CUDA_TRY(cudaSetDevice(h->device));
+  ON_DEVICE(h->device);
   const int K = h->cfg.num_samples;
   weights_kernel<<<(K + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->d_costs, K, h->d_sc, d_weights);
   CUDA_TRY(cudaGetLastError());
@@ -904,7 +970,7 @@ int mppi_top_samples(MppiHandle* h, int32_t n, float* d_traj, float* d_w, void* 
   const int K = h->cfg.num_samples;
   if (n < 1 || n > K) return fail(MPPI_ERR_INVALID, "num_samples must be in [1, %d]", K);  // mppi.py:476
   if (!h->solved) return fail(MPPI_ERR_STATE, "no solve has run yet");
-  CUDA_TRY(cudaSetDevice(h->device));
+  ON_DEVICE(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   if (!h->d_idx_in) {
     CUDA_TRY(cudaMalloc((void**)&h->d_idx_in, (size_t)K * 4));
@@ -940,7 +1006,7 @@ int mppi_top_samples(MppiHandle* h, int32_t n, float* d_traj, float* d_w, void* 
 int mppi_rollout_actions(MppiHandle* h, const float* d_state, const float* d_actions, int32_t n, float* d_traj,
                          void* stream) {
   if (!h || !d_state || !d_actions || !d_traj || n < 1) return fail(MPPI_ERR_INVALID, "bad argument");
-  CUDA_TRY(cudaSetDevice(h->device));
+  ON_DEVICE(h->device);
   SolveParams p = h->base;
   p.state = d_state;
   cudaStream_t st = (cudaStream_t)stream;
@@ -958,7 +1024,7 @@ int mppi_rollout_actions(MppiHandle* h, const float* d_state, const float* d_act
 
 int mppi_get_lambda(MppiHandle* h, double* lambda_used, double* lambda_next, void* stream) {
   if (!h) return fail(MPPI_ERR_INVALID, "null handle");
-  CUDA_TRY(cudaSetDevice(h->device));
+  ON_DEVICE(h->device);
   DeviceScalars sc;
   CUDA_TRY(cudaMemcpyAsync(&sc, h->d_sc, sizeof sc, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
@@ -969,7 +1035,7 @@ int mppi_get_lambda(MppiHandle* h, double* lambda_used, double* lambda_next, voi
 
 int mppi_get_carry(MppiHandle* h, float* d_prev, float* d_hist, void* stream) {
   if (!h) return fail(MPPI_ERR_INVALID, "null handle");
-  CUDA_TRY(cudaSetDevice(h->device));
+  ON_DEVICE(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   if (d_prev) CUDA_TRY(cudaMemcpyAsync(d_prev, h->d_prev_action, (size_t)h->E * 4, cudaMemcpyDeviceToDevice, st));
   const size_t hb = (size_t)(h->cfg.horizon - 1) * h->mi.du * 4;
@@ -979,7 +1045,7 @@ int mppi_get_carry(MppiHandle* h, float* d_prev, float* d_hist, void* stream) {
 
 int mppi_set_carry(MppiHandle* h, const float* d_prev, const float* d_hist, void* stream) {
   if (!h) return fail(MPPI_ERR_INVALID, "null handle");
-  CUDA_TRY(cudaSetDevice(h->device));
+  ON_DEVICE(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   if (d_prev) CUDA_TRY(cudaMemcpyAsync(h->d_prev_action, d_prev, (size_t)h->E * 4, cudaMemcpyDeviceToDevice, st));
   const size_t hb = (size_t)(h->cfg.horizon - 1) * h->mi.du * 4;
@@ -991,9 +1057,9 @@ int32_t mppi_last_launch_count(const MppiHandle* h) { return h ? h->last_launche
 
 int mppi_launch_info(const MppiHandle* h, int32_t* grid, int32_t* block, int32_t* smem_bytes) {
   if (!h) return fail(MPPI_ERR_INVALID, "null handle");
-  if (grid) *grid = h->grid;
-  if (block) *block = h->block;
-  if (smem_bytes) *smem_bytes = (int32_t)h->smem;
+  if (grid) *grid = h->geo[0].grid;
+  if (block) *block = h->geo[0].block;
+  if (smem_bytes) *smem_bytes = (int32_t)h->geo[0].smem;
   return MPPI_OK;
 }
 
@@ -1007,7 +1073,7 @@ int mppi_map_info(const MppiHandle* h, int32_t slot, int32_t* fast_division, uin
 
 int mppi_block_trace(MppiHandle* h, int32_t enable, uint64_t* h_out, int32_t max_blocks) {
   if (!h) return fail(MPPI_ERR_INVALID, "null handle");
-  CUDA_TRY(cudaSetDevice(h->device));
+  ON_DEVICE(h->device);
   const size_t n = (size_t)((h->cfg.num_samples + 63) / 64) * 8;
   if (enable && !h->d_trace) {
     CUDA_TRY(cudaMalloc((void**)&h->d_trace, n * 8));
@@ -1015,7 +1081,7 @@ int mppi_block_trace(MppiHandle* h, int32_t enable, uint64_t* h_out, int32_t max
   }
   if (h_out && h->d_trace) {
     CUDA_TRY(cudaDeviceSynchronize());
-    size_t blocks = std::min<size_t>((size_t)max_blocks, (size_t)h->grid);
+    size_t blocks = std::min<size_t>((size_t)max_blocks, (size_t)h->geo[0].grid);
     CUDA_TRY(cudaMemcpy(h_out, h->d_trace, blocks * 8 * 8, cudaMemcpyDeviceToHost));
   }
   if (!enable && h->d_trace) {
@@ -1027,7 +1093,7 @@ int mppi_block_trace(MppiHandle* h, int32_t enable, uint64_t* h_out, int32_t max
 
 int mppi_selftest(int32_t device, uint64_t mismatches[4]) {
   if (!mismatches) return fail(MPPI_ERR_INVALID, "null argument");
-  CUDA_TRY(cudaSetDevice(device));
+  ON_DEVICE(device);
   unsigned long long* d = nullptr;
   CUDA_TRY(cudaMalloc((void**)&d, 32));
   CUDA_TRY(cudaMemset(d, 0, 32));
@@ -1052,7 +1118,7 @@ struct MppiRefPath {
 int mppi_refpath_create(int32_t device, const float* h_path, int32_t n, const int32_t* h_index_offsets, int32_t rows,
                         float v_max, MppiRefPath** out) {
   if (!h_path || !h_index_offsets || !out || n < 1 || rows < 1) return fail(MPPI_ERR_INVALID, "bad argument");
-  CUDA_TRY(cudaSetDevice(device));
+  ON_DEVICE(device);
   MppiRefPath* r = new (std::nothrow) MppiRefPath();
   if (!r) return fail(MPPI_ERR_INVALID, "out of host memory");
   r->device = device;
@@ -1078,7 +1144,7 @@ int mppi_refpath_create(int32_t device, const float* h_path, int32_t n, const in
 
 void mppi_refpath_destroy(MppiRefPath* r) {
   if (!r) return;
-  cudaSetDevice(r->device);
+  DeviceGuard guard(r->device);
   cudaFree(r->d_path);
   cudaFree(r->d_dind);
   cudaFree(r->d_cind);
@@ -1087,7 +1153,7 @@ void mppi_refpath_destroy(MppiRefPath* r) {
 
 int mppi_refpath_update(MppiRefPath* r, const float* d_state, float* d_refpath_out, void* stream) {
   if (!r || !d_state || !d_refpath_out) return fail(MPPI_ERR_INVALID, "null argument");
-  CUDA_TRY(cudaSetDevice(r->device));
+  ON_DEVICE(r->device);
   racing_refpath_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(r->d_path, r->n, d_state, r->d_dind, r->rows, r->v_max,
                                                                r->d_cind, d_refpath_out);
   CUDA_TRY(cudaGetLastError());
@@ -1096,7 +1162,7 @@ int mppi_refpath_update(MppiRefPath* r, const float* d_state, float* d_refpath_o
 
 int mppi_refpath_index(MppiRefPath* r, int32_t set_value, int32_t* current, void* stream) {
   if (!r) return fail(MPPI_ERR_INVALID, "null argument");
-  CUDA_TRY(cudaSetDevice(r->device));
+  ON_DEVICE(r->device);
   cudaStream_t st = (cudaStream_t)stream;
   if (set_value >= 0) CUDA_TRY(cudaMemcpyAsync(r->d_cind, &set_value, 4, cudaMemcpyHostToDevice, st));
   if (current) {
@@ -1137,7 +1203,7 @@ uint64_t mppi_solve_index(const MppiHandle* h) { return h ? h->solve_count : 0; 
 
 int mppi_sample_noise(MppiHandle* h, uint64_t solve_index, float* d_noise_out, void* stream) {
   if (!h || !d_noise_out) return fail(MPPI_ERR_INVALID, "null argument");
-  CUDA_TRY(cudaSetDevice(h->device));
+  ON_DEVICE(h->device);
   SolveParams p = h->base;
   p.key.solve_lo = (uint32_t)solve_index;
   p.key.solve_hi = (uint32_t)(solve_index >> 32);

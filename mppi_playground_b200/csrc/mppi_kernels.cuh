@@ -91,14 +91,16 @@ struct SolveParams {
   unsigned p2p_seq;  // sequence number of this solve (>= 1)
   float* peer_mailbox[kMaxPeers];
   float* gather_scratch;  // [kMaxPeers, P] private copy of the gathered partials
-  int* error_flag;        // set when the exchange times out
+  int* error_flag;        // set when the exchange times out (mapped pinned host memory: the host polls it)
+  unsigned stage_bytes;   // shared-memory landing zone the host reserved for the block partials (0: none)
   int E, E_pad, P;
 };
 
 // shared-memory carve-up (host and device agree through this helper)
 struct SmemLayout {
   unsigned map_off[2];
-  unsigned nominal_off, refraw_off, ref4_off, refv_off, warpacc_off, list_off, red_off, misc_off, total;
+  unsigned stage_off, stage_cap;  // landing zone of the block partials in the last block (overlays the grids)
+  unsigned nominal_off, zero_off, refraw_off, ref4_off, refv_off, warpacc_off, list_off, red_off, misc_off, total;
 };
 
 __host__ __device__ inline unsigned align_up(unsigned x, unsigned a) { return (x + a - 1) / a * a; }
@@ -112,15 +114,20 @@ __host__ __device__ inline unsigned finish_scratch_core(int E_pad, int T, int ta
 
 __host__ __device__ inline SmemLayout make_layout(int n_maps, const unsigned* map_bytes, int T, int E_pad,
                                                    unsigned prev_action_bytes, bool refpath, int n_warps,
-                                                   int tail_per_step) {
+                                                   int tail_per_step, int spt, unsigned stage_bytes) {
   SmemLayout L;
   unsigned o = 16;  // mbarrier
+  L.stage_off = o;
   for (int i = 0; i < 2; ++i) {
     L.map_off[i] = o;
     if (i < n_maps) o += align_up(map_bytes[i], 16);
   }
+  if (o - 16 < stage_bytes) o = 16 + align_up(stage_bytes, 16);
+  L.stage_cap = o - 16;
   L.nominal_off = o;
   o += align_up(prev_action_bytes, 16);
+  L.zero_off = o;
+  o += align_up((unsigned)E_pad * 4, 16);
   L.refraw_off = o;
   if (refpath) o += (unsigned)(T + 1) * 16;
   L.ref4_off = o;
@@ -135,11 +142,11 @@ __host__ __device__ inline SmemLayout make_layout(int n_maps, const unsigned* ma
     o += align_up(acc > fin ? acc : fin, 16);
   }
   L.list_off = o;
-  o += (unsigned)n_warps * 32 * 8;  // (thread, weight) of the samples with non-zero weight
+  o += (unsigned)n_warps * 32 * 8 * (unsigned)spt;  // (local sample, weight) of the samples with non-zero weight
   L.red_off = o;
   o += 128 * 8;  // block reduction scratch (up to 4 x 32 doubles)
   L.misc_off = o;
-  o += 128;
+  o += 256;
   L.total = o;
   return L;
 }
@@ -402,7 +409,7 @@ __device__ inline void mpo_update(const SolveParams& p, const Combined& c) {
 // smem: opt[E], y[(2T-1)*du] floats supplied by the caller.
 template <class M>
 __device__ __noinline__ void finish_solve(const SolveParams& p, const Combined& c, const double* N, float* opt,
-                                          float* ybuf, float* tail) {
+                                          float* ybuf, float* tail, bool history_loaded = false) {
   // the rollout of the optimal sequence only needs the model parameters (dynamics never read the maps
   // or the reference path); a local context keeps the caller's register-resident one from escaping
   typename M::Ctx ctx{};
@@ -415,7 +422,8 @@ __device__ __noinline__ void finish_solve(const SolveParams& p, const Combined& 
     opt[e] = r;
     ybuf[H + e] = r;
   }
-  for (int i = tid; i < H; i += nt) ybuf[i] = p.history[i];
+  if (!history_loaded)  // (the solve kernel's last block fetched it while the partials were in flight)
+    for (int i = tid; i < H; i += nt) ybuf[i] = p.history[i];
   __syncthreads();
   if (p.use_sg) {  // mppi.py:423-443, 598-620
     const int W = p.sg_window, pad = W / 2, n = 2 * T - 1;
@@ -533,7 +541,10 @@ __device__ inline bool exchange_partials(const SolveParams& p, const Combined& c
   }
   __syncthreads();
   if (timed_out) {
-    if (tid == 0 && p.error_flag) *p.error_flag = 1;
+    if (tid == 0 && p.error_flag) {
+      *reinterpret_cast<volatile int*>(p.error_flag) = (int)seq;  // mapped host memory: which solve failed
+      __threadfence_system();
+    }
     return false;
   }
   const float* mine = p.peer_mailbox[p.p2p_rank] + (size_t)parity * kMaxPeers * P;
@@ -546,22 +557,13 @@ __device__ inline bool exchange_partials(const SolveParams& p, const Combined& c
 // ---------------------------------------------------------------------------
 // the solve kernel
 // ---------------------------------------------------------------------------
-template <class M, bool kBounded>
-__device__ __forceinline__ void model_step(const typename M::Ctx& ctx, float (&s)[M::DS], const float (&u)[M::DU],
-                                           float (&seen)[M::DS]) {
-  if constexpr (M::kHasBounded)
-    M::template step<kBounded>(ctx, s, u, seen);
-  else
-    M::step(ctx, s, u, seen);
-}
-
-template <class M, bool kBounded>
-__device__ __forceinline__ float model_cost(const typename M::Ctx& ctx, const float (&s)[M::DS], const float (&u)[M::DU],
-                                            const float (&pu)[M::DU], int t) {
-  if constexpr (M::kHasBounded)
-    return M::template cost<kBounded>(ctx, s, u, pu, t);
-  else
-    return M::cost(ctx, s, u, pu, t);
+// A sharded solve whose peer exchange timed out has no result: the outputs become NaN (never stale or
+// uninitialised memory) and the error flag - mapped host memory - tells the host which solve failed.
+template <class M>
+__device__ __forceinline__ void poison_outputs(const SolveParams& p) {
+  const float nan = __int_as_float(0x7fc00000);
+  for (int e = threadIdx.x; e < p.E; e += blockDim.x) p.action_out[e] = nan;
+  for (int i = threadIdx.x; i < (p.T + 1) * M::DS; i += blockDim.x) p.state_seq_out[i] = nan;
 }
 
 // Loop constants held in ordinary registers: ptxas otherwise re-materialises kernel parameters from the
@@ -588,11 +590,10 @@ template <class M>
 struct LoopConsts {
   typename M::Ctx ctx;
   float sigma[M::DU], lo[M::DU], hi[M::DU];
-  int T, zero_mean;
+  int T;
 };
 template <class M>
-__device__ __forceinline__ void pin_loop_consts(const SolveParams& p, const typename M::Ctx& ctx, bool zero_mean,
-                                                LoopConsts<M>& lc) {
+__device__ __forceinline__ void pin_loop_consts(const SolveParams& p, const typename M::Ctx& ctx, LoopConsts<M>& lc) {
   lc.ctx = ctx;
   constexpr int kHot = sizeof(lc.ctx.hv) / sizeof(float);
 #pragma unroll
@@ -609,25 +610,16 @@ __device__ __forceinline__ void pin_loop_consts(const SolveParams& p, const type
     lc.hi[d] = pin(p.u_max[d]);
   }
   lc.T = pin(p.T);
-  lc.zero_mean = __shfl_sync(kFullMask, zero_mean ? 1 : 0, (int)(threadIdx.x & 31));  // per lane, opaque
 }
 
-template <class M, bool kInject, bool kBounded>
-__device__ __forceinline__ float rollout_cost(const SolveParams& p, const typename M::Ctx& ctx_in, const float* nominal,
-                                           bool zero_mean_in, uint32_t k_lo, uint32_t k_hi, long long k_local,
-                                           const LoopConsts<M>& lc) {
+// One sample per thread, the literal transcription (general loop): rollout + stage costs + terminal cost
+// (mppi.py:280-336). `nominal` = this sample's mean sequence (the warm start, or zeros for the exploration
+// tail, mppi.py:266-275).
+template <class M, bool kInject>
+__device__ __forceinline__ float rollout_cost(const SolveParams& p, const typename M::Ctx& ctx, const float* nominal,
+                                              uint32_t k_lo, uint32_t k_hi, long long k_local) {
   constexpr int DS = M::DS, DU = M::DU, SPC = Chunking<DU>::kStepsPerChunk;
-  // bounded: every loop constant comes from the pinned register copies (lc), see pin_loop_consts
-  const typename M::Ctx& ctx = kBounded ? lc.ctx : ctx_in;
-  const bool zero_mean = kBounded ? (lc.zero_mean != 0) : zero_mean_in;
-  const int T = kBounded ? lc.T : p.T;
-  float sigma_r[DU], lo_r[DU], hi_r[DU];
-#pragma unroll
-  for (int d = 0; d < DU; ++d) {
-    sigma_r[d] = kBounded ? lc.sigma[d] : p.sigma[d];
-    lo_r[d] = kBounded ? lc.lo[d] : p.u_min[d];
-    hi_r[d] = kBounded ? lc.hi[d] : p.u_max[d];
-  }
+  const int T = p.T;
   float s[DS], seen[DS];
   {
     const float* state = state_of(p);
@@ -639,38 +631,6 @@ __device__ __forceinline__ float rollout_cost(const SolveParams& p, const typena
   for (int d = 0; d < DU; ++d) up[d] = upp[d] = 0.0f;
   float total = 0.0f;
   const float* nz = kInject ? (p.noise + (size_t)k_local * T * DU) : nullptr;
-  if constexpr (kBounded && !kInject && M::kHasBounded) {
-    // whole sampler chunks without the per-step `t < T` guard; a trailing partial chunk keeps it
-    auto one_step = [&](int t, const float* ez) {
-#pragma unroll
-      for (int d = 0; d < DU; ++d)
-        u[d] = clampf((zero_mean ? 0.0f : nominal[t * DU + d]) + sigma_r[d] * ez[d], lo_r[d], hi_r[d]);
-      float pu[DU];
-#pragma unroll
-      for (int d = 0; d < DU; ++d) pu[d] = (t == 0) ? u[d] : up[d];
-      model_step<M, kBounded>(ctx, s, u, seen);
-      total = total + model_cost<M, kBounded>(ctx, seen, u, pu, t);
-#pragma unroll
-      for (int d = 0; d < DU; ++d) {
-        upp[d] = up[d];
-        up[d] = u[d];
-      }
-    };
-    int t0 = 0, chunk = 0;
-    for (; t0 + SPC <= T; t0 += SPC, ++chunk) {
-      float z[4];
-      normal4(p.key, k_lo, k_hi, (uint32_t)chunk, z);
-#pragma unroll
-      for (int j = 0; j < SPC; ++j) one_step(t0 + j, z + j * DU);
-    }
-    if (t0 < T) {
-      float z[4];
-      normal4(p.key, k_lo, k_hi, (uint32_t)chunk, z);
-#pragma unroll
-      for (int j = 0; j < SPC; ++j)
-        if (t0 + j < T) one_step(t0 + j, z + j * DU);
-    }
-  } else
   for (int t0 = 0, chunk = 0; t0 < T; t0 += SPC, ++chunk) {
     float z[4];
     if (!kInject) normal4(p.key, k_lo, k_hi, (uint32_t)chunk, z);
@@ -680,14 +640,14 @@ __device__ __forceinline__ float rollout_cost(const SolveParams& p, const typena
       if (t < T) {
 #pragma unroll
         for (int d = 0; d < DU; ++d) {
-          float eps = kInject ? nz[t * DU + d] : sigma_r[d] * z[j * DU + d];
-          u[d] = clampf((zero_mean ? 0.0f : nominal[t * DU + d]) + eps, lo_r[d], hi_r[d]);  // == perturbed_entry
+          float eps = kInject ? nz[t * DU + d] : p.sigma[d] * z[j * DU + d];
+          u[d] = clampf(nominal[t * DU + d] + eps, p.u_min[d], p.u_max[d]);  // == perturbed_entry
         }
         float pu[DU];  // info["prev_action"]: U[:, max(t-1, 0)]  (mppi.py:299-304)
 #pragma unroll
         for (int d = 0; d < DU; ++d) pu[d] = (t == 0) ? u[d] : up[d];
-        model_step<M, kBounded>(ctx, s, u, seen);      // S[:, t+1] = dynamics(S[:, t], U[:, t])   (mppi.py:282-286)
-        total = total + model_cost<M, kBounded>(ctx, seen, u, pu, t);  // stage cost on S[:, t]  (mppi.py:307-311)
+        M::step(ctx, s, u, seen);                      // S[:, t+1] = dynamics(S[:, t], U[:, t])   (mppi.py:282-286)
+        total = total + M::cost(ctx, seen, u, pu, t);  // stage cost on S[:, t]  (mppi.py:307-311)
 #pragma unroll
         for (int d = 0; d < DU; ++d) {
           upp[d] = up[d];
@@ -703,7 +663,84 @@ __device__ __forceinline__ float rollout_cost(const SolveParams& p, const typena
     zero[d] = 0.0f;
     pa[d] = (T >= 2) ? upp[d] : up[d];
   }
-  return total + model_cost<M, kBounded>(ctx, s, zero, pa, T - 1);  // mppi.py:333-336
+  return total + M::cost(ctx, s, zero, pa, T - 1);  // mppi.py:333-336
+}
+
+// Two samples per thread, the bounded loop (racing / navigation2d): every fp32 add / mul / fma of the two
+// rollouts is ONE packed instruction (P2; sm_100 FADD2 / FMUL2 / FFMA2, each lane rounded like the scalar
+// op), the operations and their order per sample are those of the general loop with the bounded helpers
+// substituted (each proven bit-identical over its whole input range, see mppi_selftest), so costs are
+// bit-identical to rollout_cost<>. All loop constants come from the pinned register copies (lc); whole
+// sampler chunks run without the per-step `t < T` guard (a trailing partial chunk keeps it); the
+// `prev_action` of step 0 is the action itself (mppi.py:299-304), so `up` starts as u_0 instead of a per-step
+// select.
+template <class M>
+struct PairRoll {  // two samples' rollout state, one P2 per quantity
+  P2 s[M::DS], u[M::DU], up[M::DU], upp[M::DU];
+  P2 total;
+  const float *nom_a, *nom_b;  // each sample's mean sequence (the warm start, or zeros for the exploration tail)
+};
+// clamp(mean + sigma * eps) of both samples for step t (mppi.py:266-275)
+template <class M>
+__device__ __forceinline__ void pair_controls(const LoopConsts<M>& lc, const PairRoll<M>& r, int t, P2 e0, P2 e1,
+                                              P2 (&out)[2]) {
+  const float2 na = *reinterpret_cast<const float2*>(r.nom_a + 2 * t);
+  const float2 nb = *reinterpret_cast<const float2*>(r.nom_b + 2 * t);
+  out[0] = clamp2(P2(na.x, nb.x) + lc.sigma[0] * e0, lc.lo[0], lc.hi[0]);
+  out[1] = clamp2(P2(na.y, nb.y) + lc.sigma[1] * e1, lc.lo[1], lc.hi[1]);
+}
+// S[:, t+1] = dynamics(S[:, t], U[:, t]); stage cost on S[:, t] with prev_action = U[:, t-1]  (mppi.py:282-311)
+template <class M>
+__device__ __forceinline__ void pair_step(const LoopConsts<M>& lc, PairRoll<M>& r, int t, P2 e0, P2 e1) {
+  P2 seen[M::DS];
+  pair_controls<M>(lc, r, t, e0, e1, r.u);
+  M::step_pair(lc.ctx, r.s, r.u, seen);
+  r.total = r.total + M::cost_pair(lc.ctx, seen, r.u, r.up, t);
+#pragma unroll
+  for (int d = 0; d < M::DU; ++d) {
+    r.upp[d] = r.up[d];
+    r.up[d] = r.u[d];
+  }
+}
+template <class M>
+__device__ __forceinline__ void rollout_cost_pair(const SolveParams& p, const LoopConsts<M>& lc, const float* nom_a,
+                                                  const float* nom_b, uint32_t ka_lo, uint32_t ka_hi, uint32_t kb_lo,
+                                                  uint32_t kb_hi, float (&cost_out)[2]) {
+  constexpr int DS = M::DS, DU = M::DU;
+  static_assert(DU == 2, "the paired loop is written for two controls per step (one sampler chunk = two steps)");
+  const int T = lc.T;
+  PairRoll<M> r;
+  r.nom_a = nom_a;
+  r.nom_b = nom_b;
+  r.total = P2(0.0f);
+  {
+    const float* state = state_of(p);
+#pragma unroll
+    for (int i = 0; i < DS; ++i) r.s[i] = P2(state[i]);
+  }
+  // one sampler chunk = two steps; the loop body exists once (the instruction footprint matters: bench.py
+  // starts every solve with a cold L2, i.e. cold instruction fetches)
+  for (int t0 = 0, chunk = 0; t0 < T; t0 += 2, ++chunk) {
+    P2 z[4];
+    normal4_pair(p.key, ka_lo, ka_hi, kb_lo, kb_hi, (uint32_t)chunk, z);
+    if (chunk == 0) {  // prev_action at t = 0 is the action itself (mppi.py:299-304)
+      pair_controls<M>(lc, r, 0, z[0], z[1], r.up);
+#pragma unroll
+      for (int d = 0; d < DU; ++d) r.upp[d] = r.up[d];
+    }
+    pair_step<M>(lc, r, t0, z[0], z[1]);
+    if (t0 + 1 < T) pair_step<M>(lc, r, t0 + 1, z[2], z[3]);  // odd horizon: the last chunk covers one step
+  }
+  // terminal: state S[:, T], zero action, stale t = T-1 and prev_action = U[:, T-2] (mppi.py:318-328)
+  P2 zero[DU], pa[DU];
+#pragma unroll
+  for (int d = 0; d < DU; ++d) {
+    zero[d] = P2(0.0f);
+    pa[d] = (T >= 2) ? r.upp[d] : r.up[d];
+  }
+  r.total = r.total + M::cost_pair(lc.ctx, r.s, zero, pa, T - 1);  // mppi.py:333-336
+  cost_out[0] = r.total.v.x;
+  cost_out[1] = r.total.v.y;
 }
 
 __device__ __forceinline__ void stamp(const SolveParams& p, int slot) {
@@ -722,15 +759,21 @@ __host__ __device__ constexpr int tail_per_step() {
     return 0;
 }
 
-template <class M, bool kInject, int kMode>
-__global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ SolveParams p) {
+// SPT = samples per thread. 2: the launch geometry of the paired bounded loop (host-selected when the model
+// flags allow it and no noise is injected); thread `tid` of block `b` owns local samples
+// b * 2 * blockDim + {tid, blockDim + tid}. If the solve's initial state fails the kernel-side range check the
+// same launch runs the general loop once per sample (same results, slower).
+template <class M, bool kInject, int kMode, int SPT>
+__global__ void __launch_bounds__(SPT == 2 ? 256 : 512, 1) solve_kernel(const __grid_constant__ SolveParams p) {
   constexpr int DU = M::DU;
+  static_assert(SPT == 1 || (M::kHasBounded && !kInject), "two samples per thread is the bounded sampler loop");
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
-  const SmemLayout L =
-      make_layout(M::kMaps, p.map_bytes, p.T, p.E_pad, p.prev_action_bytes, M::kRefPath, n_warps, tail_per_step<M>());
+  const SmemLayout L = make_layout(M::kMaps, p.map_bytes, p.T, p.E_pad, p.prev_action_bytes, M::kRefPath, n_warps,
+                                   tail_per_step<M>(), SPT, p.stage_bytes);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   float* nominal = reinterpret_cast<float*>(smem + L.nominal_off);
+  float* zero_nominal = reinterpret_cast<float*>(smem + L.zero_off);
   float* warp_acc = reinterpret_cast<float*>(smem + L.warpacc_off);
   void* red = smem + L.red_off;
   int* misc = reinterpret_cast<int*>(smem + L.misc_off);
@@ -761,6 +804,7 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ S
     const float* src = refpath_of(p);
     for (int i = tid; i < (p.T + 1) * 4; i += blockDim.x) raw[i] = src[i];
   }
+  for (int e = tid; e < p.E_pad; e += blockDim.x) zero_nominal[e] = 0.0f;  // mean of the exploration tail
   mbar_wait(bar, 0);
   __syncthreads();
 
@@ -797,51 +841,104 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ S
   }
 
   stamp(p, 1);
-  const long long k_local = (long long)blockIdx.x * blockDim.x + tid;
-  const bool active = k_local < p.K;
-  const long long k_global = p.k_offset + k_local;
-  const uint32_t k_lo = (uint32_t)k_global, k_hi = (uint32_t)((unsigned long long)k_global >> 32);
-  const bool zero_mean = k_global >= p.explore_threshold;
+  const long long block_k0 = (long long)blockIdx.x * blockDim.x * SPT;
+  long long k_local[SPT];
+  bool active[SPT], zero_mean[SPT];
+  uint32_t k_lo[SPT], k_hi[SPT];
+#pragma unroll
+  for (int j = 0; j < SPT; ++j) {
+    k_local[j] = block_k0 + (long long)j * blockDim.x + tid;
+    active[j] = k_local[j] < p.K;
+    const long long k_global = p.k_offset + k_local[j];
+    k_lo[j] = (uint32_t)k_global;
+    k_hi[j] = (uint32_t)((unsigned long long)k_global >> 32);
+    zero_mean[j] = k_global >= p.explore_threshold;
+  }
 
   // ---- pass 1: rollout + cost -------------------------------------------------
-  float cost = INFINITY;
+  float cost[SPT];
+#pragma unroll
+  for (int j = 0; j < SPT; ++j) cost[j] = INFINITY;
   if (kMode == kReduce) {
-    if (active) cost = p.costs[k_local];
+#pragma unroll
+    for (int j = 0; j < SPT; ++j)
+      if (active[j]) cost[j] = p.costs[k_local[j]];
   } else {
-    bool bounded = false;  // uniform over the block: model flag + the solve's initial state
-    if constexpr (M::kHasBounded) bounded = (p.mp.flags & kFlagBounded) && M::state_in_bounds(ctx, state_of(p));
-    LoopConsts<M> lc;
-    if constexpr (M::kHasBounded) {
-      if (bounded) pin_loop_consts<M>(p, ctx, zero_mean, lc);  // whole warps: before the per-sample branch
+    bool paired = false;  // uniform over the block: model flag + the solve's initial state
+    if constexpr (SPT == 2) {
+      paired = (p.mp.flags & kFlagBounded) && M::state_in_pair_bounds(ctx, state_of(p));
+      if (paired) {
+        LoopConsts<M> lc;
+        pin_loop_consts<M>(p, ctx, lc);  // whole warps: before the per-sample branch
+        if (active[0]) {                 // an inactive second sample (odd K) rolls a copy of the first
+          const bool zb = active[1] ? zero_mean[1] : zero_mean[0];
+          const uint32_t kb_lo = active[1] ? k_lo[1] : k_lo[0], kb_hi = active[1] ? k_hi[1] : k_hi[0];
+          float c2[2];
+          rollout_cost_pair<M>(p, lc, zero_mean[0] ? zero_nominal : nominal, zb ? zero_nominal : nominal, k_lo[0],
+                               k_hi[0], kb_lo, kb_hi, c2);
+          cost[0] = c2[0];
+          if (active[1]) cost[1] = c2[1];
+        }
+      }
     }
-    if (active) {
-      cost = bounded ? rollout_cost<M, kInject, true>(p, ctx, nominal, zero_mean, k_lo, k_hi, k_local, lc)
-                     : rollout_cost<M, kInject, false>(p, ctx, nominal, zero_mean, k_lo, k_hi, k_local, lc);
-      p.costs[k_local] = cost;
+    if (!paired) {
+      // one sample after the other through the general loop; the per-sample values are recomputed from j
+      // (no indexing of the register arrays by a run-time j, which would push them into local memory)
+#pragma unroll 1
+      for (int j = 0; j < SPT; ++j) {
+        const long long kl = block_k0 + (long long)j * blockDim.x + tid, kg = p.k_offset + kl;
+        float c = INFINITY;
+        if (kl < p.K)
+          c = rollout_cost<M, kInject>(p, ctx, (kg >= p.explore_threshold) ? zero_nominal : nominal, (uint32_t)kg,
+                                       (uint32_t)((unsigned long long)kg >> 32), kl);
+#pragma unroll
+        for (int jj = 0; jj < SPT; ++jj) cost[jj] = (jj == j) ? c : cost[jj];
+      }
     }
+#pragma unroll
+    for (int j = 0; j < SPT; ++j)
+      if (active[j]) p.costs[k_local[j]] = cost[j];
   }
   if (kMode == kCosts) return;
   __syncthreads();
   stamp(p, 2);
 
   // ---- block-local softmax baseline (mppi.py:376; online-softmax form) -----------
+  // x = -c / lambda is monotone in c, so max_k x_k = (-min_k c_k) / lambda exactly: one reduction gives the
+  // baseline and the cost range, a second one the sums.
   const float lam = (float)p.sc->lambda;
-  const float x = active ? (-cost) / lam : -INFINITY;
-  const float xmax_b = block_reduce(x, OpMax(), -INFINITY, red);
-  const float w = active ? expf(x - xmax_b) : 0.0f;
-  const float S_b = block_reduce(w, OpAddF(), 0.0f, red);
-  const float cmin_b = block_reduce(active ? cost : INFINITY, OpMin(), INFINITY, red);
-  const float cmax_b = block_reduce(active ? cost : -INFINITY, OpMax(), -INFINITY, red);
-  float xmt_b = -INFINITY, St_b = 0.0f, Sct_b = 0.0f;
-  if (p.lambda_mode == kLamMPO) {  // second softmax at tau = softplus(rho) for the MPO step
+  float mm[2] = {-INFINITY, -INFINITY};  // max(-c), max(c)
+#pragma unroll
+  for (int j = 0; j < SPT; ++j)
+    if (active[j]) {
+      mm[0] = fmaxf(mm[0], -cost[j]);
+      mm[1] = fmaxf(mm[1], cost[j]);
+    }
+  block_reduce_n(mm, OpMax(), -INFINITY, red);
+  const float cmin_b = -mm[0], cmax_b = mm[1];
+  const float xmax_b = mm[0] / lam;
+  float w[SPT];
+  float sums[3] = {0.0f, 0.0f, 0.0f};  // S, S_tau, Sc_tau
+  float xmt_b = -INFINITY;
+  const bool mpo = p.lambda_mode == kLamMPO;
+  float tau = 1.0f;
+  if (mpo) {  // second softmax at tau = softplus(rho) for the MPO step
     const float rho = p.sc->rho;
-    const float tau = (rho > 20.0f) ? rho : log1pf(expf(rho));
-    const float xt = active ? (-cost) / tau : -INFINITY;
-    xmt_b = block_reduce(xt, OpMax(), -INFINITY, red);
-    const float et = active ? expf(xt - xmt_b) : 0.0f;
-    St_b = block_reduce(et, OpAddF(), 0.0f, red);
-    Sct_b = block_reduce(active ? et * cost : 0.0f, OpAddF(), 0.0f, red);
+    tau = (rho > 20.0f) ? rho : log1pf(expf(rho));
+    xmt_b = mm[0] / tau;
   }
+#pragma unroll
+  for (int j = 0; j < SPT; ++j) {
+    w[j] = active[j] ? expf((-cost[j]) / lam - xmax_b) : 0.0f;
+    sums[0] += w[j];
+    if (mpo && active[j]) {
+      const float et = expf((-cost[j]) / tau - xmt_b);
+      sums[1] += et;
+      sums[2] += et * cost[j];
+    }
+  }
+  block_reduce_n(sums, OpAddF(), 0.0f, red);
+  const float S_b = sums[0], St_b = sums[1], Sct_b = sums[2];
 
   stamp(p, 3);
   // ---- pass 2: regenerate the perturbed controls of the samples that carry weight and reduce
@@ -851,24 +948,39 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ S
   //      i = g, g+G, ... in order, groups are then added in order -> deterministic, all warps busy,
   //      and the cost scales with the number of samples that matter, not with K.
   int2* list = reinterpret_cast<int2*>(smem + L.list_off);
-  int* wcount = misc + 2;  // [n_warps]
+  int* wcount = misc + 2;  // [SPT * n_warps]
   {
-    const bool on = w != 0.0f;
-    const unsigned m = __ballot_sync(kFullMask, on);
-    if (lane == 0) wcount[warp] = __popc(m);
-    __syncthreads();
-    int off = 0, n_active = 0;
-    for (int i = 0; i < n_warps; ++i) {
-      off += (i < warp) ? wcount[i] : 0;
-      n_active += wcount[i];
+    unsigned m[SPT];
+#pragma unroll
+    for (int j = 0; j < SPT; ++j) {
+      m[j] = __ballot_sync(kFullMask, w[j] != 0.0f);
+      if (lane == 0) wcount[j * n_warps + warp] = __popc(m[j]);
     }
-    if (on) list[off + __popc(m & ((1u << lane) - 1u))] = make_int2(tid, __float_as_int(w));
+    __syncthreads();
+    int off[SPT], n_active = 0;
+#pragma unroll
+    for (int j = 0; j < SPT; ++j) {
+      off[j] = 0;
+      for (int i = 0; i < n_warps; ++i) {
+        const int c = wcount[j * n_warps + i];
+        if (i < warp) off[j] += c;
+        n_active += c;
+      }
+    }
+    if (SPT == 2) {  // second-sample entries follow all first-sample entries
+      int first = 0;
+      for (int i = 0; i < n_warps; ++i) first += wcount[i];
+      off[SPT - 1] += first;
+    }
+#pragma unroll
+    for (int j = 0; j < SPT; ++j)
+      if (w[j] != 0.0f)
+        list[off[j] + __popc(m[j] & ((1u << lane) - 1u))] = make_int2(j * (int)blockDim.x + tid, __float_as_int(w[j]));
     __syncthreads();
     const int n_chunks = (p.E + 3) / 4;
     float* group_acc = warp_acc;  // [G, E_pad]
     const int G = (n_chunks <= (int)blockDim.x) ? max(1, min((int)blockDim.x / n_chunks, n_warps)) : 1;
     const int g = (n_chunks <= (int)blockDim.x) ? tid / n_chunks : 0;
-    const long long block_k0 = (long long)blockIdx.x * blockDim.x;
     for (int c = (n_chunks <= (int)blockDim.x) ? tid - g * n_chunks : tid; c < n_chunks && g < G;
          c += (n_chunks <= (int)blockDim.x) ? n_chunks : (int)blockDim.x) {
       float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -933,14 +1045,37 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const __grid_constant__ S
   Combined* comb = reinterpret_cast<Combined*>(scale_buf + 256);
   double* seg_buf = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(comb) + 64);
   float* tail = reinterpret_cast<float*>(seg_buf + (size_t)p.E_pad * kMaxSegments);
-  combine_partials(p.block_partials, (int)gridDim.x, p.P, p.E_pad, comb, Nbuf, scale_buf, red, seg_buf);
+  // The partials of all blocks ([grid, P] floats, contiguous) come into shared memory with ONE bulk copy
+  // (the staged grids are dead by now, their region is the landing zone) when they fit: the combine then
+  // runs out of shared memory instead of ~10 dependent round trips to L2.
+  const float* parts = p.block_partials;
+  const unsigned part_bytes = (unsigned)gridDim.x * (unsigned)p.P * 4u;
+  if (part_bytes <= L.stage_cap && part_bytes >= 2048u) {
+    float* stage = reinterpret_cast<float*>(smem + L.stage_off);
+    if (tid == 0) {
+      fence_proxy_async_all();  // generic-proxy writes of the other blocks (made visible by their fences and
+                                // the ticket) before the async-proxy read; generic reads of the grids before it
+      mbar_expect_tx(bar, part_bytes);
+      bulk_g2s(stage, p.block_partials, part_bytes, bar);
+    }
+    // meanwhile: the carried SG history (finish_solve reads it from ybuf)
+    for (int i = tid; i < (p.T - 1) * DU; i += blockDim.x) ybuf[i] = p.history[i];
+    mbar_wait(bar, 1);
+    parts = stage;
+  } else {
+    for (int i = tid; i < (p.T - 1) * DU; i += blockDim.x) ybuf[i] = p.history[i];
+  }
+  __syncthreads();
+  combine_partials(parts, (int)gridDim.x, p.P, p.E_pad, comb, Nbuf, scale_buf, red, seg_buf);
   stamp(p, 5);
   if (p.n_shards == 1) {
-    finish_solve<M>(p, *comb, Nbuf, opt, ybuf, tail);
+    finish_solve<M>(p, *comb, Nbuf, opt, ybuf, tail, true);
   } else if (p.p2p_world > 0) {
     if (exchange_partials(p, *comb, Nbuf)) {
       combine_partials(p.gather_scratch, p.p2p_world, p.P, p.E_pad, comb, Nbuf, scale_buf, red, seg_buf);
-      finish_solve<M>(p, *comb, Nbuf, opt, ybuf, tail);
+      finish_solve<M>(p, *comb, Nbuf, opt, ybuf, tail, true);
+    } else {
+      poison_outputs<M>(p);  // a peer never arrived: NaN outputs + the error flag, never stale memory
     }
   } else {
     for (int e = tid; e < p.E; e += blockDim.x) p.rank_partial[kPartialHeader + e] = (float)Nbuf[e];

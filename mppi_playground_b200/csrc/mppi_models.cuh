@@ -86,6 +86,15 @@ __device__ __forceinline__ float map_value_bordered(const MapView& m, int ix, in
   return (float)((w >> (iy & 31)) & 1u);
 }
 
+// map_cell_bounded for two samples: the division sequence is packed, the guard / conversion run per lane.
+__device__ __forceinline__ void map_cell_bounded2(P2 x, const ExactDiv& cell, float origin, int* i0, int* i1) {
+  P2 q = x * cell.r;
+  q = fma2(fma2(-q, cell.c, x), cell.r, q);
+  const P2 qo = q + origin;
+  *i0 = __float2int_rn((fabsf(x.v.x) >= kFastDivMin) ? qo.v.x : origin);
+  *i1 = __float2int_rn((fabsf(x.v.y) >= kFastDivMin) ? qo.v.y : origin);
+}
+
 // src/envs/obstacle_map_2d.py:168-200 == src/envs/lane_map_2d.py:90-122.
 __device__ __forceinline__ float map_lookup(const MapView& m, float x, float y) {
   return map_value(m, map_cell(x, m.cell, m.ox), map_cell(y, m.cell, m.oy));
@@ -260,6 +269,37 @@ struct Navigation2D {  // src/envs/navigation_2d.py:218-279
                          : map_lookup(c.map, s[0], s[1]);
     return goal + p[11] * occ;  // :271-277
   }
+  // ---- two samples per thread (bounded loop only): step<true> / cost<true> with every fp32 add / mul / fma
+  // issued once for both samples (P2). The initial heading is >= -pi (kernel-checked, state_in_pair_bounds),
+  // so the first wrap of a step only needs the upper fold, like every later one.
+  __device__ static __forceinline__ void step_pair(const Ctx& c, P2 (&s)[DS], const P2 (&u)[DU], P2 (&seen)[DS]) {
+    const float* p = c.hv;
+#pragma unroll
+    for (int i = 0; i < DS; ++i) seen[i] = s[i];
+    const P2 th = wrap_angle_nonneg2(s[2]);  // :237
+    P2 st, ct;
+    sincos_bounded2(th, &st, &ct);
+    const P2 nx = s[0] + u[0] * ct * p[10];  // :239-241
+    const P2 ny = s[1] + u[0] * st * p[10];
+    s[2] = wrap_angle_bounded2(th + u[1] * p[10]);
+    s[0] = clamp2(nx, p[6], p[7]);  // :244-251
+    s[1] = clamp2(ny, p[8], p[9]);
+  }
+  __device__ static __forceinline__ bool state_in_pair_bounds(const Ctx& c, const float* state) {
+    return state_in_bounds(c, state) && state[2] >= -3.14159274101257324f;
+  }
+  __device__ static __forceinline__ P2 cost_pair(const Ctx& c, const P2 (&s)[DS], const P2 (&)[DU], const P2 (&)[DU],
+                                                 int) {
+    const float* p = c.hv;
+    const P2 dx = s[0] - p[4], dy = s[1] - p[5];
+    const P2 d2 = dx * dx + dy * dy;
+    const P2 goal(sqrtf(d2.v.x), sqrtf(d2.v.y));  // :269
+    int ix0, ix1, iy0, iy1;
+    map_cell_bounded2(s[0], c.map.cell, c.map.ox, &ix0, &ix1);
+    map_cell_bounded2(s[1], c.map.cell, c.map.oy, &iy0, &iy1);
+    const P2 occ(map_value_bordered(c.map, ix0, iy0), map_value_bordered(c.map, ix1, iy1));
+    return goal + p[11] * occ;  // :271-277
+  }
   // Optimal-trajectory rollout by one block (mppi.py:508-524). Same operations on the same values as
   // T calls of step(); only the schedule differs: the heading chain is the one serial part, the
   // sin/cos of every stage and the position increments are evaluated by T threads at once.
@@ -405,18 +445,112 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
     in = in + p[16] * (d0 * d0 + d1 * d1);                   // :155
     return path + vel + occ + in;                            // :157
   }
+  // ---- two samples per thread (bounded loop only): step<true> / cost<true> with every fp32 add / mul / fma
+  // issued once for both samples (P2); clamps, selects, conversions and the grid lookups stay per lane. The
+  // initial heading is >= -pi (kernel-checked, state_in_pair_bounds), so the first wrap of a step only needs
+  // the upper fold (wrap_angle_nonneg == wrap_angle there), like every later one.
+  __device__ static __forceinline__ void step_pair(const Ctx& c, P2 (&s)[DS], const P2 (&u)[DU], P2 (&seen)[DS]) {
+    const float* p = c.hv;
+#pragma unroll
+    for (int i = 0; i < DS; ++i) seen[i] = s[i];
+    const P2 th = wrap_angle_nonneg2(s[2]);  // :347
+    P2 st, ct;
+    sincos_bounded2(th, &st, &ct);
+    const P2 dx = s[3] * ct;  // :349-352
+    const P2 dy = s[3] * st;
+    const P2 r = s[3] * tan_quarter2(u[1]);
+    P2 q = r * p[17];  // yaw_rate_hot per lane: exact v tan(steer) / L
+    q = fma2(fma2(-q, p[4], r), p[17], q);
+    const P2 dth((fabsf(r.v.x) >= kFastDivMin) ? q.v.x : r.v.x, (fabsf(r.v.y) >= kFastDivMin) ? q.v.y : r.v.y);
+    const P2 nx = s[0] + dx * p[10];  // :354-357
+    const P2 ny = s[1] + dy * p[10];
+    const P2 nv = s[3] + u[0] * p[10];
+    s[2] = wrap_angle_bounded2(th + dth * p[10]);
+    s[0] = clamp2(nx, p[6], p[7]);  // :360-368
+    s[1] = clamp2(ny, p[8], p[9]);
+    s[3] = clamp2(nv, -p[5], p[5]);
+  }
+  __device__ static __forceinline__ bool state_in_pair_bounds(const Ctx& c, const float* state) {
+    return state_in_bounds(c, state) && state[2] >= -3.14159274101257324f;
+  }
+  __device__ static __forceinline__ P2 cost_pair(const Ctx& c, const P2 (&s)[DS], const P2 (&u)[DU],
+                                                 const P2 (&pu)[DU], int t) {
+    const float* p = c.hv;
+    const float4 r = c.ref[t];
+    const P2 sx = s[0] - r.x, sy = s[1] - r.y;
+    const P2 ec = r.z * sx - r.w * sy;                         // racing.py:127-131
+    const P2 el = (-r.w) * sx - r.z * sy;                      // :132-136
+    const P2 path = p[11] * (ec * ec) + p[12] * (el * el);     // :138
+    const P2 dv = s[3] - c.ref_v[t];
+    const P2 vel = p[13] * (dv * dv);                          // :141-143
+    int ix0, ix1, iy0, iy1;
+    map_cell_bounded2(s[0], c.obstacle.cell, c.obstacle.ox, &ix0, &ix1);
+    map_cell_bounded2(s[1], c.obstacle.cell, c.obstacle.oy, &iy0, &iy1);
+    P2 occ = P2(map_value_bordered(c.obstacle, ix0, iy0), map_value_bordered(c.obstacle, ix1, iy1)) +
+             P2(map_value_bordered(c.lane, ix0, iy0), map_value_bordered(c.lane, ix1, iy1));  // :146-150
+    occ = p[14] * occ;                                         // :151
+    P2 in = p[15] * (u[0] * u[0] + u[1] * u[1]);               // :154
+    const P2 d0 = u[0] - pu[0], d1 = u[1] - pu[1];
+    in = in + p[16] * (d0 * d0 + d1 * d1);                     // :155
+    return path + vel + occ + in;                              // :157
+  }
   // Optimal-trajectory rollout by one block (mppi.py:508-524): the same operations on the same values
   // as T calls of step(), rescheduled. Serial parts are only the three cheap recurrences (speed:
   // add+clamp; heading: two angle wraps; position: add+clamp); tan / sin / cos of all T stages run in
   // parallel in between. scratch: 11 * (T + 9) floats.
+  // speed and heading of every stage by ONE thread, software-pipelined: the speed recurrence
+  // (add + clamp) and the yaw increments it feeds (v tan(steer) / L * dt) run ahead of the heading
+  // recurrence (two wraps per stage), which is the only long dependent chain; increments are fetched
+  // eight stages at a time. Same operations on the same values as T calls of step().
+  template <bool kBounded>
+  __device__ static __forceinline__ void speed_heading_chain(const ModelParams& mp, const float* state, const float* adt,
+                                                             const float* tn, float* vs, float* thw, float* ths,
+                                                             int T) {
+    const float vm = mp.v[5], dt = mp.v[10];
+    float v = state[3], th = state[2];
+    ths[0] = th;
+    bool first = true;
+    for (int t0 = 0; t0 < T; t0 += 8) {
+      float a[8], tq[8], cc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a[j] = adt[t0 + j];
+        tq[j] = tn[t0 + j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {  // speed chain of the group first: it only depends on itself
+        vs[t0 + j] = v;
+        cc[j] = yaw_rate<kBounded>(mp, v, tq[j]) * dt;
+        v = clampf(v + a[j], -vm, vm);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float w;
+        if (kBounded)
+          w = (first && j == 0) ? wrap_angle_bounded(th) : wrap_angle_nonneg(th);
+        else
+          w = wrap_angle(th);
+        thw[t0 + j] = w;
+        th = kBounded ? wrap_angle_bounded(w + cc[j]) : wrap_angle(w + cc[j]);
+        ths[t0 + j + 1] = th;
+      }
+      first = false;
+    }
+    if ((T & 7) == 0) vs[T] = v;  // otherwise stage T lies inside the last group and was stored there
+  }
+  // Optimal-trajectory rollout by one block (mppi.py:508-524): the same operations on the same values
+  // as T calls of step(), rescheduled: tan of every stage in parallel, then ONE thread walks the speed and
+  // heading recurrences (speed_heading_chain), sin / cos of all stages in parallel, two threads walk the
+  // position recurrences (add + clamp). scratch: 11 * (T + 9) floats.
   __device__ static __noinline__ void rollout_block(const Ctx& c, const float* state, const float* opt, int T, float* out,
                                        float* scratch) {
     const float* p = c.p->v;
     const int tid = threadIdx.x, nt = blockDim.x, S = T + 9;  // room for whole groups of 8 (see serial_chain)
     float *adt = scratch, *tn = adt + S, *vs = tn + S, *cdt = vs + S, *ths = cdt + S, *thw = ths + S, *dx = thw + S,
           *dy = dx + S, *xs = dy + S, *ys = xs + S;
+    (void)cdt;
     const bool bounded = (c.p->flags & kFlagBounded) && state_in_bounds(c, state);
-    for (int t = T + tid; t < S; t += nt) adt[t] = cdt[t] = dx[t] = dy[t] = 0.0f;
+    for (int t = T + tid; t < S; t += nt) adt[t] = tn[t] = dx[t] = dy[t] = 0.0f;
     for (int t = tid; t < T; t += nt) {
       adt[t] = clampf(opt[2 * t], p[0], p[1]) * p[10];
       const float st = clampf(opt[2 * t + 1], p[2], p[3]);
@@ -424,18 +558,12 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
     }
     __syncthreads();
     if (tid == 0) {
-      const float vm = p[5];
-      serial_chain(state[3], adt, vs, T, [vm](float v, float a) { return clampf(v + a, -vm, vm); });
-    }
-    __syncthreads();
-    for (int t = tid; t < T; t += nt)
-      cdt[t] = (bounded ? yaw_rate<true>(*c.p, vs[t], tn[t]) : yaw_rate<false>(*c.p, vs[t], tn[t])) * p[10];
-    __syncthreads();
-    if (tid == 0) {  // heading: S[t+1].theta = wrap(wrap(S[t].theta) + c_t); thw keeps the inner wrap
+      // the chain runs in whole groups of 8: stages T .. roundup(T, 8) - 1 see zero increments and write
+      // into the padding (S = T + 9 covers index roundup(T, 8)), so the last real speed is re-stored below
       if (bounded)
-        heading_chain<true>(state[2], cdt, thw, ths, T);
+        speed_heading_chain<true>(*c.p, state, adt, tn, vs, thw, ths, T);
       else
-        heading_chain<false>(state[2], cdt, thw, ths, T);
+        speed_heading_chain<false>(*c.p, state, adt, tn, vs, thw, ths, T);
     }
     __syncthreads();
     for (int t = tid; t < T; t += nt) {

@@ -38,7 +38,10 @@ class Binding:
     dim_state: int = 0
     dim_control: int = 0
 
-    def params(self) -> List[float]:
+    def params(self, strict: bool = True) -> List[float]:
+        """Model parameter block. ``strict=False`` (solver construction): attributes the caller only sets
+        after building the solver (example/racing.py:24-46) are filled with placeholders; every solve re-reads
+        them with ``strict=True``."""
         return []
 
     def maps(self) -> List[Optional[MapSpec]]:
@@ -101,7 +104,7 @@ class GoalInDangerZoneModel(_Descriptor):
         self.u_min = torch.tensor([v_lim[0], w_lim[0]], dtype=torch.float32)
         self.u_max = torch.tensor([v_lim[1], w_lim[1]], dtype=torch.float32)
 
-    def params(self):
+    def params(self, strict: bool = True):
         return [self.v_lim[0], self.v_lim[1], self.w_lim[0], self.w_lim[1], self.dt, float(self.goal[0]),
                 float(self.goal[1]), float(self.center[0]), float(self.center[1]), self.radius, self.collision_cost]
 
@@ -119,7 +122,7 @@ class Navigation2DModel(_Descriptor):
         self.u_min, self.u_max = torch.tensor(u_min, dtype=torch.float32), torch.tensor(u_max, dtype=torch.float32)
         self.goal, self.lim, self.dt, self.obstacle_weight = tuple(goal), tuple(lim), dt, obstacle_weight
 
-    def params(self):
+    def params(self, strict: bool = True):
         lo, hi = self.u_min.tolist(), self.u_max.tolist()
         return [lo[0], hi[0], lo[1], hi[1], self.goal[0], self.goal[1], *self.lim, self.dt, self.obstacle_weight]
 
@@ -146,7 +149,7 @@ class RacingModel(_Descriptor):
         self.Qc, self.Ql, self.Qv, self.Qo, self.Qin, self.Qdin = Qc, Ql, Qv, Qo, Qin, Qdin
         self.reference_path_tensor: Optional[torch.Tensor] = None
 
-    def params(self):
+    def params(self, strict: bool = True):
         lo, hi = self.u_min.tolist(), self.u_max.tolist()
         return [lo[0], hi[0], lo[1], hi[1], self.wheelbase, self.v_max, *self.lim, self.dt, self.Qc, self.Ql,
                 self.Qv, self.Qo, self.Qin, self.Qdin]
@@ -272,21 +275,30 @@ class _ReferenceRacing(Binding):
                             float(env.L), float(env.V_MAX), *_lim4(env._obstacle_map),
                             0.1]  # delta_t default, racing_env.py:328
 
-    def params(self):
-        c = self.ctl  # the cost weights are plain Python attributes, re-read every solve (racing.py:41-46)
-        return [*self._env_params, float(c.Qc), float(c.Ql), float(c.Qv), float(c.Qo), float(c.Qin), float(c.Qdin)]
+    _WEIGHTS = ("Qc", "Ql", "Qv", "Qo", "Qin", "Qdin")
+
+    def params(self, strict: bool = True):
+        # the cost weights are plain Python attributes of the controller, re-read every solve (racing.py:41-46).
+        # example/racing.py builds the solver BEFORE it assigns them (racing.py:24-46): at construction
+        # (strict=False) missing weights are placeholders; at solve time a missing weight is the same
+        # AttributeError the reference's cost_function would raise.
+        c = self.ctl
+        if strict:
+            return [*self._env_params, *(float(getattr(c, n)) for n in self._WEIGHTS)]
+        return [*self._env_params, *(float(getattr(c, n, 0.0)) for n in self._WEIGHTS)]
 
     def maps(self):
-        c = self.ctl
-        if c.obstacle_map is None or c.lane_map is None:  # example/racing.py:83-90 raises the same way
+        c = self.ctl  # set_cost_map runs after the solver is built (example/racing.py:106-108, 227)
+        om, lm = getattr(c, "obstacle_map", None), getattr(c, "lane_map", None)
+        if om is None or lm is None:  # example/racing.py:83-90 raises the same way
             raise ValueError("reference path, obstacle map, and lane map must be set before calling solve method.")
-        return [_map_spec(c.obstacle_map), _map_spec(c.lane_map)]
+        return [_map_spec(om), _map_spec(lm)]
 
     def map_identity(self):
-        return (id(self.ctl.obstacle_map), id(self.ctl.lane_map))
+        return (id(getattr(self.ctl, "obstacle_map", None)), id(getattr(self.ctl, "lane_map", None)))
 
     def reference_path(self):
-        return self.ctl.reference_path
+        return getattr(self.ctl, "reference_path", None)
 
 
 class _ReferenceNavigation2D(Binding):
@@ -299,7 +311,7 @@ class _ReferenceNavigation2D(Binding):
                         float(e._goal_pos[0]), float(e._goal_pos[1]), *_lim4(e._obstacle_map), 0.1,
                         10000.0]  # navigation_2d.py:219,277
 
-    def params(self):
+    def params(self, strict: bool = True):
         return list(self._params)
 
     def maps(self):
@@ -315,7 +327,7 @@ class _ReferenceGoalInDangerZone(Binding):
     def __init__(self, env):
         self.env = env
 
-    def params(self):
+    def params(self, strict: bool = True):
         e = self.env  # plain Python / numpy attributes; the goal changes at every env.reset()
         return [float(e._v_min), float(e._v_max), float(e._omega_min), float(e._omega_max), float(e._dt),
                 float(e._goal[0]), float(e._goal[1]), float(e._danger_zone.center[0]),
@@ -329,11 +341,21 @@ def _wrap(x):
     return ((x + torch.pi) % (2 * torch.pi)) - torch.pi
 
 
+class ModelBindingWarning(UserWarning):
+    """Raised (as a warning) when Python callables were replaced by a built-in device model."""
+
+
 def _probe_inputs(ds: int, du: int):
+    """Probe batch for the behavioural fingerprint: 5 magnitudes x 16 rows, wide enough to drive every
+    clamp / saturation of the built-in closures (pendulum: |u| > 2, |thdot| > 8, |theta| > pi; cartpole:
+    |x| > 2.4, |theta| > 12 deg; mountaincar: both walls, |v| > 0.07, |u| > 1) as well as their interiors."""
     g = torch.Generator().manual_seed(1234)
-    state = (torch.rand(16, ds, generator=g) - 0.5) * torch.tensor([2.0, 1.0, 0.3, 2.0][:ds])
-    action = (torch.rand(16, du, generator=g) - 0.5) * 5.0
-    return state, action
+    base = torch.tensor({2: [4.0, 10.0], 4: [3.0, 2.5, 0.3, 3.0]}.get(ds, [2.0] * ds)[:ds])
+    states, actions = [], []
+    for scale, a_scale in ((1.0, 6.0), (0.3, 1.5), (0.05, 0.3), (0.008, 6.0), (1.0, 1.0)):
+        states.append((torch.rand(16, ds, generator=g) - 0.5) * 2.0 * scale * base)
+        actions.append((torch.rand(16, du, generator=g) - 0.5) * 2.0 * a_scale)
+    return torch.cat(states), torch.cat(actions)
 
 
 def _pendulum_host(s, a):
@@ -382,12 +404,21 @@ _CLOSURE_TWINS = [
 
 
 def _fingerprint(dynamics: Callable, cost_func: Callable, ds: int, du: int) -> Optional[Binding]:
+    """Match user closures against the host twins of the built-in models on the probe batch. The device
+    costs depend on the state only, so the user's cost must return the same values for several ``t``, for
+    the terminal-style call (zero action, stale ``t``, mppi.py:318-328) and for a different ``prev_action``:
+    a closure with a time-dependent, terminal or action-dependent cost does not match and is rejected."""
     state, action = _probe_inputs(ds, du)
+    zero = torch.zeros_like(action)
+
+    def info(t, prev):
+        return {"prev_action": prev.clone(), "t": t, "prev_state": state.clone(), "initial_state": state.clone()}
+
     try:
         with torch.no_grad():
-            cost = cost_func(state.clone(), action.clone(), {"prev_action": action.clone(), "t": 0,
-                                                            "prev_state": state.clone(),
-                                                            "initial_state": state.clone()})
+            costs = [cost_func(state.clone(), action.clone(), info(0, action)),
+                     cost_func(state.clone(), action.clone(), info(7, zero)),
+                     cost_func(state.clone(), zero.clone(), info(48, -action))]
             nxt = dynamics(state.clone(), action.clone())  # clones: mountaincar's closure writes through its input
     except Exception:
         return None
@@ -396,7 +427,12 @@ def _fingerprint(dynamics: Callable, cost_func: Callable, ds: int, du: int) -> O
             continue
         want_next, want_cost = twin(state, action)
         if (tuple(nxt.shape) == tuple(want_next.shape) and torch.allclose(nxt, want_next, rtol=1e-4, atol=1e-5)
-                and torch.allclose(cost.reshape(-1), want_cost, rtol=1e-4, atol=1e-5)):
+                and all(torch.allclose(c.reshape(-1), want_cost, rtol=1e-4, atol=1e-5) for c in costs)):
+            import warnings
+
+            warnings.warn(f"dynamics / cost_func match the built-in device model '{cls.name}' on an {len(state)}-row "
+                          "behavioural probe; the solve runs that CUDA model - the Python callables are not "
+                          "executed during rollouts", ModelBindingWarning, stacklevel=4)
             return cls()
     return None
 
@@ -411,8 +447,13 @@ def resolve(dynamics: Callable, cost_func: Callable, dim_state: int, dim_control
             raise ValueError("dynamics and cost_func must come from the same model descriptor")
         binding = d_self
     elif d_self is not None and type(d_self).__name__ == "RacingEnv":
-        need = ("Qc", "Ql", "Qv", "Qo", "Qin", "Qdin", "reference_path", "obstacle_map", "lane_map")
-        if c_self is None or not all(hasattr(c_self, a) for a in need):
+        # The controller is recognised by its class / bound method, NOT by its attributes: example/racing.py
+        # passes `self.cost_function` to MPPI(...) before it has assigned Qc..Qdin, reference_path or the maps
+        # (racing.py:24-58), so none of them exist yet at this point.
+        is_controller = (c_self is not None and c_self is not d_self and
+                         (type(c_self).__name__ == "racing_controller" or
+                          getattr(cost_func, "__name__", "") == "cost_function"))
+        if not is_controller:
             raise NotImplementedError("RacingEnv.dynamics is only supported with racing_controller.cost_function")
         binding = _ReferenceRacing(d_self, c_self)
     elif d_self is not None and type(d_self).__name__ == "GoalInDangerZoneEnv":

@@ -106,21 +106,7 @@ class MPPI(nn.Module):
         self._use_sg_filter, self._sg_window_size, self._sg_poly_order = use_sg_filter, sg_window_size, sg_poly_order
         self._lbps_delta = lbps_delta
         self._lambda_min, self._lambda_max = lambda_min, lambda_max
-
-        # lambda mode dispatch, mppi.py:183-210
-        if lambda_ == "MPO":
-            self._auto_lambda, mode, lam0 = "MPO", _capi.LAMBDA_MPO, 1.0
-        elif lambda_ == "LBPS":
-            self._auto_lambda, mode, lam0 = "LBPS", _capi.LAMBDA_LBPS, 1.0
-        elif lambda_ == "ESSPS":
-            self._auto_lambda, mode, lam0 = "ESSPS", _capi.LAMBDA_ESSPS, 1.0
-        elif isinstance(lambda_, float):
-            self._auto_lambda, mode, lam0 = None, _capi.LAMBDA_FIXED, lambda_
-        else:
-            raise ValueError("lambda_ must be 'MPO', 'LBPS', 'ESSPS', or a float value.")
         self._lambda_init = lambda_
-
-        self._binding = models.resolve(dynamics, cost_func, self._dim_state, self._dim_control)
 
         # sample sharding (one process per GPU)
         self._pg = process_group
@@ -129,36 +115,19 @@ class MPPI(nn.Module):
 
             shard = (dist.get_rank(process_group), dist.get_world_size(process_group))
         self._rank, self._world = shard if shard is not None else (0, 1)
-        lo, hi = shard_bounds(self._num_samples, self._world, self._rank)
-        self._shard_lo, self._local_samples = lo, hi - lo
-        self._essps_target_ess = essps_target_ess if essps_target_ess is not None else num_samples / 10
 
-        cfg = _capi.MppiConfig()
-        cfg.abi_version = _capi.ABI_VERSION
-        cfg.model = self._binding.model_id
-        cfg.horizon, cfg.num_samples = self._horizon, self._local_samples
-        cfg.dim_state, cfg.dim_control = self._dim_state, self._dim_control
-        for d in range(self._dim_control):
-            cfg.u_min[d], cfg.u_max[d], cfg.sigmas[d] = float(u_min[d]), float(u_max[d]), float(sigmas[d])
-        cfg.lambda_mode, cfg.lambda_ = mode, float(lam0)
-        cfg.lbps_delta, cfg.essps_target_ess = float(lbps_delta), float(self._essps_target_ess)
-        cfg.lambda_min, cfg.lambda_max = float(lambda_min), float(lambda_max)
-        cfg.exploration = float(exploration)
-        cfg.use_sg_filter, cfg.sg_window_size, cfg.sg_poly_order = int(bool(use_sg_filter)), sg_window_size, sg_poly_order
-        # SG coefficients exactly as the reference forms them (fp32 pinv of the Vandermonde matrix)
-        self._coeffs = self._savitzky_golay_coeffs(sg_window_size, sg_poly_order)
-        if sg_window_size <= _capi.MAX_SG:
-            cfg.sg_coeffs_given = 1
-            for i, c in enumerate(self._coeffs.tolist()):
-                cfg.sg_coeffs[i] = c
-        cfg.seed, cfg.device = int(seed) & (2**64 - 1), device.index
-        cfg.sample_offset, cfg.total_samples = lo, self._num_samples
-        p = self._binding.params()
-        cfg.num_model_params = len(p)
-        for i, v in enumerate(p):
-            cfg.model_params[i] = float(v)
-        cfg.block_size = block_size
-        self._params_cache = list(p)
+        hs = host_setup(horizon=horizon, num_samples=num_samples, dim_state=dim_state, dim_control=dim_control,
+                        dynamics=dynamics, cost_func=cost_func, u_min=u_min, u_max=u_max, sigmas=sigmas,
+                        lambda_=lambda_, lbps_delta=lbps_delta, essps_target_ess=essps_target_ess,
+                        lambda_min=lambda_min, lambda_max=lambda_max, exploration=exploration,
+                        use_sg_filter=use_sg_filter, sg_window_size=sg_window_size, sg_poly_order=sg_poly_order,
+                        seed=seed, device_index=device.index, shard=(self._rank, self._world),
+                        block_size=block_size)
+        self._auto_lambda, self._binding, self._coeffs = hs.auto_lambda, hs.binding, hs.coeffs
+        self._shard_lo, self._local_samples = hs.shard_lo, hs.local_samples
+        self._essps_target_ess = hs.essps_target_ess
+        self._params_cache = hs.params
+        cfg = hs.cfg
         h = C.c_void_p()
         with torch.cuda.device(device):
             _capi.check(self._lib.mppi_create(C.byref(cfg), C.byref(h)))
@@ -214,13 +183,21 @@ class MPPI(nn.Module):
             on_dev = int(g.is_cuda)
             if g.is_cuda and g.device != self._device:
                 g, on_dev = g.to(self._device), 1
+            # the device lookup is a bit per cell (the reference's grids are exactly 0/1:
+            # obstacle_map_2d.py:79,123,159, lane_map_2d.py:83); a grid carrying other values would silently
+            # lose them in the packing, so it is refused
+            if not bool(((g == 0) | (g == 1)).all()):
+                raise ValueError(f"occupancy grid of map slot {slot} holds values other than 0 and 1; the device "
+                                 "lookup is bit-packed and cannot represent it")
+            if g.is_cuda:  # mppi_set_map packs on the legacy default stream: the producer stream must be done
+                torch.cuda.current_stream(g.device).synchronize()
             with torch.cuda.device(self._device):
                 _capi.check(self._lib.mppi_set_map(self._h, slot, g.data_ptr(), on_dev, g.shape[0], g.shape[1],
                                                    float(cell), float(ox), float(oy)))
         self._map_identity = ident
 
     def _refresh_params(self) -> None:
-        p = self._binding.params()
+        p = self._binding.params(strict=True)
         if p != self._params_cache:
             arr = (C.c_float * len(p))(*p)
             _capi.check(self._lib.mppi_set_model_params(self._h, arr, len(p)))
@@ -442,12 +419,78 @@ class MPPI(nn.Module):
 
     # ------------------------------------------------------------------ reference helpers kept verbatim in behaviour
     def _savitzky_golay_coeffs(self, window_size: int, poly_order: int) -> torch.Tensor:
-        """First row of pinv(vander(-h..h)) in fp32 (mppi.py:568-596), on the host."""
-        if window_size % 2 == 0 or window_size <= poly_order:
-            raise ValueError("window_size must be odd and greater than poly_order.")
-        half = (window_size - 1) // 2
-        idx = torch.arange(-half, half + 1, dtype=torch.float32)
-        return torch.linalg.pinv(torch.vander(idx, N=poly_order + 1, increasing=True))[0]
+        return savitzky_golay_coeffs(window_size, poly_order)
+
+
+class HostSetup:
+    """Everything ``MPPI.__init__`` derives on the host before the first CUDA call."""
+
+    __slots__ = ("auto_lambda", "binding", "coeffs", "shard_lo", "local_samples", "essps_target_ess", "params", "cfg")
+
+
+def host_setup(*, horizon, num_samples, dim_state, dim_control, dynamics, cost_func, u_min, u_max, sigmas, lambda_,
+               lbps_delta=0.01, essps_target_ess=None, lambda_min=0.01, lambda_max=10.0, exploration=0.0,
+               use_sg_filter=False, sg_window_size=5, sg_poly_order=3, seed=42, device_index=0, shard=(0, 1),
+               block_size=0) -> HostSetup:
+    """The host half of ``MPPI.__init__`` (mppi.py:24-210): lambda-mode dispatch, callable -> device-model
+    resolution, the ``MppiConfig`` of the C ABI. Needs no GPU, so the CPU tests drive it with the very objects
+    example/*.py build (tests/test_reference_live.py) - including the solver-before-attributes order of
+    example/racing.py:24-58."""
+    hs = HostSetup()
+    # lambda mode dispatch, mppi.py:183-210
+    if lambda_ == "MPO":
+        hs.auto_lambda, mode, lam0 = "MPO", _capi.LAMBDA_MPO, 1.0
+    elif lambda_ == "LBPS":
+        hs.auto_lambda, mode, lam0 = "LBPS", _capi.LAMBDA_LBPS, 1.0
+    elif lambda_ == "ESSPS":
+        hs.auto_lambda, mode, lam0 = "ESSPS", _capi.LAMBDA_ESSPS, 1.0
+    elif isinstance(lambda_, float):
+        hs.auto_lambda, mode, lam0 = None, _capi.LAMBDA_FIXED, lambda_
+    else:
+        raise ValueError("lambda_ must be 'MPO', 'LBPS', 'ESSPS', or a float value.")
+    hs.binding = models.resolve(dynamics, cost_func, int(dim_state), int(dim_control))
+    rank, world = shard
+    lo, hi = shard_bounds(int(num_samples), world, rank)
+    hs.shard_lo, hs.local_samples = lo, hi - lo
+    hs.essps_target_ess = essps_target_ess if essps_target_ess is not None else num_samples / 10
+
+    cfg = _capi.MppiConfig()
+    cfg.abi_version = _capi.ABI_VERSION
+    cfg.model = hs.binding.model_id
+    cfg.horizon, cfg.num_samples = int(horizon), hs.local_samples
+    cfg.dim_state, cfg.dim_control = int(dim_state), int(dim_control)
+    for d in range(int(dim_control)):
+        cfg.u_min[d], cfg.u_max[d], cfg.sigmas[d] = float(u_min[d]), float(u_max[d]), float(sigmas[d])
+    cfg.lambda_mode, cfg.lambda_ = mode, float(lam0)
+    cfg.lbps_delta, cfg.essps_target_ess = float(lbps_delta), float(hs.essps_target_ess)
+    cfg.lambda_min, cfg.lambda_max = float(lambda_min), float(lambda_max)
+    cfg.exploration = float(exploration)
+    cfg.use_sg_filter, cfg.sg_window_size, cfg.sg_poly_order = int(bool(use_sg_filter)), sg_window_size, sg_poly_order
+    # SG coefficients exactly as the reference forms them (fp32 pinv of the Vandermonde matrix)
+    hs.coeffs = savitzky_golay_coeffs(sg_window_size, sg_poly_order)
+    if sg_window_size <= _capi.MAX_SG:
+        cfg.sg_coeffs_given = 1
+        for i, c in enumerate(hs.coeffs.tolist()):
+            cfg.sg_coeffs[i] = c
+    cfg.seed, cfg.device = int(seed) & (2**64 - 1), int(device_index)
+    cfg.sample_offset, cfg.total_samples = lo, int(num_samples)
+    # strict=False: example/racing.py assigns the cost weights after it built the solver; forward() re-reads
+    p = hs.binding.params(strict=False)
+    cfg.num_model_params = len(p)
+    for i, v in enumerate(p):
+        cfg.model_params[i] = float(v)
+    cfg.block_size = block_size
+    hs.params, hs.cfg = list(p), cfg
+    return hs
+
+
+def savitzky_golay_coeffs(window_size: int, poly_order: int) -> torch.Tensor:
+    """First row of pinv(vander(-h..h)) in fp32 (mppi.py:568-596), on the host."""
+    if window_size % 2 == 0 or window_size <= poly_order:
+        raise ValueError("window_size must be odd and greater than poly_order.")
+    half = (window_size - 1) // 2
+    idx = torch.arange(-half, half + 1, dtype=torch.float32)
+    return torch.linalg.pinv(torch.vander(idx, N=poly_order + 1, increasing=True))[0]
 
 
 def connect_shards_inprocess(solvers) -> None:

@@ -152,3 +152,29 @@ def extract_closures(example: str, names):
     if missing:
         raise KeyError(f"{missing} not found in {path}")
     return [found[n] for n in names]
+
+
+def load_example_with_solver(example: str, solver_cls):
+    """Import example/<example>.py *where it lies* with ``pi_mpc.mppi.MPPI`` replaced by ``solver_cls``
+    (how a user swaps the engine in: another ``pi_mpc`` first on PYTHONPATH). Returns the module object;
+    the reference's own ``pi_mpc`` is restored in ``sys.modules`` afterwards."""
+    import importlib.util
+
+    load_reference()
+    shim = types.ModuleType("pi_mpc")
+    shim_mppi = types.ModuleType("pi_mpc.mppi")
+    shim.MPPI = shim_mppi.MPPI = solver_cls
+    shim.mppi = shim_mppi
+    saved = {k: sys.modules[k] for k in list(sys.modules) if k == "pi_mpc" or k.startswith("pi_mpc.")}
+    for k in saved:
+        del sys.modules[k]
+    sys.modules["pi_mpc"], sys.modules["pi_mpc.mppi"] = shim, shim_mppi
+    try:
+        path = os.path.join(REFERENCE_ROOT, "example", f"{example}.py")
+        spec = importlib.util.spec_from_file_location(f"_dropin_{example}", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        del sys.modules["pi_mpc"], sys.modules["pi_mpc.mppi"]
+        sys.modules.update(saved)
+    return mod

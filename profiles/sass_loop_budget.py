@@ -14,7 +14,8 @@ import re
 import subprocess
 import sys
 
-SYMBOL = "_ZN4mppi12solve_kernelINS_6RacingELb0ELi0EEEvNS_11SolveParamsE"
+SYMBOL = "_ZN4mppi12solve_kernelINS_6RacingELb0ELi0ELi2EEEvNS_11SolveParamsE"  # <Racing, inject=false, kFused, SPT=2>
+SAMPLE_STEPS_PER_ITER = 4  # one Philox chunk per sample = 2 time steps, two samples per thread
 GROUPS = [
     ("fp32 arithmetic (FADD/FMUL/FFMA/FMNMX/FSEL/FSETP)", ("FADD", "FMUL", "FFMA", "FMNMX", "FSEL", "FSETP", "HFMA2")),
     ("integer / logic (IMAD, LOP3, SHF, LEA, IADD3, VIADD, ISETP, MOV)",
@@ -36,7 +37,9 @@ def loop_body(lib):
         m = re.search(r"BRA\s+0x([0-9a-f]+)", text)
         if m and addr - int(m.group(1), 16) > 0x1000:
             loop = (int(m.group(1), 16), addr)
-            return [t for a, t in ins if loop[0] <= a <= loop[1]], loop
+            body = [t for a, t in ins if loop[0] <= a <= loop[1]]
+            if sum(t.startswith(("FFMA2", "FMUL2", "FADD2")) for t in body) >= 40:  # the paired (packed fp32) loop
+                return body, loop
     raise RuntimeError("pass-1 loop not found in " + lib)
 
 

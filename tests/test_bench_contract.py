@@ -17,7 +17,8 @@ def test_reference_arm_prints_the_contract_line():
     assert line["metric"].startswith("MPPI solves/sec") and line["n_gpus"] == 1 and line["gpu_launches"] == 0
     assert line["value"] > 0 and abs(line["ms_per_step"] - 1e3 / line["value"]) < 1e-6 * line["ms_per_step"]
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and "65536/65536" in cb["sample"] and cb["value"] == line["value"]
+    assert cb["kind"] == "port" and 1 <= cb["cores"] <= 32 and "K=65536" in cb["sample"] and cb["value"] == line["value"]
+    assert line["warmup"] >= 1 and set(line["config"]) == {"workload"}  # same `config` dict as the GPU arm prints
     assert line["e2e"] == {"value": line["value"], "unit": "solves/s", "h2d_bytes_per_step": 0,
                            "d2h_bytes_per_step": 0}
     assert "K=65536" in line["config"]["workload"] and "T=80" in line["config"]["workload"]
@@ -34,3 +35,6 @@ def test_gpu_arm_constants_and_fixture():
     assert env["obstacle"].shape == (800, 800) and int(env["obstacle"].sum()) == 18602
     assert int(env["lane"].sum()) == 445529 and tuple(env["center_path"].shape) == (3678, 3)
     assert bench.ncu_traffic() is None or bench.ncu_traffic() > 0
+    # BASELINE.json configs[4]
+    K, T, ds, du, flops, nbytes, h2d, d2h = bench.wl_numbers(bench.WORKLOADS["c5"])
+    assert (K, T, ds, du) == (1048576, 50, 4, 1) and flops == K * T * 52 + K * 20 and (h2d, d2h) == (16, 200 + 816)

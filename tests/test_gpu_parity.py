@@ -286,9 +286,25 @@ def test_bounded_and_general_rollouts_agree_bit_for_bit():
     model2.u_min, model2.u_max = torch.tensor([-2.0, -0.9]), torch.tensor([2.0, 0.9])  # env clamp only
     model2.reference_path_tensor = ref
     general_action, general_states = solver2.forward(env.start_state)
-    assert torch.equal(solver2._costs, bounded_costs)
-    assert torch.equal(general_action, bounded_action)
-    assert torch.equal(general_states, bounded_states)
+    assert solver.launch_info()["block"] * 2 * solver.launch_info()["grid"] >= 2048  # two samples per thread
+    assert solver2.launch_info()["block"] * solver2.launch_info()["grid"] >= 2048
+    assert torch.equal(solver2._costs, bounded_costs)  # every one of the K costs, bit for bit
+    # the two launches differ in geometry (two samples per thread vs one), hence in the summation order of the
+    # weighted mean: same values up to fp32 rounding of the partial sums
+    np.testing.assert_allclose(general_action.cpu().numpy(), bounded_action.cpu().numpy(), rtol=0, atol=2e-6)
+    np.testing.assert_allclose(general_states.cpu().numpy(), bounded_states.cpu().numpy(), rtol=0, atol=2e-5)
+    # a start heading below -pi fails the paired loop's range check: the SAME launch geometry runs the general
+    # loop once per sample; against the general one-sample-per-thread kernel the costs are again bit-identical
+    state = env.start_state.clone()
+    state[2] = -3.5
+    m3, sv3 = build_engine(cfg)
+    m3.reference_path_tensor = ref
+    sv3.forward(state)
+    m4, sv4 = build_engine(cfg)
+    m4.u_min, m4.u_max = torch.tensor([-2.0, -0.9]), torch.tensor([2.0, 0.9])
+    m4.reference_path_tensor = ref
+    sv4.forward(state)
+    assert torch.equal(sv3._costs, sv4._costs)
 
 
 SHARD_CASES = [

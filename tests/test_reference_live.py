@@ -89,3 +89,58 @@ def test_oracle_matches_live_reference_on_a_fresh_seed():
         np.testing.assert_array_equal(tr.state_seq.numpy(), s.numpy())
         assert tr.lam == ref._lambda
         state = s[0, 1].clone()
+
+
+class _HostOnlyMPPI:
+    """Stands in for the engine's MPPI where there is no GPU: runs the real host half of its constructor
+    (mppi_playground_b200.mppi.host_setup: callable resolution + MppiConfig) on whatever the example passes."""
+
+    def __init__(self, **kw):
+        from mppi_playground_b200.mppi import host_setup
+
+        kw.pop("device", None), kw.pop("dtype", None)
+        self._horizon = kw["horizon"]
+        self.setup = host_setup(**kw)
+
+
+def test_real_racing_example_constructs_through_the_dropin_in_its_own_order():
+    """example/racing.py:16-58 builds MPPI(cost_func=self.cost_function, ...) BEFORE it assigns Qc..Qdin,
+    reference_path and the maps: resolution must not depend on those attributes, the
+    constructor must tolerate their absence, and the first solve must see the real values."""
+    from mppi_playground_b200 import _capi
+    from oracle import fixtures as fx
+
+    ns = rh.load_reference()
+    mod = rh.load_example_with_solver("racing", _HostOnlyMPPI)
+    with rh._cwd(rh.REFERENCE_ROOT):
+        env = ns.RacingEnv()
+    ctl = mod.racing_controller(env, debug=False)  # raises NotImplementedError / AttributeError before the fix
+    hs = ctl.solver.setup
+    assert hs.binding.model_id == _capi.MODEL_RACING and hs.cfg.num_model_params == _capi.RACING_NUM_PARAMS
+    assert hs.params[11:] == [0.0] * 6  # the weights did not exist yet: placeholders
+    assert hs.binding.reference_path() is None
+    with pytest.raises(ValueError, match="must be set"):
+        hs.binding.maps()
+    # what forward() reads on the first solve (racing.py:227 set_cost_map, :73-81 reference path)
+    ctl.set_cost_map(env._obstacle_map, env._lane_map)
+    fixture = fx.load_env_racing()
+    assert hs.binding.params(strict=True)[11:] == pytest.approx(fixture.Q)
+    assert len(hs.binding.maps()) == 2
+    ctl.reference_path, _ = ctl.calc_ref_trajectory(env._robot_state, env.racing_center_path, 0, ctl.solver._horizon,
+                                                    DL=0.1, lookahead_distance=3, reference_path_interval=0.85)
+    assert tuple(hs.binding.reference_path().shape) == (26, 4)
+    del ctl.Qc  # a weight that is still missing at solve time is the reference's own AttributeError
+    with pytest.raises(AttributeError):
+        hs.binding.params(strict=True)
+
+
+def test_real_navigation2d_example_arguments_resolve():
+    from mppi_playground_b200 import _capi
+    from mppi_playground_b200.mppi import host_setup
+
+    env, _ = rh.make_navigation2d()
+    hs = host_setup(horizon=30, num_samples=3000, dim_state=3, dim_control=2, dynamics=env.dynamics,
+                    cost_func=env.cost_function, u_min=env.u_min, u_max=env.u_max, sigmas=torch.tensor([0.5, 0.5]),
+                    lambda_="ESSPS")  # example/navigation2d.py:16-27
+    assert hs.binding.model_id == _capi.MODEL_NAVIGATION2D and hs.cfg.lambda_mode == _capi.LAMBDA_ESSPS
+    assert hs.cfg.essps_target_ess == 300.0

@@ -21,6 +21,8 @@ from oracle import fixtures as fx  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--block-size", type=int, default=0)
 ap.add_argument("--solves", type=int, default=30)
+ap.add_argument("--flush", action="store_true", help="write a 192 MiB buffer before the traced solve (cold L2, like "
+                                                     "bench.py's timed steps)")
 a = ap.parse_args()
 env = fx.load_env_racing()
 model, solver = build_engine(bench.CFG, block_size=a.block_size)
@@ -31,6 +33,9 @@ for s in range(a.solves):
     model.reference_path_tensor = ref
     if s == a.solves - 1:
         _capi.check(lib.mppi_block_trace(h, 1, None, 0))
+        if a.flush:
+            torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device="cuda").zero_()
+            torch.cuda.synchronize()
     _, seq = solver.forward(state)
     state = seq[0, 1].cpu()
 info = solver.launch_info()
