@@ -10,6 +10,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <cub/device/device_radix_sort.cuh>
 #include <new>
 #include <string>
@@ -151,6 +153,7 @@ struct MppiHandle {
   float* d_costs = nullptr;
   float* d_block_partials = nullptr;
   float* d_rank_partial = nullptr;
+  float* d_dry = nullptr;  // dummy targets of the finisher block's warm-up pass
   unsigned int* d_counter = nullptr;
   uint32_t* d_map[2] = {nullptr, nullptr};
   bool map_set[2] = {false, false};
@@ -184,7 +187,6 @@ struct MppiHandle {
   bool timing = false;
   unsigned long long* d_trace = nullptr;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
-  std::unordered_map<const void*, unsigned> smem_opt_in;
 };
 
 namespace {
@@ -246,9 +248,14 @@ int launch_solve(MppiHandle* h, const SolveParams& p, int mode, bool inject, cud
     PICK(kReduce);
 #undef PICK
   if (!k) return fail(MPPI_ERR_STATE, "no kernel for this launch geometry");
-  {  // opt in to the large dynamic shared memory once per kernel instantiation (and again if it grows)
-    unsigned& have = h->smem_opt_in[(const void*)k];
-    if (have < g.smem) {
+  {  // opt in to the large dynamic shared memory once per kernel instantiation and device, and again only if
+     // it GROWS: the attribute belongs to the function (per device), not to a handle - a second handle with a
+     // smaller layout must not lower the limit under a first one (its launches would fail: invalid argument)
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, unsigned> opted;
+    std::lock_guard<std::mutex> lock(mu);
+    unsigned& have = opted[{h->device, (const void*)k}];
+    if (have < g.smem && g.smem > 48u * 1024u) {
       CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
       have = g.smem;
     }
@@ -259,7 +266,8 @@ int launch_solve(MppiHandle* h, const SolveParams& p, int mode, bool inject, cud
     CUDA_TRY(cudaEventCreate(&e1));
     CUDA_TRY(cudaEventRecord(e0, st));
   }
-  k<<<g.grid, g.block, g.smem, st>>>(p);
+  // kFused / kReduce: block 0 is the finisher, blocks 1 .. g.grid are the workers
+  k<<<g.grid + (mode != kCosts ? 1 : 0), g.block, g.smem, st>>>(p);
   if (e0) {
     CUDA_TRY(cudaEventRecord(e1, st));
     h->events.emplace_back(e0, e1);
@@ -569,6 +577,7 @@ int mppi_create(const MppiConfig* cfg, MppiHandle** out) {
   ALLOC(h->d_costs, (size_t)K * 4);
   ALLOC(h->d_rank_partial, (size_t)h->P * 4);
   ALLOC(h->d_counter, 16);
+  ALLOC(h->d_dry, dry_scratch_floats(h->E_pad, T, DS, DU) * 4);
   // staging for mppi_solve_host: state | refpath | action | state_seq
   size_t stage_floats = 8 + (size_t)(T + 1) * 4 + (size_t)h->E_pad + (size_t)(T + 1) * DS + 8;
   ALLOC(h->d_stage, stage_floats * 4);
@@ -606,6 +615,7 @@ int mppi_create(const MppiConfig* cfg, MppiHandle** out) {
   b.costs = h->d_costs;
   b.rank_partial = h->d_rank_partial;
   b.counter = h->d_counter;
+  b.dry_scratch = h->d_dry;
   b.key.seed_lo = (uint32_t)cfg->seed;
   b.key.seed_hi = (uint32_t)(cfg->seed >> 32);
   b.lambda_mode = cfg->lambda_mode;
@@ -650,6 +660,7 @@ void mppi_destroy(MppiHandle* h) {
   cudaFree(h->d_block_partials);
   cudaFree(h->d_rank_partial);
   cudaFree(h->d_counter);
+  cudaFree(h->d_dry);
   cudaFree(h->d_map[0]);
   cudaFree(h->d_map[1]);
   cudaFree(h->d_stage);
@@ -1057,7 +1068,7 @@ int32_t mppi_last_launch_count(const MppiHandle* h) { return h ? h->last_launche
 
 int mppi_launch_info(const MppiHandle* h, int32_t* grid, int32_t* block, int32_t* smem_bytes) {
   if (!h) return fail(MPPI_ERR_INVALID, "null handle");
-  if (grid) *grid = h->geo[0].grid;
+  if (grid) *grid = h->geo[0].grid + 1;  // workers + the finisher block (LBPS / ESSPS cost launches: workers only)
   if (block) *block = h->geo[0].block;
   if (smem_bytes) *smem_bytes = (int32_t)h->geo[0].smem;
   return MPPI_OK;
@@ -1074,15 +1085,15 @@ int mppi_map_info(const MppiHandle* h, int32_t slot, int32_t* fast_division, uin
 int mppi_block_trace(MppiHandle* h, int32_t enable, uint64_t* h_out, int32_t max_blocks) {
   if (!h) return fail(MPPI_ERR_INVALID, "null handle");
   ON_DEVICE(h->device);
-  const size_t n = (size_t)((h->cfg.num_samples + 63) / 64) * 8;
+  const size_t n = (size_t)((h->cfg.num_samples + 63) / 64 + 1) * kTraceSlots;  // every worker block + the finisher
   if (enable && !h->d_trace) {
     CUDA_TRY(cudaMalloc((void**)&h->d_trace, n * 8));
     CUDA_TRY(cudaMemset(h->d_trace, 0, n * 8));
   }
   if (h_out && h->d_trace) {
     CUDA_TRY(cudaDeviceSynchronize());
-    size_t blocks = std::min<size_t>((size_t)max_blocks, (size_t)h->geo[0].grid);
-    CUDA_TRY(cudaMemcpy(h_out, h->d_trace, blocks * 8 * 8, cudaMemcpyDeviceToHost));
+    size_t blocks = std::min<size_t>((size_t)max_blocks, (size_t)h->geo[0].grid + 1);
+    CUDA_TRY(cudaMemcpy(h_out, h->d_trace, blocks * kTraceSlots * 8, cudaMemcpyDeviceToHost));
   }
   if (!enable && h->d_trace) {
     cudaFree(h->d_trace);

@@ -305,7 +305,7 @@ struct Navigation2D {  // src/envs/navigation_2d.py:218-279
   // sin/cos of every stage and the position increments are evaluated by T threads at once.
   // scratch: 8 * (T + 9) floats.
   __device__ static __noinline__ void rollout_block(const Ctx& c, const float* state, const float* opt, int T, float* out,
-                                       float* scratch) {
+                                       float* scratch, unsigned long long* trace_row = nullptr) {
     const float* p = c.p->v;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int S = T + 9;  // room for whole groups of 8 (see serial_chain)
@@ -543,7 +543,7 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
   // heading recurrences (speed_heading_chain), sin / cos of all stages in parallel, two threads walk the
   // position recurrences (add + clamp). scratch: 11 * (T + 9) floats.
   __device__ static __noinline__ void rollout_block(const Ctx& c, const float* state, const float* opt, int T, float* out,
-                                       float* scratch) {
+                                       float* scratch, unsigned long long* trace_row = nullptr) {
     const float* p = c.p->v;
     const int tid = threadIdx.x, nt = blockDim.x, S = T + 9;  // room for whole groups of 8 (see serial_chain)
     float *adt = scratch, *tn = adt + S, *vs = tn + S, *cdt = vs + S, *ths = cdt + S, *thw = ths + S, *dx = thw + S,
@@ -557,6 +557,7 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
       tn[t] = bounded ? tan_quarter(st) : tanf(st);
     }
     __syncthreads();
+    stamp_row(trace_row, 10);
     if (tid == 0) {
       // the chain runs in whole groups of 8: stages T .. roundup(T, 8) - 1 see zero increments and write
       // into the padding (S = T + 9 covers index roundup(T, 8)), so the last real speed is re-stored below
@@ -566,6 +567,7 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
         speed_heading_chain<false>(*c.p, state, adt, tn, vs, thw, ths, T);
     }
     __syncthreads();
+    stamp_row(trace_row, 11);
     for (int t = tid; t < T; t += nt) {
       float st, ct;
       sincosf(thw[t], &st, &ct);
@@ -573,6 +575,7 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
       dy[t] = vs[t] * st * p[10];
     }
     __syncthreads();
+    stamp_row(trace_row, 12);
     if (tid == 0 || tid == 32) {
       const bool isx = tid == 0;
       float q = isx ? state[0] : state[1];
@@ -582,6 +585,7 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
       serial_chain(q, dq, qs, T, [lo, hi](float x, float d) { return clampf(x + d, lo, hi); });
     }
     __syncthreads();
+    stamp_row(trace_row, 13);
     for (int t = tid; t <= T; t += nt) {
       out[t * DS + 0] = xs[t];
       out[t * DS + 1] = ys[t];

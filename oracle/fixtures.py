@@ -81,6 +81,23 @@ GOLDEN_CASES = ["mujoco_cartpole", "goal_in_danger_zone", "pendulum_c1", "pendul
                 "navigation2d_essps", "navigation2d_mpo_expl", "racing_sg", "racing_example"]
 
 
+# one case per BASELINE.json size (configs[1..3]), recorded with the reference's native noise draws; the noise is
+# kept as a digest and regenerated (oracle/gen_golden.py:noise_digest, full_size_cases)
+FULL_SIZE_CASES = ["full_cartpole_c2", "full_navigation2d_c3", "full_racing_c4"]
+
+
+def regenerate_noise(case: SimpleNamespace, solver, s: int):
+    """Draw solve ``s``'s noise from the oracle's native sampler (must be called once per solve, in order, on a
+    solver built with the constructor draw burnt) and hold it against the recorded digest. Returns the noise
+    tensor, or None when this host's torch build produces a different normal_() stream than the recording."""
+    noise = solver._draw_noise()
+    flat = noise.numpy().reshape(-1)
+    same = (np.array_equal(noise.numpy()[:4], case.noise_head[s]) and
+            np.array_equal(flat[::4099][:4096], case.noise_sample[s]) and
+            float(flat.astype(np.float64).sum()) == float(case.noise_sum[s]))
+    return noise if same else None
+
+
 def load_case(name: str) -> SimpleNamespace:
     z = np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"))
     cfg = json.loads(str(z["cfg"]))

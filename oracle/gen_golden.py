@@ -51,9 +51,20 @@ class CostRecorder:
         return torch.sum(stage, dim=1) + calls[horizon]
 
 
-def run_case(name, solver, recorder, horizon, state0, advance, n_solves, pre_solve=None, extra_cfg=None, top_n=8):
+def noise_digest(noise: np.ndarray):
+    """What a full-size case keeps of its noise tensor instead of the tensor itself (42 MB per solve at
+    K=65536, T=80): the case is recorded with the reference's NATIVE draws (torch.manual_seed(seed), one
+    constructor draw, one draw per solve - mppi.py:93,146,261), which the oracle's sampler reproduces on the
+    same torch build; the digest (head rows, a strided sample, the fp64 sum) proves a regenerated stream is the
+    recorded one before anything is compared against the recorded outputs."""
+    flat = noise.reshape(-1)
+    return noise[:4].copy(), flat[::4099][:4096].copy(), np.float64(flat.astype(np.float64).sum())
+
+
+def run_case(name, solver, recorder, horizon, state0, advance, n_solves, pre_solve=None, extra_cfg=None, top_n=8,
+             store_noise=True):
     rec = {k: [] for k in ("state", "noise", "costs", "lam", "lam_next", "action_seq", "state_seq", "top_traj",
-                           "top_w", "refpath")}
+                           "top_w", "refpath", "noise_head", "noise_sample", "noise_sum")}
     state = state0.clone()
     for s in range(n_solves):
         if pre_solve is not None:
@@ -61,7 +72,11 @@ def run_case(name, solver, recorder, horizon, state0, advance, n_solves, pre_sol
         lam_before = solver._lambda
         a, ss = solver.forward(state=state.clone())
         rec["state"].append(state.numpy().copy())
-        rec["noise"].append(solver._action_noises.numpy().copy())
+        if store_noise:
+            rec["noise"].append(solver._action_noises.numpy().copy())
+        else:
+            h, sm, tot = noise_digest(solver._action_noises.numpy())
+            rec["noise_head"].append(h), rec["noise_sample"].append(sm), rec["noise_sum"].append(tot)
         rec["costs"].append(recorder.take_total(horizon).numpy().copy())
         mode = getattr(solver, "_auto_lambda", None)
         # lambda the weights were formed with: MPO updates after the weights (mppi.py:376 vs :398)
@@ -81,7 +96,7 @@ def run_case(name, solver, recorder, horizon, state0, advance, n_solves, pre_sol
     print(f"{name}: {os.path.getsize(path) / 1e3:.0f} kB, lam={rec['lam']}")
 
 
-def closure_case(name, example, fn_names, cfg, state0, n_solves=3):
+def closure_case(name, example, fn_names, cfg, state0, n_solves=3, **run_kw):
     ns = rh.load_reference()
     dyn, cost = rh.extract_closures(example, fn_names)
     recorder = CostRecorder(cost)
@@ -93,10 +108,10 @@ def closure_case(name, example, fn_names, cfg, state0, n_solves=3):
         return dyn(state.clone().view(1, -1), a[0].view(1, -1)).view(-1)
 
     run_case(name, solver, recorder, cfg["horizon"], torch.tensor(state0, dtype=torch.float32), advance, n_solves,
-             extra_cfg=dict(cfg, model=example, state0=state0))
+             extra_cfg=dict(cfg, model=example, state0=state0), **run_kw)
 
 
-def nav2d_case(name, cfg, n_solves=3):
+def nav2d_case(name, cfg, n_solves=3, **run_kw):
     env, ns = rh.make_navigation2d()
     recorder = CostRecorder(env.cost_function)
     kw = dict(cfg)
@@ -108,10 +123,10 @@ def nav2d_case(name, cfg, n_solves=3):
         return env.dynamics(state.view(1, -1), u.view(1, -1)).view(-1)
 
     run_case(name, solver, recorder, cfg["horizon"], env._robot_state.clone(), advance, n_solves,
-             extra_cfg=dict(cfg, model="navigation2d"))
+             extra_cfg=dict(cfg, model="navigation2d"), **run_kw)
 
 
-def racing_case(name, cfg, n_solves=3):
+def racing_case(name, cfg, n_solves=3, **run_kw):
     env, ctl, ns = rh.make_racing()
     recorder = CostRecorder(ctl.cost_function)
     kw = dict(cfg)
@@ -129,7 +144,7 @@ def racing_case(name, cfg, n_solves=3):
         return env.dynamics(state.view(1, -1), u.view(1, -1)).view(-1)
 
     run_case(name, ctl.solver, recorder, cfg["horizon"], env._robot_state.clone(), advance, n_solves,
-             pre_solve=pre_solve, extra_cfg=dict(cfg, model="racing"))
+             pre_solve=pre_solve, extra_cfg=dict(cfg, model="racing"), **run_kw)
 
 
 def goal_zone_case(name, cfg, goal, state0, n_solves=3):
@@ -189,9 +204,24 @@ def env_fixtures():
     print("env fixtures written")
 
 
+def full_size_cases():
+    """One recorded case per BASELINE.json size (configs[1], [2], [3]) from the live reference: native noise
+    draws, the noise kept as a digest (see noise_digest), every one of the K costs kept."""
+    closure_case("full_cartpole_c2", "cartpole", ["dynamics", "stage_cost"],
+                 dict(horizon=50, num_samples=8192, dim_state=4, dim_control=1, u_min=[-3.0], u_max=[3.0],
+                      sigmas=[1.0], lambda_=0.001), [0.0, 0.0, 0.05, 0.0], n_solves=2, store_noise=False)
+    nav2d_case("full_navigation2d_c3", dict(horizon=60, num_samples=32768, sigmas=[0.5, 0.5], lambda_="LBPS"),
+               n_solves=2, store_noise=False)
+    racing_case("full_racing_c4", dict(horizon=80, num_samples=65536, sigmas=[0.5, 0.1], lambda_=1.0,
+                                       use_sg_filter=True), n_solves=2, store_noise=False)
+
+
 def main(only=None):
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    if only == "full":
+        full_size_cases()
+        return
     if only is None:
         env_fixtures()
     # BASELINE.json config 1, verbatim: the reference's own CPU-runnable case
@@ -228,4 +258,4 @@ def main(only=None):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else None)  # `extra`: only the later-added models
+    main(sys.argv[1] if len(sys.argv) > 1 else None)  # `extra`: only the later-added models; `full`: BASELINE sizes

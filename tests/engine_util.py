@@ -88,10 +88,12 @@ class ParityStats:
 # action <= 4e-5, state <= 6e-6, lambda (LBPS / ESSPS) <= 1e-5; the bars below are ~10x that.
 TOL = dict(cost_rel=2e-5, flip_frac=2e-3, action=5e-4, state=5e-4, lam_rel=1e-4)
 # MPO: the reference's fp32 autograd gradient carries a rounding term of
-# (ulp(logsumexp)/2) * E_w[c]/tau - several percent of the gradient when c/tau ~ 1e3 - so its own
-# lambda trajectory moves by O(1e-2) under ulp-level changes of the costs; lambda (and what
-# depends on it) is compared at that noise floor.
-TOL_MPO = dict(TOL, lam_rel=2e-2, action=5e-3, state=5e-3)
+# (ulp(logsumexp)/2) * E_w[c]/tau - several percent of the gradient when c/tau ~ 1e3. Its own lambda
+# trajectory moves by 2.7e-3 relative (action_seq by 9e-4) when every stage cost is moved by ONE ulp
+# (tests/test_oracle_golden.py::test_mpo_lambda_moves_under_one_ulp_of_cost_noise, and against the live
+# reference in tests/test_reference_live.py); the engine's costs differ from the reference's CPU path by libm
+# ulps, so lambda (and what depends on it) is compared at 3x that floor.
+TOL_MPO = dict(TOL, lam_rel=8e-3, action=3e-3, state=3e-3)
 
 
 # LBPS: lambda is the argmin of an objective that is flat at its minimum, so fp32 rounding of the

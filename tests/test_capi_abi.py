@@ -108,7 +108,10 @@ def test_pass1_loop_issue_budget_does_not_regress():
     body, _ = mod.loop_body(lib)
     ops = [t.split()[0].split(".")[0] for t in body]
     per = len(body) / mod.SAMPLE_STEPS_PER_ITER
-    assert per <= 135, f"{per} SASS instructions per sample-timestep (round 1: 184 scalar; round 2 paired loop: ~130)"
+    assert per <= 140, f"{per} SASS instructions per sample-timestep (round 1: 184 scalar; round 2 paired loop: 138.5)"
+    # ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 regardless of -fmad=false, which would break the
+    # reference's separate roundings: every packed add must be in the uncontractable fma-by-one form (P2 operator+)
+    assert ops.count("FADD2") == 0, "a plain packed add in the loop: ptxas may have fused a product into it"
     packed = sum(ops.count(k) for k in ("FFMA2", "FMUL2", "FADD2"))
     assert packed >= 120, f"only {packed} packed fp32 instructions (FFMA2/FMUL2/FADD2) in the paired loop"
     assert not {"LDL", "STL", "LD", "ST"} & set(ops), "local/generic memory traffic inside the pass-1 loop"

@@ -144,3 +144,90 @@ def test_real_navigation2d_example_arguments_resolve():
                     lambda_="ESSPS")  # example/navigation2d.py:16-27
     assert hs.binding.model_id == _capi.MODEL_NAVIGATION2D and hs.cfg.lambda_mode == _capi.LAMBDA_ESSPS
     assert hs.cfg.essps_target_ess == 300.0
+
+
+def test_reference_shaped_doubles_carry_what_the_live_objects_carry():
+    """tests/reference_shapes.py stands in for the reference's objects on the GPU box (tests/test_gpu_dropin.py).
+    Here, where the reference is importable, the doubles are held against the real thing: same class names, same
+    attribute values for everything the bindings read, and the bindings produce identical parameter blocks /
+    grids / geometry from either."""
+    import reference_shapes as rs
+    from mppi_playground_b200 import models
+
+    env, ctl, _ = rh.make_racing()
+    d_env = rs.RacingEnv(device="cpu")
+    assert type(d_env).__name__ == type(env).__name__ and rs.racing_controller.__name__ == type(ctl).__name__
+    for name in ("u_min", "u_max", "L", "V_MAX", "racing_center_path", "_robot_state"):
+        np.testing.assert_array_equal(getattr(d_env, name).numpy(), getattr(env, name).numpy(), err_msg=name)
+    for m_name in ("_obstacle_map", "_lane_map"):
+        live, dbl = getattr(env, m_name), getattr(d_env, m_name)
+        assert type(dbl).__name__ == type(live).__name__
+        assert dbl._cell_size == live._cell_size and list(dbl._cell_map_origin) == list(live._cell_map_origin)
+        np.testing.assert_array_equal(dbl._map_torch.numpy(), live._map_torch.numpy())
+        if m_name == "_obstacle_map":
+            assert dbl.x_lim == live.x_lim and dbl.y_lim == live.y_lim
+
+    class _NoSolver:
+        def __init__(self, **kw):
+            self._horizon = kw["horizon"]
+
+    d_ctl = rs.racing_controller(d_env, _NoSolver)
+    d_ctl.set_cost_map(d_env._obstacle_map, d_env._lane_map)
+    live_b = models.resolve(env.dynamics, ctl.cost_function, 4, 2)
+    dbl_b = models.resolve(d_env.dynamics, d_ctl.cost_function, 4, 2)
+    assert type(live_b) is type(dbl_b) and live_b.params() == dbl_b.params()
+    for (g0, *geo0), (g1, *geo1) in zip(live_b.maps(), dbl_b.maps()):
+        assert geo0 == geo1 and torch.equal(g0, g1)
+    # the double's update() produces the reference's own look-ahead path
+    want, ind = ctl.calc_ref_trajectory(env._robot_state, env.racing_center_path, 0, 25, DL=0.1,
+                                        lookahead_distance=3, reference_path_interval=0.85)
+    d_ctl.solver.forward = lambda state: None
+    d_ctl.update(d_env._robot_state, d_env.racing_center_path)
+    np.testing.assert_array_equal(d_ctl.reference_path.numpy(), want.numpy())
+    assert d_ctl.current_path_index == ind
+
+    nav, _ = rh.make_navigation2d()
+    d_nav = rs.Navigation2DEnv(device="cpu")
+    assert type(d_nav).__name__ == type(nav).__name__
+    for name in ("u_min", "u_max", "_goal_pos", "_robot_state"):
+        np.testing.assert_array_equal(getattr(d_nav, name).numpy(), getattr(nav, name).numpy(), err_msg=name)
+    lb = models.resolve(nav.dynamics, nav.cost_function, 3, 2)
+    db = models.resolve(d_nav.dynamics, d_nav.cost_function, 3, 2)
+    assert lb.params() == db.params() and lb.maps()[0][1:] == db.maps()[0][1:]
+    assert torch.equal(lb.maps()[0][0], db.maps()[0][0])
+
+
+def test_live_reference_mpo_lambda_moves_under_one_ulp_of_cost_noise():
+    """The same experiment as tests/test_oracle_golden.py::test_mpo_lambda_moves_under_one_ulp_of_cost_noise, on
+    the LIVE reference's MPPI: one ulp on every stage cost moves the reference's own MPO lambda by > 1e-3."""
+    from types import SimpleNamespace
+
+    from oracle import fixtures as fx
+    from test_oracle_golden import mpo_trajectory_under_ulp_noise
+
+    case = fx.load_case("navigation2d_mpo_expl")
+    env, ns = rh.make_navigation2d()
+    kw = {k: v for k, v in fx.solver_kwargs(case.cfg).items()}
+
+    class _Ref:  # adapts the reference's forward() to the (lam_next, action_seq) record the helper reads
+        def __init__(self, cost):
+            self.m = ns.MPPI(dim_state=3, dim_control=2, dynamics=env.dynamics, cost_func=cost, u_min=env.u_min,
+                             u_max=env.u_max, sigmas=torch.tensor(case.cfg["sigmas"]), **kw)
+
+        def forward(self, state, noise):
+            import unittest.mock as um
+
+            # inject the recorded noise: the reference draws through self._noise_distribution.rsample (mppi.py:261)
+            with um.patch.object(self.m._noise_distribution, "rsample", lambda sample_shape: noise.clone()):
+                a, _ = self.m.forward(state.clone())
+            return SimpleNamespace(lam_next=float(self.m._lambda), action_seq=a.detach())
+
+    def make(wrap):
+        return None, _Ref(wrap(env.cost_function))
+
+    base_l, base_a = mpo_trajectory_under_ulp_noise(make, case, "base")
+    np.testing.assert_array_equal(base_l, case.lam_next)  # the unperturbed run IS the recorded golden run
+    np.testing.assert_array_equal(base_a, case.action_seq)
+    l, a = mpo_trajectory_under_ulp_noise(make, case, "up")
+    assert float(np.max(np.abs(l - base_l) / np.abs(base_l))) > 1e-3
+    assert float(np.max(np.abs(a - base_a))) > 3e-4

@@ -39,19 +39,29 @@ for s in range(a.solves):
     _, seq = solver.forward(state)
     state = seq[0, 1].cpu()
 info = solver.launch_info()
-g = info["grid"]
-buf = (C.c_uint64 * (g * 8))()
+g = info["grid"]  # row 0: the finisher block, rows 1..: the workers
+buf = (C.c_uint64 * (g * 16))()
 _capi.check(lib.mppi_block_trace(h, 1, buf, g))
-t = np.array(buf, dtype=np.uint64).reshape(g, 8).astype(np.int64)
+t = np.array(buf, dtype=np.uint64).reshape(g, 16).astype(np.int64)
 t0 = t[:, 0].min()
 rel = (t - t0) / 1e3
-names = ["start", "staged", "costs", "weights", "partial", "combined", "finished", "pre-rollout"]
 print("launch", info)
-for i, n in enumerate(names):
-    col = rel[:, i][t[:, i] > 0]
+print("workers (blocks 1..):")
+w = rel[1:]
+for i, n in [(0, "start"), (1, "staged"), (2, "costs"), (3, "weights"), (4, "partial")]:
+    col = w[:, i][t[1:, i] > 0]
     if len(col):
-        print(f"{n:9s} n={len(col):4d} min={col.min():8.2f} median={np.median(col):8.2f} max={col.max():8.2f} us")
-d = rel[:, 2] - rel[:, 1]
-print("pass1 (staged->costs) per block: min %.2f median %.2f max %.2f us" % (d.min(), np.median(d), d.max()))
-d = rel[:, 4] - rel[:, 3]
-print("pass2 (weights->partial) per block: min %.2f median %.2f max %.2f us" % (d.min(), np.median(d), d.max()))
+        print(f"  {n:9s} n={len(col):4d} min={col.min():8.2f} median={np.median(col):8.2f} max={col.max():8.2f} us")
+d = w[:, 2] - w[:, 1]
+print("  pass1 (staged->costs) per block: min %.2f median %.2f max %.2f us" % (d.min(), np.median(d), d.max()))
+d = w[:, 4] - w[:, 3]
+print("  pass2 (weights->partial) per block: min %.2f median %.2f max %.2f us" % (d.min(), np.median(d), d.max()))
+print("finisher (block 0):")
+for i, n in [(0, "start"), (1, "warm-up pass over"), (2, "all workers' tickets seen"), (3, "partials in shared memory"),
+             (8, "  combine: header reductions done"), (9, "  combine: numerators done"),
+             (5, "combined"), (7, "pre-rollout (SG, carry done)"), (10, "  rollout: controls / tan done"),
+             (11, "  rollout: speed + heading chain done"), (12, "  rollout: sin / cos done"),
+             (13, "  rollout: position chains done"), (6, "finished")]:
+    if t[0, i] > 0:
+        print(f"  {n:40s} {rel[0, i]:8.2f} us")
+print("  tail after the last worker's partial: %.2f us" % (rel[0, 6] - w[:, 4].max()))
