@@ -32,6 +32,7 @@ constexpr int kMaxPeers = 8;
 constexpr int kMaxSegments = 16;   // combine_partials: threads = segments x float4 columns
 constexpr int kPartialHeader = 8;  // xmax S xmax_tau S_tau Sc_tau cmin cmax pad
 constexpr int kMaxSgWindow = 33;
+constexpr unsigned kRedBytes = 1536;  // block reduction scratch
 constexpr int kTraceSlots = 16;  // %globaltimer stamps per block (mppi_block_trace)
 
 // Scalars carried on the device between solves.
@@ -146,7 +147,7 @@ __host__ __device__ inline SmemLayout make_layout(int n_maps, const unsigned* ma
   L.list_off = o;
   o += (unsigned)n_warps * 32 * 8 * (unsigned)spt;  // (local sample, weight) of the samples with non-zero weight
   L.red_off = o;
-  o += 128 * 8;  // block reduction scratch (up to 4 x 32 doubles)
+  o += kRedBytes;  // block reduction scratch (up to 4 x 32 doubles; combine_partials_small: 4 x 32 floats + 3 x 32 doubles)
   L.misc_off = o;
   o += 256;
   L.total = o;
@@ -251,6 +252,119 @@ __device__ __forceinline__ void block_reduce_n(T (&v)[N], Op op, T identity, voi
 
 constexpr int kCombineChunk = 256;  // partials whose rescale factors are staged at once
 
+// combine_partials for the common case (n <= blockDim, n <= kCombineChunk: one partial per thread in the header
+// stage). Built for latency - this runs in ONE block while every other SM waits: four barriers in all, the
+// numerators accumulate in fp32 (fmaf, <= ~n/segments terms per thread, fixed order) and only the handful of
+// segment sums and the softmax denominators are added in fp64. Deterministic.
+__device__ __forceinline__ void combine_partials_small(const float* __restrict__ parts, int n, int P, int E_pad,
+                                                       Combined* out, double* N, float* scale_buf, void* red,
+                                                       double* seg_buf, unsigned long long* trace_row) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = (nt + 31) >> 5;
+  float* redf = reinterpret_cast<float*>(red);        // [4][32] maxima
+  double* redd = reinterpret_cast<double*>(red) + 64;  // [3][32] sums (bytes 512..1279 of kRedBytes)
+  float4 h0 = make_float4(-INFINITY, 0.f, -INFINITY, 0.f), h1 = make_float4(0.f, INFINITY, -INFINITY, 0.f);
+  if (tid < n) {
+    const float4* q = reinterpret_cast<const float4*>(parts + (size_t)tid * P);
+    h0 = q[0];
+    h1 = q[1];
+  }
+  float mx[4] = {h0.x, h0.z, -h1.y, h1.z};  // xmax, xmax_tau, -cmin, cmax
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx[i] = fmaxf(mx[i], __shfl_xor_sync(kFullMask, mx[i], o));
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) redf[i * 32 + warp] = mx[i];
+  __syncthreads();  // (1)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float r = (lane < nw) ? redf[i * 32 + lane] : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(kFullMask, r, o));
+    mx[i] = r;
+  }
+  const float xm = mx[0], xmt = mx[1];
+  double sums[3] = {0.0, 0.0, 0.0};
+  if (tid < n) {
+    const float sc = expf(h0.x - xm);
+    scale_buf[tid] = sc;
+    sums[0] = (double)h0.y * (double)sc;
+    if (xmt > -INFINITY) {
+      const double st = (double)expf(h0.z - xmt);
+      sums[1] = (double)h0.w * st;
+      sums[2] = (double)h1.x * st;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sums[i] += __shfl_xor_sync(kFullMask, sums[i], o);
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) redd[i * 32 + warp] = sums[i];
+  __syncthreads();  // (2) rescale factors and the per-warp sums are published
+  stamp_row(trace_row, 8);
+  const int n_vec = E_pad / 4;
+  const int n_seg = max(1, min(kMaxSegments, nt / n_vec));
+  const int seg = tid / n_vec, vc = tid - seg * n_vec;
+  if (seg < n_seg) {
+    const int per = (n + n_seg - 1) / n_seg, lo = seg * per, hi = min(n, lo + per);
+    const float* col = parts + kPartialHeader + 4 * vc;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;  // even / odd rows: two independent chains
+    int b = lo;
+    for (; b + 2 <= hi; b += 2) {
+      const float4 x0 = *reinterpret_cast<const float4*>(col + (size_t)b * P);
+      const float4 x1 = *reinterpret_cast<const float4*>(col + (size_t)(b + 1) * P);
+      const float s0 = scale_buf[b], s1 = scale_buf[b + 1];
+      a0.x = fmaf(x0.x, s0, a0.x);
+      a0.y = fmaf(x0.y, s0, a0.y);
+      a0.z = fmaf(x0.z, s0, a0.z);
+      a0.w = fmaf(x0.w, s0, a0.w);
+      a1.x = fmaf(x1.x, s1, a1.x);
+      a1.y = fmaf(x1.y, s1, a1.y);
+      a1.z = fmaf(x1.z, s1, a1.z);
+      a1.w = fmaf(x1.w, s1, a1.w);
+    }
+    if (b < hi) {
+      const float4 x0 = *reinterpret_cast<const float4*>(col + (size_t)b * P);
+      const float s0 = scale_buf[b];
+      a0.x = fmaf(x0.x, s0, a0.x);
+      a0.y = fmaf(x0.y, s0, a0.y);
+      a0.z = fmaf(x0.z, s0, a0.z);
+      a0.w = fmaf(x0.w, s0, a0.w);
+    }
+    double* dst = seg_buf + (size_t)seg * E_pad + 4 * vc;
+    dst[0] = (double)a0.x + (double)a1.x;
+    dst[1] = (double)a0.y + (double)a1.y;
+    dst[2] = (double)a0.z + (double)a1.z;
+    dst[3] = (double)a0.w + (double)a1.w;
+  }
+  __syncthreads();  // (3)
+  stamp_row(trace_row, 9);
+  for (int e = tid; e < E_pad; e += nt) {
+    double a = 0.0;
+    for (int sgm = 0; sgm < n_seg; ++sgm) a += seg_buf[(size_t)sgm * E_pad + e];
+    N[e] = a;
+  }
+  if (tid == 0) {
+    double t[3] = {0.0, 0.0, 0.0};
+    for (int w = 0; w < nw; ++w) {
+      t[0] += redd[w];
+      t[1] += redd[32 + w];
+      t[2] += redd[64 + w];
+    }
+    out->xmax = xm;
+    out->xmax_tau = xmt;
+    out->cmin = -mx[2];
+    out->cmax = mx[3];
+    out->S = t[0];
+    out->S_tau = t[1];
+    out->Sc_tau = t[2];
+  }
+  __syncthreads();  // (4)
+}
+
 // Combine n partials (stride P, rows 32 B aligned) into `out` + N[E_pad] (shared, doubles).
 // Deterministic: fixed traversal order, independent of which block runs it.
 // Two block reductions for the header (maxima, then rescaled sums); the numerators are summed by
@@ -260,6 +374,10 @@ __device__ __noinline__ void combine_partials(const float* __restrict__ parts, i
                                         double* seg_buf /*[kMaxSegments, E_pad]*/,
                                         unsigned long long* trace_row = nullptr) {
   const int tid = threadIdx.x, nt = blockDim.x;
+  if (n <= nt && n <= kCombineChunk && E_pad / 4 <= nt) {
+    combine_partials_small(parts, n, P, E_pad, out, N, scale_buf, red, seg_buf, trace_row);
+    return;
+  }
   // header pass: every thread keeps the header of its first partial in registers so that the common
   // case n <= blockDim costs ONE global round trip for both reductions and the rescale factors
   float4 h0 = make_float4(-INFINITY, 0.f, -INFINITY, 0.f), h1 = make_float4(0.f, INFINITY, -INFINITY, 0.f);
@@ -449,22 +567,27 @@ __device__ __forceinline__ FinishOut dry_outputs(const SolveParams& p) {
 // Everything after the weighted sum (mppi.py:381-458). Runs in ONE block.
 // smem: opt[E], y[(2T-1)*du] floats supplied by the caller. `poll` (dry pass only): returns true when the
 // real work is ready, in which case the remaining stages of the warm-up are skipped.
+// `state` / `mp`: the solve's initial state and the model parameters - the finisher block hands in copies it
+// made in shared memory while the workers were rolling (`prepared`: it also took the nominal / state snapshots
+// and loaded the SG history into ybuf), so that nothing here waits on global or parameter memory.
 template <class M, class Poll>
 __device__ __noinline__ void finish_solve(const SolveParams& p, const FinishOut& o, const Combined& c, const double* N,
-                                          float* opt, float* ybuf, float* tail, bool history_loaded, Poll poll) {
+                                          float* opt, float* ybuf, float* tail, bool prepared, const float* state,
+                                          const ModelParams* mp, Poll poll) {
   // the rollout of the optimal sequence only needs the model parameters (dynamics never read the maps
   // or the reference path); a local context keeps the caller's register-resident one from escaping
   typename M::Ctx ctx{};
-  if constexpr (uses_params<M>()) ctx.p = &p.mp;
+  if constexpr (uses_params<M>()) ctx.p = mp;
   constexpr int DS = M::DS, DU = M::DU;
   const int tid = threadIdx.x, nt = blockDim.x, T = p.T, E = p.E;
   const int H = (T - 1) * DU;
+  const double rS = 1.0 / c.S;  // one division per thread instead of one per entry
   for (int e = tid; e < E; e += nt) {
-    float r = (float)(N[e] / c.S);  // sum_k softmax_k * u_k  (mppi.py:381-384)
+    float r = (float)(N[e] * rS);  // sum_k softmax_k * u_k  (mppi.py:381-384)
     opt[e] = r;
     ybuf[H + e] = r;
   }
-  if (!history_loaded)  // (the solve kernel's finisher fetched it while the workers were rolling)
+  if (!prepared)
     for (int i = tid; i < H; i += nt) ybuf[i] = p.history[i];
   __syncthreads();
   if (p.use_sg) {  // mppi.py:423-443, 598-620
@@ -482,45 +605,51 @@ __device__ __noinline__ void finish_solve(const SolveParams& p, const FinishOut&
     }
     __syncthreads();
   }
-  for (int e = tid; e < E; e += nt) {
-    float a = opt[e];
-    o.action_out[e] = a;
-    o.nominal_snapshot[e] = p.prev_action[e];
-    o.prev_action[e] = a;  // warm start, no time shift (mppi.py:452)
-  }
-  for (int i = tid; i < H; i += nt)  // history = cat(history[1:], opt[0]) (mppi.py:455-458)
-    o.history[i] = (i < H - DU) ? ybuf[i + DU] : opt[i - (H - DU)];
-  if (tid == 32 % nt) {
-    DeviceScalars* sc = o.sc;
-    sc->lambda_used = sc->lambda;
-    sc->S = c.S;
-    sc->xmax = c.xmax;
-    sc->cmin = c.cmin;
-    sc->cmax = c.cmax;
-    if (p.lambda_mode == kLamMPO) mpo_update(p, c, sc);
-  }
-  const float* state = state_of(p);
-  if (tid < DS) o.state_snapshot[tid] = state[tid];
+  // optimal-trajectory rollout (mppi.py:448-449, 508-524) first: it is the long pole; the stores of the
+  // carried state below are issued by warps that have no part in it (or after it)
   if (!o.dry) stamp(p, 7);
   if (o.dry && poll()) return;
-  // optimal-trajectory rollout (mppi.py:448-449, 508-524)
-  if constexpr (M::kParallelTail) {
-    __syncthreads();
-    M::rollout_block(ctx, state, opt, T, o.state_seq_out, tail,
-                     (p.trace && !o.dry) ? p.trace + (size_t)blockIdx.x * kTraceSlots : nullptr);
-  } else if (tid == 0) {
-    float s[DS], seen[DS], u[DU];
-#pragma unroll
-    for (int i = 0; i < DS; ++i) s[i] = state[i];
-    for (int t = 0; t < T; ++t) {
-#pragma unroll
-      for (int d = 0; d < DU; ++d) u[d] = opt[t * DU + d];
-      M::step(ctx, s, u, seen);
-#pragma unroll
-      for (int i = 0; i < DS; ++i) o.state_seq_out[t * DS + i] = seen[i];
+  // the carried state: plain stores (and two scalar reads), done by threads (first, first + stride, ...)
+  auto carry = [&](int first, int stride) {
+    for (int e = first; e < E; e += stride) {
+      float a = opt[e];
+      o.action_out[e] = a;
+      if (!prepared) o.nominal_snapshot[e] = p.prev_action[e];
+      o.prev_action[e] = a;  // warm start, no time shift (mppi.py:452)
     }
+    for (int i = first; i < H; i += stride)  // history = cat(history[1:], opt[0]) (mppi.py:455-458)
+      o.history[i] = (i < H - DU) ? ybuf[i + DU] : opt[i - (H - DU)];
+    if (first == 0) {
+      DeviceScalars* sc = o.sc;
+      sc->lambda_used = sc->lambda;
+      sc->S = c.S;
+      sc->xmax = c.xmax;
+      sc->cmin = c.cmin;
+      sc->cmax = c.cmax;
+      if (p.lambda_mode == kLamMPO) mpo_update(p, c, sc);
+    }
+    if (!prepared && first < DS) o.state_snapshot[first] = state[first];
+  };
+  if constexpr (M::kParallelTail) {
+    // the rollout's spare warps run carry() beside its roles (nothing waits on those stores)
+    M::rollout_block(ctx, state, opt, T, o.state_seq_out, tail,
+                     (p.trace && !o.dry) ? p.trace + (size_t)blockIdx.x * kTraceSlots : nullptr, carry);
+  } else {
+    if (tid == 0) {
+      float s[DS], seen[DS], u[DU];
 #pragma unroll
-    for (int i = 0; i < DS; ++i) o.state_seq_out[T * DS + i] = s[i];
+      for (int i = 0; i < DS; ++i) s[i] = state[i];
+      for (int t = 0; t < T; ++t) {
+#pragma unroll
+        for (int d = 0; d < DU; ++d) u[d] = opt[t * DU + d];
+        M::step(ctx, s, u, seen);
+#pragma unroll
+        for (int i = 0; i < DS; ++i) o.state_seq_out[t * DS + i] = seen[i];
+      }
+#pragma unroll
+      for (int i = 0; i < DS; ++i) o.state_seq_out[T * DS + i] = s[i];
+    }
+    carry(tid, nt);
   }
 }
 struct NoPoll {
@@ -846,8 +975,23 @@ __device__ __noinline__ void finisher_block(const SolveParams& p, const SmemLayo
     mbar_init(bar, 1);
     fence_mbar_init();
   }
-  // the carried SG history (finish_solve reads it from ybuf; nobody writes it before the real finish)
+  // ---- 0. everything the epilogue reads besides the partials, fetched now: the carried SG history (finish_solve
+  // reads it from ybuf; nobody writes it before the real finish), the solve's state and the model parameters
+  // (shared-memory copies), and the snapshots get_top_samples re-rolls from (warm start, state)
   for (int i = tid; i < (p.T - 1) * DU; i += blockDim.x) ybuf[i] = p.history[i];
+  ModelParams* mp_s = reinterpret_cast<ModelParams*>(misc + 16);
+  float* state_s = reinterpret_cast<float*>(misc + 52);
+  {
+    const float* st = state_of(p);
+    if (tid < M::DS) {
+      const float v = st[tid];
+      state_s[tid] = v;
+      p.state_snapshot[tid] = v;
+    }
+    if (tid < 32) mp_s->v[tid] = p.mp.v[tid];
+    if (tid == 32) mp_s->flags = p.mp.flags;
+    for (int e = tid; e < p.E; e += blockDim.x) p.nominal_snapshot[e] = p.prev_action[e];
+  }
   auto workers_done = [&]() -> bool {  // uniform over the block
     __syncthreads();
     if (tid == 0) misc[0] = ld_acquire_gpu(p.counter) >= n_workers ? 1 : 0;
@@ -868,7 +1012,7 @@ __device__ __noinline__ void finisher_block(const SolveParams& p, const SmemLayo
     combine_partials(parts, (int)n_workers, p.P, p.E_pad, comb, Nbuf, scale_buf, red, seg_buf);
     if (!workers_done()) {
       const FinishOut dry = dry_outputs<M>(p);
-      finish_solve<M>(p, dry, *comb, Nbuf, opt, ybuf, tail, true, workers_done);
+      finish_solve<M>(p, dry, *comb, Nbuf, opt, ybuf, tail, true, state_s, mp_s, workers_done);
     }
   }
   stamp(p, 1);
@@ -903,11 +1047,11 @@ __device__ __noinline__ void finisher_block(const SolveParams& p, const SmemLayo
   stamp(p, 5);
   const FinishOut out = real_outputs<M>(p);
   if (p.n_shards == 1) {
-    finish_solve<M>(p, out, *comb, Nbuf, opt, ybuf, tail, true, NoPoll());
+    finish_solve<M>(p, out, *comb, Nbuf, opt, ybuf, tail, true, state_s, mp_s, NoPoll());
   } else if (p.p2p_world > 0) {
     if (exchange_partials(p, *comb, Nbuf)) {
       combine_partials(p.gather_scratch, p.p2p_world, p.P, p.E_pad, comb, Nbuf, scale_buf, red, seg_buf);
-      finish_solve<M>(p, out, *comb, Nbuf, opt, ybuf, tail, true, NoPoll());
+      finish_solve<M>(p, out, *comb, Nbuf, opt, ybuf, tail, true, state_s, mp_s, NoPoll());
     } else {
       poison_outputs<M>(p);  // a peer never arrived: NaN outputs + the error flag, never stale memory
     }
@@ -1226,11 +1370,11 @@ __global__ void __launch_bounds__(256, 1) finish_kernel(const __grid_constant__ 
   float* tail = reinterpret_cast<float*>(seg_buf + (size_t)p.E_pad * kMaxSegments);
   void* red = smem + finish_scratch_core(p.E_pad, p.T, tail_per_step<M>());
   combine_partials(parts, n, p.P, p.E_pad, comb, Nbuf, scale_buf, red, seg_buf);
-  finish_solve<M>(p, real_outputs<M>(p), *comb, Nbuf, opt, ybuf, tail, false, NoPoll());
+  finish_solve<M>(p, real_outputs<M>(p), *comb, Nbuf, opt, ybuf, tail, false, state_of(p), &p.mp, NoPoll());
 }
 
 __host__ __device__ inline unsigned finish_scratch_bytes(int E_pad, int T, int tail_per_step) {
-  return finish_scratch_core(E_pad, T, tail_per_step) + 128 * 8;
+  return finish_scratch_core(E_pad, T, tail_per_step) + kRedBytes;
 }
 
 // ---------------------------------------------------------------------------
@@ -1558,6 +1702,9 @@ __global__ void selftest_kernel(unsigned long long* bad /*[4]*/) {
       b_sc += (__float_as_uint(s0) != __float_as_uint(s1) || __float_as_uint(c0) != __float_as_uint(c1)) ? 1u : 0u;
     }
     if (ax < 9.0f) b_wrap += (__float_as_uint(wrap_angle_bounded(x)) != __float_as_uint(wrap_angle(x))) ? 1u : 0u;
+    if (x > -9.4f && x < 9.0f) b_wrap += (__float_as_uint(wrap_angle_above(x)) != __float_as_uint(wrap_angle(x))) ? 1u : 0u;
+    if (x >= -3.14159274101257324f && x < 9.0f)
+      b_wrap += (__float_as_uint(wrap_angle_nonneg_fast(x)) != __float_as_uint(wrap_angle(x))) ? 1u : 0u;
     if (x >= -3.14159274101257324f && x < 9.0f)
       b_wrap += (__float_as_uint(wrap_angle_nonneg(x)) != __float_as_uint(wrap_angle(x))) ? 1u : 0u;
     {  // paired-sample (P2) forms against the scalar helpers, both lanes: lane 1 carries the neighbouring float

@@ -100,31 +100,66 @@ __device__ __forceinline__ float map_lookup(const MapView& m, float x, float y) 
   return map_value(m, map_cell(x, m.cell, m.ox), map_cell(y, m.cell, m.oy));
 }
 
-// Heading recurrence of the unicycle / bicycle models, one thread; the per-stage increments inc[t] do
-// not depend on the heading, so they are fetched eight at a time ahead of the dependent chain:
-// thw[t] = wrap(ths[t]); ths[t+1] = wrap(thw[t] + inc[t]). Arrays are padded like serial_chain's.
-// kBounded: after the first stage every heading is itself a wrap output (>= -pi), so the inner wrap
-// only needs the upper fold (wrap_angle_nonneg).
+// ---- serial recurrences of the optimal-trajectory rollout (Navigation2D / Racing rollout_block) --------------
+// thw[t] = wrap(ths[t]); ths[t+1] = wrap(thw[t] + cdt[t]). kBounded: every rolled-out heading is itself a
+// wrap output (>= -pi) and the host proved |cdt| < 6 < 2 pi, so the inner wrap only needs the upper fold and
+// the outer one never sees an argument below -3 pi (wrap_angle_above).
 template <bool kBounded>
-__device__ __forceinline__ void heading_chain(float th, const float* inc, float* thw, float* ths, int T) {
+__device__ __forceinline__ void heading_chain_flagged(float th, const float* cdt, float* thw, float* ths,
+                                                             int T, const volatile int* wait_on,
+                                                             volatile int* prog) {
   ths[0] = th;
   bool first = true;
   for (int t0 = 0; t0 < T; t0 += 8) {
+    if (wait_on) wait_progress(wait_on, t0 + 8);
     float cc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) cc[j] = inc[t0 + j];
+    for (int j = 0; j < 8; ++j) cc[j] = cdt[t0 + j];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float w;
-      if (kBounded)
-        w = (first && j == 0) ? wrap_angle_bounded(th) : wrap_angle_nonneg(th);
-      else
+      if (kBounded) {
+        w = wrap_angle_nonneg_fast(th);
+        if (j == 0 && first) w = wrap_angle_bounded(th);  // the solve's initial heading may lie below -pi
+      } else {
         w = wrap_angle(th);
+      }
       thw[t0 + j] = w;
-      th = kBounded ? wrap_angle_bounded(w + cc[j]) : wrap_angle(w + cc[j]);
+      th = kBounded ? wrap_angle_above(w + cc[j]) : wrap_angle(w + cc[j]);
       ths[t0 + j + 1] = th;
     }
     first = false;
+    if (prog) publish_progress(prog, t0 + 8);
+  }
+}
+// `aux(first, stride)` spread over the warps that have no role in a pipelined rollout (5, 7, 8, ...)
+template <class Aux>
+__device__ __forceinline__ void aux_by_spare_warps(int warp, int lane, int nt, Aux aux) {
+  const int n_warps = nt >> 5, spare = 1 + (n_warps - 7);  // warp 5 and warps 7 .. n_warps - 1
+  const int slot = warp == 5 ? 0 : warp - 6;
+  aux(slot * 32 + lane, spare * 32);
+}
+// q[t+1] = clamp(q[t] + dq[t]) for the lanes `lane < 2` of one warp (x: lane 0, y: lane 1); wait_on[0] / [1]:
+// progress of the even / odd groups of increments
+__device__ __forceinline__ void position_chains(int lane, const float* state, const float* dx, const float* dy,
+                                                       float* xs, float* ys, const float* lim, int T,
+                                                       const volatile int* wait_on) {
+  const bool isx = lane == 0;
+  float q = isx ? state[0] : state[1];
+  float* qs = isx ? xs : ys;
+  const float* dq = isx ? dx : dy;
+  const float lo = isx ? lim[0] : lim[2], hi = isx ? lim[1] : lim[3];
+  qs[0] = q;
+  for (int t0 = 0; t0 < T; t0 += 8) {
+    if (wait_on) wait_progress(wait_on + ((t0 >> 3) & 1), t0 + 8);  // even / odd groups: two producer warps
+    float d[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] = dq[t0 + j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      q = clampf(q + d[j], lo, hi);
+      qs[t0 + j + 1] = q;
+    }
   }
 }
 
@@ -301,52 +336,82 @@ struct Navigation2D {  // src/envs/navigation_2d.py:218-279
     return goal + p[11] * occ;  // :271-277
   }
   // Optimal-trajectory rollout by one block (mppi.py:508-524). Same operations on the same values as
-  // T calls of step(); only the schedule differs: the heading chain is the one serial part, the
-  // sin/cos of every stage and the position increments are evaluated by T threads at once.
-  // scratch: 8 * (T + 9) floats.
+  // T calls of step(); only the schedule differs: the roles run concurrently in separate warps, each trailing
+  // the one before through shared-memory progress flags (warp 1 heading recurrence | warps 2, 6 sin / cos +
+  // position increments, alternating groups | warp 3 x and y recurrences | warps 5, 7.. `aux`), see
+  // Racing::rollout_block. scratch: 9 * (T + 9) floats.
+  template <class Aux>
   __device__ static __noinline__ void rollout_block(const Ctx& c, const float* state, const float* opt, int T, float* out,
-                                       float* scratch, unsigned long long* trace_row = nullptr) {
+                                       float* scratch, unsigned long long* trace_row, Aux aux) {
     const float* p = c.p->v;
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int S = T + 9;  // room for whole groups of 8 (see serial_chain)
+    const int S = T + 9;  // the recurrences run in whole groups of 8 stages
     float *wdt = scratch, *ths = wdt + S, *thw = ths + S, *dx = thw + S, *dy = dx + S, *xs = dy + S, *ys = xs + S,
           *vc = ys + S;
+    volatile int* prog = reinterpret_cast<volatile int*>(vc + S);  // [2] heading [3] increments even [4] odd groups
+    const bool bounded = (c.p->flags & kFlagBounded) && state_in_bounds(c, state);
+    const bool pipelined = nt >= 256;  // eight warps: the roles below plus two for `aux`
     for (int t = T + tid; t < S; t += nt) wdt[t] = dx[t] = dy[t] = 0.0f;
+    if (tid < 5) prog[tid] = 0;
     for (int t = tid; t < T; t += nt) {
       vc[t] = clampf(opt[2 * t], p[0], p[1]);
       wdt[t] = clampf(opt[2 * t + 1], p[2], p[3]) * p[10];
     }
     __syncthreads();
-    if (tid == 0) {  // heading: S[t+1].theta = wrap(wrap(S[t].theta) + c_t); thw keeps the inner wrap
-      if ((c.p->flags & kFlagBounded) && state_in_bounds(c, state))
-        heading_chain<true>(state[2], wdt, thw, ths, T);
-      else
-        heading_chain<false>(state[2], wdt, thw, ths, T);
-    }
-    __syncthreads();
-    for (int t = tid; t < T; t += nt) {
+    stamp_row(trace_row, 10);
+    auto increments = [&](int t) {  // thw[t] is a wrap output (|thw| <= pi): sincos_bounded == sincosf there
       float st, ct;
-      sincosf(thw[t], &st, &ct);
+      sincos_bounded(thw[t], &st, &ct);
       dx[t] = vc[t] * ct * p[10];
       dy[t] = vc[t] * st * p[10];
+    };
+    if (pipelined) {
+      const int warp = tid >> 5, lane = tid & 31;
+      if (warp == 1) {
+        if (lane == 0) {  // heading: S[t+1].theta = wrap(wrap(S[t].theta) + c_t); thw keeps the inner wrap
+          if (bounded)
+            heading_chain_flagged<true>(state[2], wdt, thw, ths, T, nullptr, prog + 2);
+          else
+            heading_chain_flagged<false>(state[2], wdt, thw, ths, T, nullptr, prog + 2);
+          stamp_row(trace_row, 12, 32);
+        }
+      } else if (warp == 2 || warp == 6) {
+        const int parity = warp == 2 ? 0 : 1;
+        for (int t0 = 8 * parity; t0 < T; t0 += 16) {
+          if (lane == 0) wait_progress(prog + 2, t0 + 8);
+          __syncwarp();
+          if (lane < 8 && t0 + lane < T) increments(t0 + lane);
+          __syncwarp();
+          if (lane == 0) publish_progress(prog + 3 + parity, t0 + 8);
+        }
+      } else if (warp == 3) {
+        if (lane < 2) position_chains(lane, state, dx, dy, xs, ys, p + 6, T, prog + 3);
+      } else if (warp == 5 || warp >= 7) {
+        aux_by_spare_warps(warp, lane, nt, aux);
+      }
+      __syncthreads();
+      stamp_row(trace_row, 13);
+    } else {
+      if (tid == 0) {
+        if (bounded)
+          heading_chain_flagged<true>(state[2], wdt, thw, ths, T, nullptr, nullptr);
+        else
+          heading_chain_flagged<false>(state[2], wdt, thw, ths, T, nullptr, nullptr);
+      }
+      __syncthreads();
+      for (int t = tid; t < T; t += nt) increments(t);
+      __syncthreads();
+      if (tid < 2) position_chains(tid, state, dx, dy, xs, ys, p + 6, T, nullptr);
+      aux(tid, nt);
+      __syncthreads();
     }
-    __syncthreads();
-    if (tid == 0 || tid == 32) {
-      const bool isx = tid == 0;
-      float q = isx ? state[0] : state[1];
-      float* qs = isx ? xs : ys;
-      const float* dq = isx ? dx : dy;
-      const float lo = isx ? p[6] : p[8], hi = isx ? p[7] : p[9];
-      serial_chain(q, dq, qs, T, [lo, hi](float x, float d) { return clampf(x + d, lo, hi); });
-    }
-    __syncthreads();
     for (int t = tid; t <= T; t += nt) {
       out[t * DS + 0] = xs[t];
       out[t * DS + 1] = ys[t];
       out[t * DS + 2] = ths[t];
     }
   }
-  static constexpr int kTailScratchPerStep = 8;
+  static constexpr int kTailScratchPerStep = 9;
 };
 
 // ---------------------------------------------------------------------------
@@ -494,63 +559,50 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
     in = in + p[16] * (d0 * d0 + d1 * d1);                     // :155
     return path + vel + occ + in;                              // :157
   }
-  // Optimal-trajectory rollout by one block (mppi.py:508-524): the same operations on the same values
-  // as T calls of step(), rescheduled. Serial parts are only the three cheap recurrences (speed:
-  // add+clamp; heading: two angle wraps; position: add+clamp); tan / sin / cos of all T stages run in
-  // parallel in between. scratch: 11 * (T + 9) floats.
-  // speed and heading of every stage by ONE thread, software-pipelined: the speed recurrence
-  // (add + clamp) and the yaw increments it feeds (v tan(steer) / L * dt) run ahead of the heading
-  // recurrence (two wraps per stage), which is the only long dependent chain; increments are fetched
-  // eight stages at a time. Same operations on the same values as T calls of step().
-  template <bool kBounded>
-  __device__ static __forceinline__ void speed_heading_chain(const ModelParams& mp, const float* state, const float* adt,
-                                                             const float* tn, float* vs, float* thw, float* ths,
-                                                             int T) {
-    const float vm = mp.v[5], dt = mp.v[10];
-    float v = state[3], th = state[2];
-    ths[0] = th;
-    bool first = true;
+  // ---- optimal-trajectory rollout by one block (mppi.py:508-524): the same operations on the same values as
+  // T calls of step(), rescheduled. tan of every stage first (parallel); then the roles below run CONCURRENTLY
+  // in separate warps, each trailing the one before through shared-memory progress flags (groups of 8 stages):
+  //   warp 0  speed recurrence v' = clamp(v + a dt) (3 dependent operations per stage)
+  //   warp 4  yaw increments v tan(steer) / L * dt of a group (8 lanes)
+  //   warp 1  heading recurrence (two angle wraps per stage) - the long pole, 9 dependent fp32 operations per
+  //           stage in the bounded form (wrap_angle_nonneg_fast / wrap_angle_above)
+  //   warps 2, 6  sin / cos of the wrapped headings and the position increments, alternating groups (8 lanes)
+  //   warp 3  the x and y recurrences (add + clamp), two lanes
+  //   warps 5, 7.. `aux` (the caller's stores of the carried state), off everybody's critical path
+  // (warp w issues on scheduler w % 4: the heading warp shares its scheduler only with an `aux` warp, never
+  // with a role that spins on a flag)
+  // so the wall time is the heading chain plus a short fill / drain instead of the sum of the phases. Blocks
+  // with fewer than eight warps run the same operations phase by phase. scratch: 11 * (T + 9) floats.
+  __device__ static __forceinline__ void speed_chain(const ModelParams& mp, const float* state, const float* adt,
+                                                     float* vs, int T, volatile int* prog) {
+    const float vm = mp.v[5];
+    float v = state[3];
     for (int t0 = 0; t0 < T; t0 += 8) {
-      float a[8], tq[8], cc[8];
+      float a[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = adt[t0 + j];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        a[j] = adt[t0 + j];
-        tq[j] = tn[t0 + j];
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {  // speed chain of the group first: it only depends on itself
         vs[t0 + j] = v;
-        cc[j] = yaw_rate<kBounded>(mp, v, tq[j]) * dt;
         v = clampf(v + a[j], -vm, vm);
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float w;
-        if (kBounded)
-          w = (first && j == 0) ? wrap_angle_bounded(th) : wrap_angle_nonneg(th);
-        else
-          w = wrap_angle(th);
-        thw[t0 + j] = w;
-        th = kBounded ? wrap_angle_bounded(w + cc[j]) : wrap_angle(w + cc[j]);
-        ths[t0 + j + 1] = th;
-      }
-      first = false;
+      if (prog) publish_progress(prog, t0 + 8);
     }
     if ((T & 7) == 0) vs[T] = v;  // otherwise stage T lies inside the last group and was stored there
   }
-  // Optimal-trajectory rollout by one block (mppi.py:508-524): the same operations on the same values
-  // as T calls of step(), rescheduled: tan of every stage in parallel, then ONE thread walks the speed and
-  // heading recurrences (speed_heading_chain), sin / cos of all stages in parallel, two threads walk the
-  // position recurrences (add + clamp). scratch: 11 * (T + 9) floats.
+  template <class Aux>
   __device__ static __noinline__ void rollout_block(const Ctx& c, const float* state, const float* opt, int T, float* out,
-                                       float* scratch, unsigned long long* trace_row = nullptr) {
+                                       float* scratch, unsigned long long* trace_row, Aux aux) {
     const float* p = c.p->v;
-    const int tid = threadIdx.x, nt = blockDim.x, S = T + 9;  // room for whole groups of 8 (see serial_chain)
+    const int tid = threadIdx.x, nt = blockDim.x, S = T + 9;  // the recurrences run in whole groups of 8 stages
     float *adt = scratch, *tn = adt + S, *vs = tn + S, *cdt = vs + S, *ths = cdt + S, *thw = ths + S, *dx = thw + S,
           *dy = dx + S, *xs = dy + S, *ys = xs + S;
-    (void)cdt;
+    // progress: [0] speed [1] yaw increments [2] heading [3] position increments, even groups [4] odd groups
+    volatile int* prog = reinterpret_cast<volatile int*>(ys + S);
     const bool bounded = (c.p->flags & kFlagBounded) && state_in_bounds(c, state);
-    for (int t = T + tid; t < S; t += nt) adt[t] = tn[t] = dx[t] = dy[t] = 0.0f;
+    const bool pipelined = nt >= 256;  // eight warps: the roles below plus two for `aux`
+    for (int t = T + tid; t < S; t += nt) adt[t] = tn[t] = cdt[t] = dx[t] = dy[t] = 0.0f;
+    if (tid < 5) prog[tid] = 0;
     for (int t = tid; t < T; t += nt) {
       adt[t] = clampf(opt[2 * t], p[0], p[1]) * p[10];
       const float st = clampf(opt[2 * t + 1], p[2], p[3]);
@@ -558,34 +610,75 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
     }
     __syncthreads();
     stamp_row(trace_row, 10);
-    if (tid == 0) {
-      // the chain runs in whole groups of 8: stages T .. roundup(T, 8) - 1 see zero increments and write
-      // into the padding (S = T + 9 covers index roundup(T, 8)), so the last real speed is re-stored below
-      if (bounded)
-        speed_heading_chain<true>(*c.p, state, adt, tn, vs, thw, ths, T);
-      else
-        speed_heading_chain<false>(*c.p, state, adt, tn, vs, thw, ths, T);
-    }
-    __syncthreads();
-    stamp_row(trace_row, 11);
-    for (int t = tid; t < T; t += nt) {
+    auto yaw_increment = [&](int t) {
+      cdt[t] = (bounded ? yaw_rate<true>(*c.p, vs[t], tn[t]) : yaw_rate<false>(*c.p, vs[t], tn[t])) * p[10];
+    };
+    auto increments = [&](int t) {  // thw[t] is a wrap output (|thw| <= pi): sincos_bounded == sincosf there
       float st, ct;
-      sincosf(thw[t], &st, &ct);
+      sincos_bounded(thw[t], &st, &ct);
       dx[t] = vs[t] * ct * p[10];
       dy[t] = vs[t] * st * p[10];
+    };
+    if (pipelined) {
+      const int warp = tid >> 5, lane = tid & 31;
+      if (warp == 0) {
+        if (lane == 0) {
+          speed_chain(*c.p, state, adt, vs, T, prog + 0);
+          stamp_row(trace_row, 11, 0);
+        }
+      } else if (warp == 4) {
+        for (int t0 = 0; t0 < T; t0 += 8) {
+          if (lane == 0) wait_progress(prog + 0, t0 + 8);
+          __syncwarp();
+          if (lane < 8) yaw_increment(t0 + lane);  // (stages T.. of the last group: zero inputs, padding)
+          __syncwarp();
+          if (lane == 0) publish_progress(prog + 1, t0 + 8);
+        }
+      } else if (warp == 1) {
+        if (lane == 0) {
+          const long long c0 = clock64();
+          if (bounded)
+            heading_chain_flagged<true>(state[2], cdt, thw, ths, T, prog + 1, prog + 2);
+          else
+            heading_chain_flagged<false>(state[2], cdt, thw, ths, T, prog + 1, prog + 2);
+          stamp_row(trace_row, 12, 32);
+          if (trace_row) trace_row[15] = (unsigned long long)(clock64() - c0);  // SM cycles of the chain
+        }
+      } else if (warp == 2 || warp == 6) {
+        const int parity = warp == 2 ? 0 : 1;
+        for (int t0 = 8 * parity; t0 < T; t0 += 16) {
+          if (lane == 0) wait_progress(prog + 2, t0 + 8);
+          __syncwarp();
+          if (lane < 8 && t0 + lane < T) increments(t0 + lane);
+          __syncwarp();
+          if (lane == 0) publish_progress(prog + 3 + parity, t0 + 8);
+        }
+        if (parity == 0) stamp_row(trace_row, 14, 64);
+      } else if (warp == 3) {
+        if (lane < 2) position_chains(lane, state, dx, dy, xs, ys, p + 6, T, prog + 3);
+      } else if (warp == 5 || warp >= 7) {
+        aux_by_spare_warps(warp, lane, nt, aux);
+      }
+      __syncthreads();
+      stamp_row(trace_row, 13);
+    } else {
+      if (tid == 0) speed_chain(*c.p, state, adt, vs, T, nullptr);
+      __syncthreads();
+      for (int t = tid; t < T; t += nt) yaw_increment(t);
+      __syncthreads();
+      if (tid == 0) {
+        if (bounded)
+          heading_chain_flagged<true>(state[2], cdt, thw, ths, T, nullptr, nullptr);
+        else
+          heading_chain_flagged<false>(state[2], cdt, thw, ths, T, nullptr, nullptr);
+      }
+      __syncthreads();
+      for (int t = tid; t < T; t += nt) increments(t);
+      __syncthreads();
+      if (tid < 2) position_chains(tid, state, dx, dy, xs, ys, p + 6, T, nullptr);
+      aux(tid, nt);
+      __syncthreads();
     }
-    __syncthreads();
-    stamp_row(trace_row, 12);
-    if (tid == 0 || tid == 32) {
-      const bool isx = tid == 0;
-      float q = isx ? state[0] : state[1];
-      float* qs = isx ? xs : ys;
-      const float* dq = isx ? dx : dy;
-      const float lo = isx ? p[6] : p[8], hi = isx ? p[7] : p[9];
-      serial_chain(q, dq, qs, T, [lo, hi](float x, float d) { return clampf(x + d, lo, hi); });
-    }
-    __syncthreads();
-    stamp_row(trace_row, 13);
     for (int t = tid; t <= T; t += nt) {
       out[t * DS + 0] = xs[t];
       out[t * DS + 1] = ys[t];

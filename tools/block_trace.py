@@ -60,8 +60,13 @@ print("finisher (block 0):")
 for i, n in [(0, "start"), (1, "warm-up pass over"), (2, "all workers' tickets seen"), (3, "partials in shared memory"),
              (8, "  combine: header reductions done"), (9, "  combine: numerators done"),
              (5, "combined"), (7, "pre-rollout (SG, carry done)"), (10, "  rollout: controls / tan done"),
-             (11, "  rollout: speed + heading chain done"), (12, "  rollout: sin / cos done"),
-             (13, "  rollout: position chains done"), (6, "finished")]:
+             (11, "  rollout: speed chain done (warp 0)"), (12, "  rollout: heading chain done (warp 1)"),
+             (14, "  rollout: sin / cos done (warp 2)"), (13, "  rollout: position chains done, block joined"),
+             (6, "finished")]:
     if t[0, i] > 0:
         print(f"  {n:40s} {rel[0, i]:8.2f} us")
 print("  tail after the last worker's partial: %.2f us" % (rel[0, 6] - w[:, 4].max()))
+if t[0, 15] > 0 and t[0, 12] > t[0, 10] > 0:
+    cyc, ns = int(t[0, 15]), int(t[0, 12] - t[0, 10])
+    print(f"  heading chain: {cyc} SM cycles in {ns} ns = {cyc / ns * 1e3:.0f} MHz, {cyc / bench.HORIZON:.1f} cycles per stage")
+
