@@ -527,6 +527,12 @@ __device__ inline void mpo_update(const SolveParams& p, const Combined& c, Devic
   sc->lambda = (double)expf(nrho);  // torch.exp(log_temperature).item()
 }
 
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* ptr) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
+}
+
 // Where finish_solve stores its results: the solve's real outputs and carried state, or - for the finisher
 // block's warm-up pass (see solve_kernel) - dummy targets of the same sizes in global memory.
 struct FinishOut {
@@ -565,15 +571,18 @@ __device__ __forceinline__ FinishOut dry_outputs(const SolveParams& p) {
 }
 
 // Everything after the weighted sum (mppi.py:381-458). Runs in ONE block.
-// smem: opt[E], y[(2T-1)*du] floats supplied by the caller. `poll` (dry pass only): returns true when the
-// real work is ready, in which case the remaining stages of the warm-up are skipped.
+// smem: opt[E], y[(2T-1)*du] floats supplied by the caller. Dry pass only: `poll_counter` / `poll_need` /
+// `poll_flag` - when the counter has reached `poll_need` the real work is ready and the remaining stages of the
+// warm-up are skipped. (Plain arguments, not a callable: the dry and the real pass must run the SAME
+// instantiation of this function, or the warm-up would warm a copy of the code the real pass never executes.)
 // `state` / `mp`: the solve's initial state and the model parameters - the finisher block hands in copies it
 // made in shared memory while the workers were rolling (`prepared`: it also took the nominal / state snapshots
 // and loaded the SG history into ybuf), so that nothing here waits on global or parameter memory.
-template <class M, class Poll>
+template <class M>
 __device__ __noinline__ void finish_solve(const SolveParams& p, const FinishOut& o, const Combined& c, const double* N,
                                           float* opt, float* ybuf, float* tail, bool prepared, const float* state,
-                                          const ModelParams* mp, Poll poll) {
+                                          const ModelParams* mp, const unsigned* poll_counter = nullptr,
+                                          unsigned poll_need = 0, int* poll_flag = nullptr) {
   // the rollout of the optimal sequence only needs the model parameters (dynamics never read the maps
   // or the reference path); a local context keeps the caller's register-resident one from escaping
   typename M::Ctx ctx{};
@@ -608,7 +617,12 @@ __device__ __noinline__ void finish_solve(const SolveParams& p, const FinishOut&
   // optimal-trajectory rollout (mppi.py:448-449, 508-524) first: it is the long pole; the stores of the
   // carried state below are issued by warps that have no part in it (or after it)
   if (!o.dry) stamp(p, 7);
-  if (o.dry && poll()) return;
+  if (o.dry && poll_counter) {  // uniform over the block
+    __syncthreads();
+    if (tid == 0) *poll_flag = ld_acquire_gpu(poll_counter) >= poll_need ? 1 : 0;
+    __syncthreads();
+    if (*poll_flag) return;
+  }
   // the carried state: plain stores (and two scalar reads), done by threads (first, first + stride, ...)
   auto carry = [&](int first, int stride) {
     for (int e = first; e < E; e += stride) {
@@ -652,9 +666,6 @@ __device__ __noinline__ void finish_solve(const SolveParams& p, const FinishOut&
     carry(tid, nt);
   }
 }
-struct NoPoll {
-  __device__ bool operator()() const { return false; }
-};
 
 // ---------------------------------------------------------------------------
 // fused shard exchange over peer memory
@@ -935,12 +946,6 @@ __host__ __device__ constexpr int tail_per_step() {
     return 0;
 }
 
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* ptr) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
-  return v;
-}
-
 // The finisher block of solve_kernel (block 0; the workers are blocks 1 .. gridDim.x - 1).
 //  1. warm-up: combine + finish + optimal-trajectory rollout on dummy data with dummy targets. The epilogue is
 //     ~25 kB of code that runs ONCE per solve in one block; executed cold (bench.py flushes L2 between solves;
@@ -1012,7 +1017,7 @@ __device__ __noinline__ void finisher_block(const SolveParams& p, const SmemLayo
     combine_partials(parts, (int)n_workers, p.P, p.E_pad, comb, Nbuf, scale_buf, red, seg_buf);
     if (!workers_done()) {
       const FinishOut dry = dry_outputs<M>(p);
-      finish_solve<M>(p, dry, *comb, Nbuf, opt, ybuf, tail, true, state_s, mp_s, workers_done);
+      finish_solve<M>(p, dry, *comb, Nbuf, opt, ybuf, tail, true, state_s, mp_s, p.counter, n_workers, misc);
     }
   }
   stamp(p, 1);
@@ -1047,11 +1052,11 @@ __device__ __noinline__ void finisher_block(const SolveParams& p, const SmemLayo
   stamp(p, 5);
   const FinishOut out = real_outputs<M>(p);
   if (p.n_shards == 1) {
-    finish_solve<M>(p, out, *comb, Nbuf, opt, ybuf, tail, true, state_s, mp_s, NoPoll());
+    finish_solve<M>(p, out, *comb, Nbuf, opt, ybuf, tail, true, state_s, mp_s);
   } else if (p.p2p_world > 0) {
     if (exchange_partials(p, *comb, Nbuf)) {
       combine_partials(p.gather_scratch, p.p2p_world, p.P, p.E_pad, comb, Nbuf, scale_buf, red, seg_buf);
-      finish_solve<M>(p, out, *comb, Nbuf, opt, ybuf, tail, true, state_s, mp_s, NoPoll());
+      finish_solve<M>(p, out, *comb, Nbuf, opt, ybuf, tail, true, state_s, mp_s);
     } else {
       poison_outputs<M>(p);  // a peer never arrived: NaN outputs + the error flag, never stale memory
     }
@@ -1370,7 +1375,7 @@ __global__ void __launch_bounds__(256, 1) finish_kernel(const __grid_constant__ 
   float* tail = reinterpret_cast<float*>(seg_buf + (size_t)p.E_pad * kMaxSegments);
   void* red = smem + finish_scratch_core(p.E_pad, p.T, tail_per_step<M>());
   combine_partials(parts, n, p.P, p.E_pad, comb, Nbuf, scale_buf, red, seg_buf);
-  finish_solve<M>(p, real_outputs<M>(p), *comb, Nbuf, opt, ybuf, tail, false, state_of(p), &p.mp, NoPoll());
+  finish_solve<M>(p, real_outputs<M>(p), *comb, Nbuf, opt, ybuf, tail, false, state_of(p), &p.mp);
 }
 
 __host__ __device__ inline unsigned finish_scratch_bytes(int E_pad, int T, int tail_per_step) {
