@@ -10,6 +10,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <cub/device/device_radix_sort.cuh>
@@ -158,6 +160,7 @@ struct MppiHandle {
   uint32_t* d_map[2] = {nullptr, nullptr};
   bool map_set[2] = {false, false};
   unsigned long long fastdiv_mismatches[2] = {0, 0};
+  bool tiny_quotient_ok[2] = {false, false};  // check_tiny_quotient_kernel found no mismatch for this slot
   float proved_wheelbase = -1.0f, wheelbase_rcp = 1.0f;
   bool wheelbase_exact = false;
   // host-call staging (mppi_solve_host)
@@ -184,6 +187,8 @@ struct MppiHandle {
   bool peer_opened[kMaxPeers] = {};
   const float* inline_state = nullptr;  // set for the duration of a host-call solve
   const float* inline_ref = nullptr;
+  unsigned* host_done = nullptr;  // set for the duration of a host-call solve: completion word in h_pinned
+  unsigned host_done_seq = 0;
   bool timing = false;
   unsigned long long* d_trace = nullptr;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
@@ -373,6 +378,8 @@ int make_params(MppiHandle* h, const float* d_state, const float* d_refpath, con
     p.gather_scratch = h->d_gather_scratch;
     p.error_flag = h->d_error_flag;
   }
+  p.host_done = h->host_done;
+  p.host_done_seq = h->host_done_seq;
   p.inline_inputs = 0;
   if (h->inline_state) {
     p.inline_inputs = 1;
@@ -451,14 +458,15 @@ void refresh_model_flags(MppiHandle* h) {
       const double yaw = fabs((double)v[5]) * tan(smax) / (double)v[4] * fabs((double)v[10]);
       if (yaw < 6.0 && clamp_redundant && (flags & kFlagSameMapGeometry) &&
           box_maps_inside(b, 0, v[6], v[7], v[8], v[9]) && b.map_fastdiv[0] && h->wheelbase_exact &&
-          fabsf(b.map_ox[0]) >= 1e-20f && fabsf(b.map_oy[0]) >= 1e-20f)
+          h->tiny_quotient_ok[0] && fabsf(b.map_ox[0]) >= 1e-20f && fabsf(b.map_oy[0]) >= 1e-20f)
         flags |= kFlagBounded;
     }
+    if (v[4] == 1.0f) flags |= kFlagUnitL;
   } else if (h->cfg.model == MPPI_MODEL_NAVIGATION2D) {
     const double wmax = std::max(fabs((double)v[2]), fabs((double)v[3]));
     if (wmax * fabs((double)v[10]) < 6.0 && clamp_redundant && h->map_set[0] &&
-        box_maps_inside(b, 0, v[6], v[7], v[8], v[9]) && b.map_fastdiv[0] && fabsf(b.map_ox[0]) >= 1e-20f &&
-        fabsf(b.map_oy[0]) >= 1e-20f)
+        box_maps_inside(b, 0, v[6], v[7], v[8], v[9]) && b.map_fastdiv[0] && h->tiny_quotient_ok[0] &&
+        fabsf(b.map_ox[0]) >= 1e-20f && fabsf(b.map_oy[0]) >= 1e-20f)
       flags |= kFlagBounded;
   }
   b.mp.flags = flags;
@@ -579,7 +587,7 @@ int mppi_create(const MppiConfig* cfg, MppiHandle** out) {
   ALLOC(h->d_counter, 16);
   ALLOC(h->d_dry, dry_scratch_floats(h->E_pad, T, DS, DU) * 4);
   // staging for mppi_solve_host: state | refpath | action | state_seq
-  size_t stage_floats = 8 + (size_t)(T + 1) * 4 + (size_t)h->E_pad + (size_t)(T + 1) * DS + 8;
+  size_t stage_floats = 8 + (size_t)(T + 1) * 4 + (size_t)h->E_pad + (size_t)(T + 1) * DS + 8 + 16;  // + done word
   ALLOC(h->d_stage, stage_floats * 4);
   if (cudaHostAlloc((void**)&h->h_pinned, stage_floats * 4, cudaHostAllocMapped) != cudaSuccess)
     return cleanup(fail(MPPI_ERR_CUDA, "cudaMallocHost failed"));
@@ -740,6 +748,17 @@ int mppi_set_map(MppiHandle* h, int32_t slot, const float* grid, int32_t on_devi
     b.map_rcp[slot] = rcp;
     b.map_fastdiv[slot] = ok ? 1 : 0;
     h->fastdiv_mismatches[slot] = ok ? 0 : 1;
+    // the paired loop's cell index carries no |x| < 1e-30 guard: prove it for this (cell, origin)
+    h->tiny_quotient_ok[slot] = false;
+    unsigned long long* d_bad = nullptr;
+    unsigned long long bad = 1;
+    if (ok && cudaMalloc((void**)&d_bad, 8) == cudaSuccess) {
+      cudaMemset(d_bad, 0, 8);
+      check_tiny_quotient_kernel<<<148 * 4, 256>>>(cell, rcp, ox, oy, d_bad);
+      if (cudaMemcpy(&bad, d_bad, 8, cudaMemcpyDeviceToHost) != cudaSuccess) bad = 1;
+      cudaFree(d_bad);
+      h->tiny_quotient_ok[slot] = bad == 0;
+    }
   }
   b.map_ox[slot] = ox;
   b.map_oy[slot] = oy;
@@ -801,6 +820,14 @@ int mppi_solve_host(MppiHandle* h, const float* h_state, const float* h_refpath,
   float* d_act = hp + n_state + n_ref;
   float* d_seq = d_act + n_act;
   int rc;
+  // completion word: the finisher block stores the call's sequence number into mapped pinned memory after its
+  // output stores (system-scope fence in between); the host spins on it - a stream synchronisation costs
+  // wake-up latency on a ~60 us solve. A kernel fault never sets it: the bounded spin then falls back to
+  // cudaStreamSynchronize, which reports the error.
+  volatile unsigned* done = reinterpret_cast<volatile unsigned*>(d_seq + n_seq + 8);
+  const unsigned seq = (unsigned)(h->solve_count + 1) | 0x80000000u;
+  h->host_done = const_cast<unsigned*>(done);
+  h->host_done_seq = seq;
   const bool inline_ok = (!h->mi.refpath || n_ref <= (size_t)kInlineRefFloats) &&
                          !(h->cfg.lambda_mode == MPPI_LAMBDA_LBPS || h->cfg.lambda_mode == MPPI_LAMBDA_ESSPS);
   if (inline_ok) {
@@ -816,11 +843,28 @@ int mppi_solve_host(MppiHandle* h, const float* h_state, const float* h_refpath,
       memcpy(hp + n_state, h_refpath, n_ref * 4);
       in_floats += n_ref;
     }
-    CUDA_TRY(cudaMemcpyAsync(h->d_stage, hp, in_floats * 4, cudaMemcpyHostToDevice, st));
+    cudaError_t e = cudaMemcpyAsync(h->d_stage, hp, in_floats * 4, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) {
+      h->host_done = nullptr;
+      return fail(MPPI_ERR_CUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
+    }
     rc = solve_impl(h, h->d_stage, h->mi.refpath ? h->d_stage + n_state : nullptr, nullptr, d_act, d_seq, st);
   }
+  h->host_done = nullptr;
   if (rc) return rc;
-  CUDA_TRY(cudaStreamSynchronize(st));
+  {
+    const auto t0 = std::chrono::steady_clock::now();
+    unsigned spins = 0;
+    while (*done != seq) {
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();
+#endif
+      if ((++spins & 0x3ffu) == 0 &&
+          std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(200)) break;  // slow or faulted kernel
+    }
+    if (*done != seq) CUDA_TRY(cudaStreamSynchronize(st));  // (also surfaces a kernel fault)
+    std::atomic_thread_fence(std::memory_order_acquire);
+  }
   memcpy(h_action_seq, d_act, (size_t)h->E * 4);
   memcpy(h_state_seq, d_seq, n_seq * 4);
   return MPPI_OK;

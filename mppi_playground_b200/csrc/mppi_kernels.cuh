@@ -29,7 +29,7 @@ enum LambdaMode : int { kLamFixed = 0, kLamMPO = 1, kLamLBPS = 2, kLamESSPS = 3 
 
 constexpr int kInlineRefFloats = 512;
 constexpr int kMaxPeers = 8;
-constexpr int kMaxSegments = 16;   // combine_partials: threads = segments x float4 columns
+constexpr int kMaxSegments = 8;    // combine_partials: threads = segments x float4 columns
 constexpr int kPartialHeader = 8;  // xmax S xmax_tau S_tau Sc_tau cmin cmax pad
 constexpr int kMaxSgWindow = 33;
 constexpr unsigned kRedBytes = 1536;  // block reduction scratch
@@ -96,6 +96,8 @@ struct SolveParams {
   int* error_flag;        // set when the exchange times out (mapped pinned host memory: the host polls it)
   unsigned stage_bytes;   // shared-memory landing zone the host reserved for the block partials (0: none)
   float* dry_scratch;     // global dummy targets of the finisher block's warm-up pass (dry_scratch_floats())
+  unsigned* host_done;    // mppi_solve_host: mapped pinned word the finisher sets to host_done_seq when the outputs
+  unsigned host_done_seq; // are in host memory (the host spins on it instead of a stream synchronisation), else null
   int E, E_pad, P;
 };
 
@@ -785,6 +787,7 @@ __device__ __forceinline__ void pin_loop_consts(const SolveParams& p, const type
   constexpr int kHot = sizeof(lc.ctx.hv) / sizeof(float);
 #pragma unroll
   for (int i = 0; i < kHot; ++i) lc.ctx.hv[i] = pin(ctx.p->v[i]);
+  if constexpr (M::kHasHotFlags) lc.ctx.hflags = pin(ctx.p->flags);
   if constexpr (M::kMaps == 1) pin_map(lc.ctx.map);
   if constexpr (M::kMaps == 2) {
     pin_map(lc.ctx.obstacle);
@@ -1076,7 +1079,13 @@ __device__ __noinline__ void finisher_block(const SolveParams& p, const SmemLayo
   }
   __syncthreads();
   stamp(p, 6);
-  if (tid == 0) *p.counter = 0u;
+  if (tid == 0) {
+    *p.counter = 0u;
+    if (p.host_done) {  // every output store of this block happened before the barrier above
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned*>(p.host_done) = p.host_done_seq;
+    }
+  }
 }
 
 // SPT = samples per thread. 2: the launch geometry of the paired bounded loop (host-selected when the model
@@ -1686,6 +1695,23 @@ __global__ void check_fastdiv_kernel(float c, float r, unsigned long long* misma
     float fast = fmaf(fmaf(-q, c, x), r, q);
     float ref = x / c;
     bad += (__float_as_uint(fast) == __float_as_uint(ref)) ? 0u : 1u;
+  }
+  bad = __reduce_add_sync(kFullMask, bad);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, (unsigned long long)bad);
+}
+
+// Proof obligation of the guard-free cell index (map_cell_bounded2): for every x with |x| < kFastDivMin - zero and
+// denormals included - the fast division sequence plus the origin rounds to the same cell as the origin alone.
+__global__ void check_tiny_quotient_kernel(float c, float r, float ox, float oy, unsigned long long* mismatches) {
+  unsigned bad = 0;
+  const unsigned top = __float_as_uint(kFastDivMin);  // magnitudes [0, top) are the unproven range of div_exact
+  const unsigned long long n = 2ull * top, stride = (unsigned long long)gridDim.x * blockDim.x;
+  const int want_x = __float2int_rn(ox), want_y = __float2int_rn(oy);
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float x = __uint_as_float((unsigned)(i >> 1) | ((unsigned)(i & 1ull) << 31));
+    float q = x * r;
+    q = fmaf(fmaf(-q, c, x), r, q);
+    bad += (__float2int_rn(q + ox) != want_x || __float2int_rn(q + oy) != want_y) ? 1u : 0u;
   }
   bad = __reduce_add_sync(kFullMask, bad);
   if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, (unsigned long long)bad);

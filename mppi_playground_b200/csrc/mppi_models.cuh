@@ -86,13 +86,16 @@ __device__ __forceinline__ float map_value_bordered(const MapView& m, int ix, in
   return (float)((w >> (iy & 31)) & 1u);
 }
 
-// map_cell_bounded for two samples: the division sequence is packed, the guard / conversion run per lane.
+// map_cell_bounded for two samples: the division sequence is packed, the conversion runs per lane. No guard for
+// |x| < 1e-30 (where the fast division is not proven): there the sequence yields some |q| <= ~|x| / cell, far
+// below half an ulp of the origin, so q + origin == origin like the guarded form - checked for EVERY such x
+// against this very (cell, origin) by check_tiny_quotient_kernel in mppi_set_map (kFlagBounded requires it).
 __device__ __forceinline__ void map_cell_bounded2(P2 x, const ExactDiv& cell, float origin, int* i0, int* i1) {
   P2 q = x * cell.r;
   q = fma2(fma2(-q, cell.c, x), cell.r, q);
   const P2 qo = q + origin;
-  *i0 = __float2int_rn((fabsf(x.v.x) >= kFastDivMin) ? qo.v.x : origin);
-  *i1 = __float2int_rn((fabsf(x.v.y) >= kFastDivMin) ? qo.v.y : origin);
+  *i0 = __float2int_rn(qo.v.x);
+  *i1 = __float2int_rn(qo.v.y);
 }
 
 // src/envs/obstacle_map_2d.py:168-200 == src/envs/lane_map_2d.py:90-122.
@@ -177,6 +180,7 @@ constexpr int kFlagUnitWheelbase = 2;    // Racing: L == 1.0f, so x / L == x exa
 //                                        sequence can overshoot, so the tail rollout keeps the clamp)
 // The kernel additionally requires the solve's initial heading / speed to be in range (uniform check).
 constexpr int kFlagBounded = 4;
+constexpr int kFlagUnitL = 8;  // Racing: the wheelbase is exactly 1.0f: r / L is r itself, the division is skipped
 
 // ---------------------------------------------------------------------------
 struct Pendulum {  // example/pendulum.py:17-47
@@ -257,6 +261,7 @@ struct MountainCar {  // example/mountaincar.py:17-55
 struct Navigation2D {  // src/envs/navigation_2d.py:218-279
   static constexpr int DS = 3, DU = 2, kMaps = 1;
   static constexpr bool kRefPath = false, kParallelTail = true, kHasBounded = true, kUsesParams = true;
+  static constexpr bool kHasHotFlags = false;
   struct Ctx {
     MapView map;
     const ModelParams* p;  // v_min v_max w_min w_max goal_x goal_y x_lo x_hi y_lo y_hi dt w_obst
@@ -418,12 +423,14 @@ struct Navigation2D {  // src/envs/navigation_2d.py:218-279
 struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
   static constexpr int DS = 4, DU = 2, kMaps = 2;
   static constexpr bool kRefPath = true, kParallelTail = true, kHasBounded = true, kUsesParams = true;
+  static constexpr bool kHasHotFlags = true;
   struct Ctx {
     MapView obstacle, lane;
     const ModelParams* p;  // a_min a_max s_min s_max L v_max x_lo x_hi y_lo y_hi dt Qc Ql Qv Qo Qin Qdin
     const float4* ref;     // per stage t: (x, y, sin yaw, cos yaw) of reference_path[t]
     const float* ref_v;    // per stage t: target speed reference_path[t, 3]
     float hv[18];          // register copy of p->v[0..17] for the bounded pass-1 loop (pin_loop_consts)
+    int hflags;            // register copy of p->flags
   };
   template <bool kBounded>
   __device__ static __forceinline__ const float* params(const Ctx& c) {
@@ -524,9 +531,12 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
     const P2 dx = s[3] * ct;  // :349-352
     const P2 dy = s[3] * st;
     const P2 r = s[3] * tan_quarter2(u[1]);
-    P2 q = r * p[17];  // yaw_rate_hot per lane: exact v tan(steer) / L
-    q = fma2(fma2(-q, p[4], r), p[17], q);
-    const P2 dth((fabsf(r.v.x) >= kFastDivMin) ? q.v.x : r.v.x, (fabsf(r.v.y) >= kFastDivMin) ? q.v.y : r.v.y);
+    P2 dth = r;  // v tan(steer) / L: for L == 1.0f exactly the quotient is r itself
+    if (!(c.hflags & kFlagUnitL)) {  // (uniform over the launch) yaw_rate_hot per lane: exact r / L
+      P2 q = r * p[17];
+      q = fma2(fma2(-q, p[4], r), p[17], q);
+      dth = P2((fabsf(r.v.x) >= kFastDivMin) ? q.v.x : r.v.x, (fabsf(r.v.y) >= kFastDivMin) ? q.v.y : r.v.y);
+    }
     const P2 nx = s[0] + dx * p[10];  // :354-357
     const P2 ny = s[1] + dy * p[10];
     const P2 nv = s[3] + u[0] * p[10];
