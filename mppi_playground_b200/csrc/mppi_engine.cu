@@ -328,8 +328,10 @@ int launch_search(MppiHandle* h, const float* costs, long long n, cudaStream_t s
   q.essps_target = h->cfg.essps_target_ess;
   q.sc = h->d_sc;
   cudaLaunchConfig_t cfg{};
+  // costs in registers for the whole search when they fit (kSearchPerThread per thread), else re-read from L2
+  const bool in_regs = n <= (long long)kSearchCluster * kSearchThreadsReg * kSearchPerThread;
   cfg.gridDim = dim3(kSearchCluster);
-  cfg.blockDim = dim3(1024);
+  cfg.blockDim = dim3(in_regs ? kSearchThreadsReg : kSearchThreadsGlobal);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -339,7 +341,10 @@ int launch_search(MppiHandle* h, const float* costs, long long n, cudaStream_t s
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, lambda_search_kernel, q));
+  if (in_regs)
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, lambda_search_kernel<kSearchPerThread>, q));
+  else
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, lambda_search_kernel<0>, q));
   CUDA_TRY(cudaGetLastError());
   h->last_launches++;
   return MPPI_OK;

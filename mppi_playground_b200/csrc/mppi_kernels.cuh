@@ -1392,65 +1392,107 @@ __host__ __device__ inline unsigned finish_scratch_bytes(int E_pad, int T, int t
 }
 
 // ---------------------------------------------------------------------------
-// LBPS / ESSPS: lambda search on costs[K] (mppi.py:341-370, 526-566). One block;
-// the control flow of scipy's bounded Brent / brentq runs redundantly in every
-// thread in fp64, each objective evaluation is a block-wide reduction.
+// LBPS / ESSPS: lambda search on costs[K] (mppi.py:341-370, 526-566). One thread-block cluster; the control
+// flow of scipy's bounded Brent / brentq runs in fp64 in warp 0 of every CTA (redundantly, identical values),
+// which publishes each trial lambda to its block; every objective evaluation is a cluster-wide reduction
+// (softmax_stats) in which all warps take part.
 // ---------------------------------------------------------------------------
+// ---- one objective evaluation of the lambda search -------------------------------------------------------
+// w = softmax(-c / lambda) in fp32 like the reference; the three sums (sum e, sum e^2, sum e c with
+// e = exp(x - xmax)) are formed in fp32 per thread and per warp, every warp stores its row straight into EVERY
+// CTA's shared memory (distributed shared memory), ONE cluster barrier, and warp 0 of every CTA adds the
+// kSearchCluster * warps rows in a fixed order - identical totals everywhere. fp64 is kept out of everything that
+// runs in more than one warp: on this GPU a warp-wide fp64 instruction issues once per ~16 cycles per scheduler,
+// and the round-1 form (fp64 accumulation per sample, the search bookkeeping redundantly in all 8192 threads)
+// spent 3.5 us per evaluation there.
 struct SearchStats {
   double S, S2, Sc;
 };
-
 constexpr int kSearchCluster = 8;  // CTAs of the lambda search (one thread-block cluster, portable size)
+constexpr int kSearchMaxWarps = 32;
 
-// Cluster-wide sum of `v[N]`: block reduction, then every CTA stores its partial into every CTA's
-// exchange buffer through distributed shared memory and all add the kSearchCluster partials in rank
-// order (identical result everywhere). `phase` alternates the buffer half so that one cluster barrier
-// per call is enough.
-template <int N>
-__device__ __forceinline__ void cluster_sum(double (&v)[N], double* xchg /*[2][kSearchCluster][4]*/, int& phase,
-                                            void* red) {
+struct SearchShared {
+  float4 rows[2][kSearchCluster * kSearchMaxWarps];  // [phase][cta * warps + warp] = (S, S2, Sc, -)
+  float lam;                                         // next lambda, published by warp 0
+  int done;
+};
+
+__device__ __forceinline__ void named_barrier_sync(int id, int n_threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
+
+template <int kPerThread>
+__device__ __forceinline__ SearchStats softmax_stats(const float* __restrict__ costs, long long n,
+                                                     const float (&creg)[kPerThread > 0 ? kPerThread : 1], int n_mine,
+                                                     float lam, float cmin, SearchShared* sh, int& phase) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank(), nblk = cluster.num_blocks();
-  block_reduce_n(v, OpAddD(), 0.0, red);
-  if (threadIdx.x < nblk) {
-    double* remote = cluster.map_shared_rank(xchg, threadIdx.x) + ((size_t)phase * kSearchCluster + rank) * 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  const float xmax = (-cmin) / lam;
+  // (-c) / lam per sample as q = x * r corrected by one residual step (r = RN(1 / lam)): the IEEE quotient in all
+  // but rare last-bit cases, 3 instructions instead of the ~20 of a full division - the evaluation is issue
+  // bound on the 8 SMs of the cluster, and a 1-ulp difference in a few exponents is far below the fp32
+  // rounding of the sums the reference itself forms
+  const float rl = 1.0f / lam;
+  auto term = [&](float c, float& a0, float& a1, float& a2) {
+    const float x = -c;
+    float qd = x * rl;
+    qd = fmaf(fmaf(-qd, lam, x), rl, qd);
+    const float e = expf(qd - xmax);
+    a0 += e;
+    a1 = fmaf(e, e, a1);
+    a2 = fmaf(e, c, a2);
+  };
+  float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f;
+  if constexpr (kPerThread > 0) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) remote[i] = v[i];
+    for (int j = 0; j < kPerThread; ++j)
+      if (j < n_mine) term(creg[j], v0, v1, v2);
+  } else {
+    const long long stride = (long long)nblk * blockDim.x;
+    for (long long i = (long long)rank * blockDim.x + threadIdx.x; i < n; i += stride) term(costs[i], v0, v1, v2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v0 += __shfl_xor_sync(kFullMask, v0, o);
+    v1 += __shfl_xor_sync(kFullMask, v1, o);
+    v2 += __shfl_xor_sync(kFullMask, v2, o);
+  }
+  if (lane < (int)nblk) {
+    float4* remote = cluster.map_shared_rank(&sh->rows[phase][0], lane);
+    remote[rank * nw + warp] = make_float4(v0, v1, v2, 0.0f);
   }
   cluster.sync();
-  const double* mine = xchg + (size_t)phase * kSearchCluster * 4;
+  SearchStats r{0.0, 0.0, 0.0};
+  if (warp == 0) {  // (only warp 0 consumes the totals)
+    // the top of the reduction tree is where fp32 rounding would show (a few large partial sums): the rows are
+    // added as float-float pairs (error-free two-sum), i.e. to ~2^-45 - the per-thread and per-warp levels below
+    // average their independent roundings out over thousands of partials
+    const int n_rows = (int)nblk * nw;
+    float hi[3] = {0.0f, 0.0f, 0.0f}, lo[3] = {0.0f, 0.0f, 0.0f};
+    auto add = [](float& h, float& l, float xh, float xl) {  // (h, l) += (xh, xl)
+      const float s = h + xh, bb = s - h;
+      const float err = (h - (s - bb)) + (xh - bb);
+      h = s;
+      l += err + xl;
+    };
+    for (int i = lane; i < n_rows; i += 32) {
+      const float4 t = sh->rows[phase][i];
+      add(hi[0], lo[0], t.x, 0.0f);
+      add(hi[1], lo[1], t.y, 0.0f);
+      add(hi[2], lo[2], t.z, 0.0f);
+    }
 #pragma unroll
-  for (int i = 0; i < N; ++i) {
-    double a = 0.0;
-    for (unsigned r = 0; r < nblk; ++r) a += mine[r * 4 + i];
-    v[i] = a;
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float oh = __shfl_xor_sync(kFullMask, hi[k], o), ol = __shfl_xor_sync(kFullMask, lo[k], o);
+        add(hi[k], lo[k], oh, ol);
+      }
+    r = SearchStats{(double)hi[0] + (double)lo[0], (double)hi[1] + (double)lo[1], (double)hi[2] + (double)lo[2]};
   }
   phase ^= 1;
-}
-
-__device__ inline SearchStats softmax_stats(const float* __restrict__ costs, long long n, double lambda, float cmin,
-                                            void* red, double* xchg, int& phase) {
-  // w = softmax(-c / lambda) in fp32 like the reference; sums kept in fp64. Each CTA of the cluster
-  // covers an interleaved slice of the costs.
-  namespace cg = cooperative_groups;
-  cg::cluster_group cluster = cg::this_cluster();
-  const long long stride = (long long)cluster.num_blocks() * blockDim.x;
-  const float lam = (float)lambda;
-  const float xmax = (-cmin) / lam;
-  double v[3] = {0.0, 0.0, 0.0};
-  for (long long i = (long long)cluster.block_rank() * blockDim.x + threadIdx.x; i < n; i += stride) {
-    float c = costs[i];
-    float e = expf((-c) / lam - xmax);
-    v[0] += (double)e;
-    v[1] += (double)e * (double)e;
-    v[2] += (double)e * (double)c;
-  }
-  cluster_sum(v, xchg, phase, red);
-  SearchStats r;
-  r.S = v[0];
-  r.S2 = v[1];
-  r.Sc = v[2];
   return r;
 }
 
@@ -1464,39 +1506,80 @@ struct SearchParams {
 
 __device__ inline double dsign(double x) { return (x > 0.0) - (x < 0.0); }
 
-__global__ void __launch_bounds__(1024, 1) lambda_search_kernel(const SearchParams q) {
+constexpr int kSearchThreadsReg = 512, kSearchPerThread = 16;  // register path: K <= 8 * 512 * 16 = 65536
+constexpr int kSearchThreadsGlobal = 1024;
+
+template <int kPerThread>
+__global__ void __launch_bounds__(kPerThread > 0 ? kSearchThreadsReg : kSearchThreadsGlobal, 1)
+    lambda_search_kernel(const SearchParams q) {
   // launched as ONE thread-block cluster of kSearchCluster CTAs (cudaLaunchAttributeClusterDimension)
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
-  __shared__ double red[128];
+  __shared__ double red[2 * 32 * 3];
   __shared__ double xchg[2 * kSearchCluster * 4];
+  __shared__ SearchShared sh;
   int phase = 0;
   float cmin = INFINITY, cmax = -INFINITY;
+  float creg[kPerThread > 0 ? kPerThread : 1];
+  int n_mine = 0;
   cluster.sync();  // every CTA of the cluster is resident before anyone touches remote shared memory
   {
     const long long stride = (long long)cluster.num_blocks() * blockDim.x;
-    for (long long i = (long long)cluster.block_rank() * blockDim.x + threadIdx.x; i < q.n; i += stride) {
-      float c = q.costs[i];
-      cmin = fminf(cmin, c);
-      cmax = fmaxf(cmax, c);
+    const long long first = (long long)cluster.block_rank() * blockDim.x + threadIdx.x;
+    if constexpr (kPerThread > 0) {
+#pragma unroll
+      for (int j = 0; j < kPerThread; ++j) {
+        const long long i = first + (long long)j * stride;
+        creg[j] = (i < q.n) ? q.costs[i] : 0.0f;
+        if (i < q.n) {
+          n_mine = j + 1;
+          cmin = fminf(cmin, creg[j]);
+          cmax = fmaxf(cmax, creg[j]);
+        }
+      }
+    } else {
+      for (long long i = first; i < q.n; i += stride) {
+        float c = q.costs[i];
+        cmin = fminf(cmin, c);
+        cmax = fmaxf(cmax, c);
+      }
     }
     float mm[2] = {-cmin, cmax};
     block_reduce_n(mm, OpMax(), -INFINITY, red);
     if (threadIdx.x < cluster.num_blocks()) {
-      double* remote = cluster.map_shared_rank(xchg, threadIdx.x) + ((size_t)phase * kSearchCluster + cluster.block_rank()) * 4;
+      double* remote = cluster.map_shared_rank(xchg, threadIdx.x) + (size_t)cluster.block_rank() * 4;
       remote[0] = (double)mm[0];
       remote[1] = (double)mm[1];
     }
     cluster.sync();
     float a = -INFINITY, b = -INFINITY;
     for (unsigned r = 0; r < cluster.num_blocks(); ++r) {
-      a = fmaxf(a, (float)xchg[(phase * kSearchCluster + r) * 4 + 0]);
-      b = fmaxf(b, (float)xchg[(phase * kSearchCluster + r) * 4 + 1]);
+      a = fmaxf(a, (float)xchg[r * 4 + 0]);
+      b = fmaxf(b, (float)xchg[r * 4 + 1]);
     }
     cmin = -a;
     cmax = b;
-    phase ^= 1;
   }
+  const int n_threads = (int)blockDim.x;
+  if (threadIdx.x >= 32) {
+    // ---- helper warps: one cluster-wide evaluation per lambda that warp 0 publishes, until it is done
+    for (;;) {
+      named_barrier_sync(1, n_threads);
+      if (sh.done) break;
+      (void)softmax_stats<kPerThread>(q.costs, q.n, creg, n_mine, sh.lam, cmin, &sh, phase);
+    }
+    cluster.sync();  // no CTA may exit while a peer can still address its shared memory
+    return;
+  }
+  // ---- warp 0: the search itself (all 32 lanes redundantly; only this warp touches the fp64 pipe)
+  auto stats_at = [&](double lam) {
+    if (threadIdx.x == 0) {
+      sh.lam = (float)lam;
+      sh.done = 0;
+    }
+    named_barrier_sync(1, n_threads);
+    return softmax_stats<kPerThread>(q.costs, q.n, creg, n_mine, (float)lam, cmin, &sh, phase);
+  };
   int evals = 0;
   double result;
   if (q.mode == kLamLBPS) {
@@ -1504,8 +1587,9 @@ __global__ void __launch_bounds__(1024, 1) lambda_search_kernel(const SearchPara
     const double range = (double)(float)(cmax - cmin);
     const double pen = sqrt((1.0 - q.lbps_delta) / q.lbps_delta);
     auto J = [&](double lam) {
-      SearchStats s = softmax_stats(q.costs, q.n, lam, cmin, red, xchg, phase);
+      const SearchStats s = stats_at(lam);
       ++evals;
+      // sum w^2 and sum w c as the fp32 values torch's .item() hands to Python, the rest in fp64 (mppi.py:526-557)
       double ess = 1.0 / (double)(float)(s.S2 / (s.S * s.S));
       double expected = (double)(float)(s.Sc / s.S);
       return expected + range * pen / sqrt(ess);
@@ -1584,7 +1668,7 @@ __global__ void __launch_bounds__(1024, 1) lambda_search_kernel(const SearchPara
   } else {
     // ESS(lambda) = 1 / sum w^2  (mppi.py:526-532); root of ESS - target (mppi.py:351-370)
     auto F = [&](double lam) {
-      SearchStats s = softmax_stats(q.costs, q.n, lam, cmin, red, xchg, phase);
+      const SearchStats s = stats_at(lam);
       ++evals;
       return 1.0 / (double)(float)(s.S2 / (s.S * s.S)) - q.essps_target;
     };
@@ -1596,7 +1680,8 @@ __global__ void __launch_bounds__(1024, 1) lambda_search_kernel(const SearchPara
     } else {
       // scipy.optimize.brentq, xtol = 2e-12, rtol = 4 eps, maxiter = 100
       const double xtol = 2e-12, rtol = 8.881784197001252e-16;
-      double xpre = q.lambda_min, xcur = q.lambda_max, fpre = F(xpre), fcur = F(xcur);
+      // (brentq evaluates f(a), f(b) first: the very values the reference's own range check just formed)
+      double xpre = q.lambda_min, xcur = q.lambda_max, fpre = f_lo, fcur = f_hi;
       double xblk = 0.0, fblk = 0.0, spre = 0.0, scur = 0.0;
       result = xcur;
       bool done = false;
@@ -1659,10 +1744,14 @@ __global__ void __launch_bounds__(1024, 1) lambda_search_kernel(const SearchPara
       }
     }
   }
-  if (threadIdx.x == 0 && cluster.block_rank() == 0) {
-    q.sc->lambda = result;
-    q.sc->search_evals = evals;
+  if (threadIdx.x == 0) {
+    sh.done = 1;
+    if (cluster.block_rank() == 0) {
+      q.sc->lambda = result;
+      q.sc->search_evals = evals;
+    }
   }
+  named_barrier_sync(1, n_threads);  // releases the helper warps
   cluster.sync();  // no CTA may exit while a peer can still address its shared memory
 }
 

@@ -96,10 +96,13 @@ TOL = dict(cost_rel=2e-5, flip_frac=2e-3, action=5e-4, state=5e-4, lam_rel=1e-4)
 TOL_MPO = dict(TOL, lam_rel=8e-3, action=3e-3, state=3e-3)
 
 
-# LBPS: lambda is the argmin of an objective that is flat at its minimum, so fp32 rounding of the
-# objective (relative ~1e-7) moves the argmin by ~sqrt(2 dJ / J'') ~ 1e-3 relative when the minimum is
-# interior; at the bracket ends (the recorded nav2d case sits at lambda_max) it is exact to ~1e-6.
-TOL_LBPS = dict(TOL, lam_rel=3e-3, action=2e-3, state=2e-3)
+# LBPS: lambda is the argmin of an objective that is flat at its minimum, so rounding of the objective
+# (relative ~1e-8) moves the argmin by ~sqrt(2 dJ / J'') when the minimum is interior: the reference's own
+# lambda moves by 2.3e-3 .. 3.4e-3 relative when every stage cost is moved by ONE ulp
+# (tests/test_oracle_golden.py::test_lbps_lambda_moves_under_one_ulp_of_cost_noise, BASELINE config 3 at full
+# size); the bar is 3x that floor. At the bracket ends (the small recorded nav2d case sits at lambda_max) the
+# engine matches to ~1e-5.
+TOL_LBPS = dict(TOL, lam_rel=1e-2, action=2e-3, state=2e-3)
 
 
 def tol_for(lambda_):
