@@ -76,6 +76,11 @@ typedef enum MppiLambdaMode {
 #define MPPI_GOAL_ZONE_NUM_PARAMS 11
 
 /* Mirrors the keyword arguments of MPPI.__init__ (src/pi_mpc/mppi.py:24-47). */
+/* MppiConfig.flags: force the loop form of racing / navigation2d rollouts (default: picked from the sample
+ * count, see paired_loop_pays in csrc/mppi_engine.cu) */
+#define MPPI_CFG_FORCE_PAIRED 1 /* two samples per thread, packed fp32 */
+#define MPPI_CFG_FORCE_SINGLE 2 /* one sample per thread */
+
 typedef struct MppiConfig {
   int32_t abi_version; /* MPPI_ABI_VERSION */
   int32_t model;       /* MppiModel */
@@ -108,7 +113,7 @@ typedef struct MppiConfig {
   int32_t num_model_params;
   float model_params[MPPI_MAX_MODEL_PARAMS];
   int32_t block_size; /* 0: engine picks */
-  int32_t flags;      /* reserved, 0 */
+  int32_t flags;      /* MPPI_CFG_*: launch-geometry overrides (tests, tuning); 0: engine picks */
 } MppiConfig;
 
 typedef struct MppiHandle MppiHandle;

@@ -17,6 +17,7 @@ MAX_DU, MAX_SG, MAX_PARAMS = 4, 33, 32
 (MODEL_PENDULUM, MODEL_CARTPOLE, MODEL_MOUNTAINCAR, MODEL_NAVIGATION2D, MODEL_RACING, MODEL_CARTPOLE_CONTINUOUS,
  MODEL_GOAL_IN_DANGER_ZONE) = range(7)
 LAMBDA_FIXED, LAMBDA_MPO, LAMBDA_LBPS, LAMBDA_ESSPS = range(4)
+CFG_FORCE_PAIRED, CFG_FORCE_SINGLE = 1, 2  # MppiConfig.flags
 NAV2D_NUM_PARAMS, RACING_NUM_PARAMS, GOAL_ZONE_NUM_PARAMS = 12, 17, 11
 
 

@@ -231,6 +231,22 @@ int pick_block(const MppiHandle* h, int n_maps, const unsigned* map_bytes, unsig
   return best;
 }
 
+// Two samples per thread (packed fp32) or one? Pass 1 is bound by the slower of (a) one warp's dependent chain
+// and (b) the issue slots of the warps that share a scheduler. Measured on the racing model (B200, round 2):
+// 277 vs 184 SASS instructions per warp and time step; a lone warp sustains ~0.34 instructions per cycle, a
+// scheduler ~0.65 (paired: every packed instruction holds the FMA pipe two cycles) / ~0.75 (single).
+// K = 65536: 2 paired warps per scheduler (852 cycles per step) beat 4 single ones (981); at K <= ~49k - a shard
+// of a multi-GPU solve, the K = 4000 of the reference's examples - the single loop's shorter chain wins.
+bool paired_loop_pays(long long K) {
+  auto cycles_per_step = [&](int spt) {
+    const double warps = ceil((double)K / spt / 32.0);
+    const double w = std::max(1.0, ceil(warps / ((kNumSMs - 1) * 4.0)));  // warps on the fullest scheduler
+    const double instr = spt == 2 ? 277.0 : 184.0, ipc_chain = 0.34, ipc_sched = spt == 2 ? 0.65 : 0.75;
+    return std::max(instr / ipc_chain, w * instr / ipc_sched);
+  };
+  return cycles_per_step(2) <= cycles_per_step(1);
+}
+
 template <class M>
 int launch_solve(MppiHandle* h, const SolveParams& p, int mode, bool inject, cudaStream_t st) {
   const MppiHandle::Geometry& g = h->geo[inject ? 1 : 0];
@@ -484,7 +500,9 @@ void refresh_launch_geometry(MppiHandle* h) {
     MppiHandle::Geometry& g = h->geo[v];
     // two samples per thread: the model's bounded loop is available (host-verified flags) and the noise
     // comes from the in-kernel sampler; the kernel re-checks the solve's initial state
-    g.spt = (v == 0 && pair_model && (h->base.mp.flags & kFlagBounded)) ? 2 : 1;
+    const bool want_pair = (h->cfg.flags & MPPI_CFG_FORCE_PAIRED) ||
+                           (!(h->cfg.flags & MPPI_CFG_FORCE_SINGLE) && paired_loop_pays(h->cfg.num_samples));
+    g.spt = (v == 0 && pair_model && (h->base.mp.flags & kFlagBounded) && want_pair) ? 2 : 1;
     int bs = h->cfg.block_size > 0 ? h->cfg.block_size : pick_block(h, h->mi.maps, mb, h->base.prev_action_bytes, g.spt);
     if (bs <= 0) bs = 64;  // nothing fits (oversized grids): the shared-memory check below reports it
     if (g.spt == 2 && bs > 256) bs = 256;

@@ -856,6 +856,63 @@ __device__ __forceinline__ float rollout_cost(const SolveParams& p, const typena
   return total + M::cost(ctx, s, zero, pa, T - 1);  // mppi.py:333-336
 }
 
+// One sample per thread, the bounded loop (racing / navigation2d): rollout_cost<> with the bounded helpers
+// substituted (each proven bit-identical over its whole input range, see mppi_selftest), every loop constant
+// taken from the pinned register copies and whole sampler chunks run without the per-step `t < T` guard.
+// Chosen by the host when the samples are too few to keep two paired warps per scheduler busy (a sharded solve
+// on several GPUs, the K ~ 4000 of the reference's examples): half the dependent chain per warp, twice the warps.
+template <class M>
+__device__ __forceinline__ float rollout_cost_bounded(const SolveParams& p, const LoopConsts<M>& lc,
+                                                      const float* nominal, uint32_t k_lo, uint32_t k_hi) {
+  constexpr int DS = M::DS, DU = M::DU, SPC = Chunking<DU>::kStepsPerChunk;
+  const int T = lc.T;
+  float s[DS], seen[DS];
+  {
+    const float* state = state_of(p);
+#pragma unroll
+    for (int i = 0; i < DS; ++i) s[i] = state[i];
+  }
+  float u[DU], up[DU], upp[DU];
+#pragma unroll
+  for (int d = 0; d < DU; ++d) up[d] = upp[d] = 0.0f;
+  float total = 0.0f;
+  auto one_step = [&](int t, const float* ez) {
+#pragma unroll
+    for (int d = 0; d < DU; ++d) u[d] = clampf(nominal[t * DU + d] + lc.sigma[d] * ez[d], lc.lo[d], lc.hi[d]);
+    float pu[DU];  // info["prev_action"]: U[:, max(t-1, 0)]  (mppi.py:299-304)
+#pragma unroll
+    for (int d = 0; d < DU; ++d) pu[d] = (t == 0) ? u[d] : up[d];
+    M::template step<true>(lc.ctx, s, u, seen);
+    total = total + M::template cost<true>(lc.ctx, seen, u, pu, t);
+#pragma unroll
+    for (int d = 0; d < DU; ++d) {
+      upp[d] = up[d];
+      up[d] = u[d];
+    }
+  };
+  int t0 = 0, chunk = 0;
+  for (; t0 + SPC <= T; t0 += SPC, ++chunk) {
+    float z[4];
+    normal4(p.key, k_lo, k_hi, (uint32_t)chunk, z);
+#pragma unroll
+    for (int j = 0; j < SPC; ++j) one_step(t0 + j, z + j * DU);
+  }
+  if (t0 < T) {
+    float z[4];
+    normal4(p.key, k_lo, k_hi, (uint32_t)chunk, z);
+#pragma unroll
+    for (int j = 0; j < SPC; ++j)
+      if (t0 + j < T) one_step(t0 + j, z + j * DU);
+  }
+  float zero[DU], pa[DU];
+#pragma unroll
+  for (int d = 0; d < DU; ++d) {
+    zero[d] = 0.0f;
+    pa[d] = (T >= 2) ? upp[d] : up[d];
+  }
+  return total + M::template cost<true>(lc.ctx, s, zero, pa, T - 1);  // mppi.py:333-336
+}
+
 // Two samples per thread, the bounded loop (racing / navigation2d): every fp32 add / mul / fma of the two
 // rollouts is ONE packed instruction (P2; sm_100 FADD2 / FMUL2 / FFMA2, each lane rounded like the scalar
 // op), the operations and their order per sample are those of the general loop with the bounded helpers
@@ -1217,6 +1274,16 @@ __global__ void __launch_bounds__(SPT == 2 ? 256 : 512, 1) solve_kernel(const __
           cost[0] = c2[0];
           if (active[1]) cost[1] = c2[1];
         }
+      }
+    }
+    if constexpr (SPT == 1 && !kInject && M::kHasBounded) {
+      // (uniform over the block) the bounded single-sample loop: same flag, the single loop's range check
+      paired = (p.mp.flags & kFlagBounded) && M::state_in_bounds(ctx, state_of(p));
+      if (paired) {
+        LoopConsts<M> lc;
+        pin_loop_consts<M>(p, ctx, lc);  // whole warps: before the per-sample branch
+        if (active[0])
+          cost[0] = rollout_cost_bounded<M>(p, lc, zero_mean[0] ? zero_nominal : nominal, k_lo[0], k_hi[0]);
       }
     }
     if (!paired) {

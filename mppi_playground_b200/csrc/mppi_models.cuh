@@ -65,7 +65,7 @@ __device__ __forceinline__ int map_cell(float x, const ExactDiv& cell, float ori
 __device__ __forceinline__ int map_cell_bounded(float x, const ExactDiv& cell, float origin) {
   float q = x * cell.r;
   q = fmaf(fmaf(-q, cell.c, x), cell.r, q);
-  return __float2int_rn((fabsf(x) >= kFastDivMin) ? q + origin : origin);
+  return __float2int_rn(q + origin);  // (no |x| < 1e-30 guard: see map_cell_bounded2)
 }
 
 __device__ __forceinline__ float map_value(const MapView& m, int ix, int iy) {
@@ -473,7 +473,11 @@ struct Racing {  // src/envs/racing_env.py:327-372 + example/racing.py:110-159
       sincosf(th, &st, &ct);
     float dx = s[3] * ct;  // :349-352
     float dy = s[3] * st;
-    float dth = kBounded ? yaw_rate_hot(p, s[3], tan_quarter(steer)) : yaw_rate<false>(*c.p, s[3], tanf(steer));
+    float dth;
+    if (kBounded)  // (L == 1.0f exactly: v tan(steer) / L is the product itself)
+      dth = (c.hflags & kFlagUnitL) ? s[3] * tan_quarter(steer) : yaw_rate_hot(p, s[3], tan_quarter(steer));
+    else
+      dth = yaw_rate<false>(*c.p, s[3], tanf(steer));
     float nx = s[0] + dx * p[10];  // :354-357
     float ny = s[1] + dy * p[10];
     float nth = kBounded ? wrap_angle_bounded(th + dth * p[10]) : wrap_angle(th + dth * p[10]);

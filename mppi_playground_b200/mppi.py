@@ -69,6 +69,7 @@ class MPPI(nn.Module):
         process_group=None,
         block_size: int = 0,
         fused_exchange: bool = True,
+        samples_per_thread: int = 0,
     ) -> None:
         """Arguments up to ``seed`` are the reference's (mppi.py:24-47).
 
@@ -76,7 +77,9 @@ class MPPI(nn.Module):
         split the K samples over one process per GPU (``num_samples`` stays the
         GLOBAL count); ``block_size`` overrides the launch geometry; ``fused_exchange`` (default) wires the
         ranks' mailboxes over CUDA IPC so that a fixed-lambda / MPO sharded solve is one kernel launch per GPU
-        with the partials exchanged by peer stores over NVLink (False: NCCL all-gather + a finish kernel).
+        with the partials exchanged by peer stores over NVLink (False: NCCL all-gather + a finish kernel);
+        ``samples_per_thread`` (0: engine picks from the sample count; 1 / 2: force the single / paired-sample
+        loop of the racing and navigation2d rollouts - tests and tuning).
         """
         super().__init__()
         u_min, u_max, sigmas = (torch.as_tensor(x) for x in (u_min, u_max, sigmas))
@@ -122,7 +125,7 @@ class MPPI(nn.Module):
                         lambda_min=lambda_min, lambda_max=lambda_max, exploration=exploration,
                         use_sg_filter=use_sg_filter, sg_window_size=sg_window_size, sg_poly_order=sg_poly_order,
                         seed=seed, device_index=device.index, shard=(self._rank, self._world),
-                        block_size=block_size)
+                        block_size=block_size, samples_per_thread=samples_per_thread)
         self._auto_lambda, self._binding, self._coeffs = hs.auto_lambda, hs.binding, hs.coeffs
         self._shard_lo, self._local_samples = hs.shard_lo, hs.local_samples
         self._essps_target_ess = hs.essps_target_ess
@@ -431,7 +434,7 @@ class HostSetup:
 def host_setup(*, horizon, num_samples, dim_state, dim_control, dynamics, cost_func, u_min, u_max, sigmas, lambda_,
                lbps_delta=0.01, essps_target_ess=None, lambda_min=0.01, lambda_max=10.0, exploration=0.0,
                use_sg_filter=False, sg_window_size=5, sg_poly_order=3, seed=42, device_index=0, shard=(0, 1),
-               block_size=0) -> HostSetup:
+               block_size=0, samples_per_thread=0) -> HostSetup:
     """The host half of ``MPPI.__init__`` (mppi.py:24-210): lambda-mode dispatch, callable -> device-model
     resolution, the ``MppiConfig`` of the C ABI. Needs no GPU, so the CPU tests drive it with the very objects
     example/*.py build (tests/test_reference_live.py) - including the solver-before-attributes order of
@@ -480,6 +483,9 @@ def host_setup(*, horizon, num_samples, dim_state, dim_control, dynamics, cost_f
     for i, v in enumerate(p):
         cfg.model_params[i] = float(v)
     cfg.block_size = block_size
+    if samples_per_thread not in (0, 1, 2):
+        raise ValueError("samples_per_thread must be 0 (engine picks), 1 or 2")
+    cfg.flags = {0: 0, 1: _capi.CFG_FORCE_SINGLE, 2: _capi.CFG_FORCE_PAIRED}[samples_per_thread]
     hs.params, hs.cfg = list(p), cfg
     return hs
 

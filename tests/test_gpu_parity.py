@@ -305,10 +305,14 @@ def test_bounded_and_general_rollouts_agree_bit_for_bit():
     cfg = dict(model="racing", horizon=40, num_samples=2048, sigmas=[0.5, 0.1], lambda_=1.0)
     env = fx.load_env_racing()
     ref, _ = eng.racing_reference_path(env.start_state, env.center_path, 0, 40)
-    model, solver = build_engine(cfg)
+    model, solver = build_engine(cfg, samples_per_thread=2)  # the paired (packed fp32) bounded loop
     model.reference_path_tensor = ref
     bounded_action, bounded_states = solver.forward(env.start_state)
     bounded_costs = solver._costs
+    model1, solver1 = build_engine(cfg, samples_per_thread=1)  # the single-sample bounded loop
+    model1.reference_path_tensor = ref
+    solver1.forward(env.start_state)
+    assert torch.equal(solver1._costs, bounded_costs)
 
     model2, solver2 = build_engine(cfg)
     model2.u_min, model2.u_max = torch.tensor([-2.0, -0.9]), torch.tensor([2.0, 0.9])  # env clamp only
@@ -325,7 +329,7 @@ def test_bounded_and_general_rollouts_agree_bit_for_bit():
     # loop once per sample; against the general one-sample-per-thread kernel the costs are again bit-identical
     state = env.start_state.clone()
     state[2] = -3.5
-    m3, sv3 = build_engine(cfg)
+    m3, sv3 = build_engine(cfg, samples_per_thread=2)
     m3.reference_path_tensor = ref
     sv3.forward(state)
     m4, sv4 = build_engine(cfg)
