@@ -215,6 +215,12 @@ def fp32_peak(device_index: int):
 def run_b200(args, rank, local_rank, world):
     import torch.distributed as dist
 
+    # stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner at the first
+    # collective) are sent to stderr for the duration of the run
+    real_stdout = os.dup(1)
+    sys.stdout.flush()
+    os.dup2(2, 1)
+
     from mppi_playground_b200 import _capi
 
     wl = WORKLOADS[args.config]
@@ -441,7 +447,8 @@ def run_b200(args, rank, local_rank, world):
                                  "algorithmic_bytes_per_launch": BYTES, "peak_source": peak_src}},
             "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -218,11 +218,12 @@ int mppi_launch_info(const MppiHandle* h, int32_t* grid, int32_t* block, int32_t
  * used. model_flags: bit0 both racing grids share one geometry, bit1 unit wheelbase. */
 int mppi_map_info(const MppiHandle* h, int32_t slot, int32_t* fast_division, uint64_t* mismatches,
                   int32_t* model_flags);
-/* Profiling aid: with enable != 0 every block of the solve kernel stamps %globaltimer (ns) into a row of 16
- * slots; h_out (may be NULL) receives [min(max_blocks, grid), 16] stamps of the last solve. Row 0 is the
+/* Profiling aid: with enable != 0 every block of the solve kernel stamps %globaltimer (ns) into a row of 24
+ * slots; h_out (may be NULL) receives [min(max_blocks, grid), 24] stamps of the last solve. Row 0 is the
  * finisher block (0 start, 1 warm-up pass over, 2 all workers' tickets seen, 3 partials in shared memory,
  * 8-9 inside the combine, 5 combined, 7 SG / carry done, 10-13 inside the optimal-trajectory rollout,
- * 6 finished); rows 1.. are the worker blocks (0 start, 1 inputs staged, 2 costs done, 3 weights done,
+ * 6 finished; sharded fused solves: 16 exchange entered, 17 partial sent to the peers, 18 all peers' flags seen,
+ * 19 gathered); rows 1.. are the worker blocks (0 start, 1 inputs staged, 2 costs done, 3 weights done,
  * 4 partial written). Unused slots keep 0. */
 int mppi_block_trace(MppiHandle* h, int32_t enable, uint64_t* h_out, int32_t max_blocks);
 /* Exhaustive device self-test of the bounded arithmetic helpers against the general ones, over every

@@ -33,7 +33,7 @@ constexpr int kMaxSegments = 8;    // combine_partials: threads = segments x flo
 constexpr int kPartialHeader = 8;  // xmax S xmax_tau S_tau Sc_tau cmin cmax pad
 constexpr int kMaxSgWindow = 33;
 constexpr unsigned kRedBytes = 1536;  // block reduction scratch
-constexpr int kTraceSlots = 16;  // %globaltimer stamps per block (mppi_block_trace)
+constexpr int kTraceSlots = 24;  // %globaltimer stamps per block (mppi_block_trace)
 
 // Scalars carried on the device between solves.
 struct DeviceScalars {
@@ -694,6 +694,7 @@ __device__ __forceinline__ float ld_volatile(const float* ptr) {
 // reach solve s+2 after every rank published s+1, i.e. after every rank finished reading solve s.
 __device__ inline bool exchange_partials(const SolveParams& p, const Combined& c, const double* N) {
   const int tid = threadIdx.x, nt = blockDim.x, G = p.p2p_world, P = p.P;
+  stamp(p, 16);
   const unsigned seq = p.p2p_seq, parity = seq & 1u;
   const size_t slot = ((size_t)parity * kMaxPeers + p.p2p_rank) * P;
   for (int r = 0; r < G; ++r) {
@@ -715,6 +716,7 @@ __device__ inline bool exchange_partials(const SolveParams& p, const Combined& c
   __shared__ int timed_out;
   if (tid == 0) timed_out = 0;
   __syncthreads();
+  stamp(p, 17);  // this rank's partial is on its way to every peer
   if (tid < G) {
     unsigned* peer_flags = reinterpret_cast<unsigned*>(p.peer_mailbox[tid] + (size_t)2 * kMaxPeers * P);
     st_release_sys(peer_flags + parity * kMaxPeers + p.p2p_rank, seq);
@@ -736,10 +738,12 @@ __device__ inline bool exchange_partials(const SolveParams& p, const Combined& c
     }
     return false;
   }
+  stamp(p, 18);  // every peer's flag has arrived
   const float* mine = p.peer_mailbox[p.p2p_rank] + (size_t)parity * kMaxPeers * P;
   for (int i = tid; i < G * P; i += nt) p.gather_scratch[i] = ld_volatile(mine + i);
   __threadfence();
   __syncthreads();
+  stamp(p, 19);
   return true;
 }
 

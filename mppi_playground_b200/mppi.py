@@ -246,12 +246,31 @@ class MPPI(nn.Module):
         action = torch.empty(T, du, device=self._device, dtype=torch.float32)
         states = torch.empty(T + 1, ds, device=self._device, dtype=torch.float32)
         s = _stream_ptr(self._device)
+        if self._fused:
+            # a peer that never arrived leaves NaN outputs and sets a flag in mapped host memory: report the
+            # failure of an EARLIER solve before launching the next one (no synchronisation needed to read it)
+            self.check_exchange(synchronize=False)
         if self._world == 1 or self._fused:
             _capi.check(self._lib.mppi_solve(self._h, st.data_ptr(), _ptr(ref), _ptr(noise), action.data_ptr(),
                                              states.data_ptr(), s))
         else:
             self._sharded_solve(st, ref, noise, action, states, s)
         return action, states.view(1, T + 1, ds)
+
+    def check_exchange(self, synchronize: bool = True) -> None:
+        """Raise if the fused peer exchange of a sharded solve timed out (a rank's kernel was not running within
+        ~2 s of the others: the outputs of that solve are NaN on this rank and the carried state was not updated).
+        ``synchronize=True`` waits for the solves launched so far first; ``forward`` calls it without waiting, so a
+        failure surfaces at the latest on the next solve."""
+        if not self._fused:
+            return
+        if synchronize:
+            torch.cuda.current_stream(self._device).synchronize()
+        flag = C.c_int32()
+        _capi.check(self._lib.mppi_p2p_status(self._h, C.byref(flag)))
+        if flag.value:
+            raise RuntimeError(f"fused shard exchange timed out in solve #{flag.value} on rank {self._rank}: a peer's "
+                               "solve kernel was not running concurrently (outputs of that solve are NaN)")
 
     def _sharded_solve(self, st, ref, noise, action, states, s) -> None:
         """K split over ranks: roll the shard, exchange the shard partials

@@ -654,3 +654,22 @@ def test_full_size_solves_by_size_independent_properties(cfg):
     # (3) determinism
     a2, s2 = twin.forward(state)
     assert torch.equal(a2, action) and torch.equal(s2, states) and torch.equal(twin._costs, costs)
+
+
+def test_fused_exchange_timeout_is_reported_not_returned():
+    """A shard whose peers never launch must not hand back stale or uninitialised memory: the kernel gives up
+    after ~2 s, writes NaN outputs and raises a flag in mapped host memory; check_exchange() - and the next
+    forward() - raise."""
+    from mppi_playground_b200.mppi import connect_shards_inprocess
+
+    cfg = dict(model="cartpole", horizon=20, num_samples=1024, u_min=[-3.0], u_max=[3.0], sigmas=[1.0], lambda_=1.0)
+    shards = [build_engine(cfg, shard=(r, 2)) for r in range(2)]
+    solvers = [sv for _, sv in shards]
+    connect_shards_inprocess(solvers)
+    state = torch.tensor([0.0, 0.1, 0.05, -0.1])
+    action, states = solvers[0].forward(state)  # rank 1 never launches
+    with pytest.raises(RuntimeError, match="timed out"):
+        solvers[0].check_exchange()
+    assert torch.isnan(action).all() and torch.isnan(states).all()
+    # the flag is reported once; a later failure would be reported by the next forward() without a sync
+    solvers[0].check_exchange()

@@ -40,9 +40,9 @@ for s in range(a.solves):
     state = seq[0, 1].cpu()
 info = solver.launch_info()
 g = info["grid"]  # row 0: the finisher block, rows 1..: the workers
-buf = (C.c_uint64 * (g * 16))()
+buf = (C.c_uint64 * (g * 24))()
 _capi.check(lib.mppi_block_trace(h, 1, buf, g))
-t = np.array(buf, dtype=np.uint64).reshape(g, 16).astype(np.int64)
+t = np.array(buf, dtype=np.uint64).reshape(g, 24).astype(np.int64)
 t0 = t[:, 0].min()
 rel = (t - t0) / 1e3
 print("launch", info)
