@@ -135,10 +135,34 @@ int mppi_set_model_params(MppiHandle* h, const float* params, int32_t n);
 /* Occupancy grid for slot 0 (obstacle map; NAVIGATION2D and RACING) or slot 1
  * (lane map; RACING). `grid` is the reference's [W,H] fp32 0/1 map, x on the
  * slow axis (src/envs/obstacle_map_2d.py:195), on the device if on_device != 0.
- * It is bit-packed once into the layout the kernels stage into shared memory.
- * Synchronous. */
+ * It is bit-packed once into the layout the kernels stage into shared memory;
+ * grids too large for shared memory (beyond ~200 kB packed per solve, e.g. two
+ * 2000 x 2000 maps) stay in global memory and are read through L2 by a separate
+ * kernel instantiation (the reference's lookup has no size limit,
+ * obstacle_map_2d.py:168-200). Synchronous. */
 int mppi_set_map(MppiHandle* h, int32_t slot, const float* grid, int32_t on_device, int32_t width, int32_t height,
                  float cell_size, float origin_x, float origin_y);
+
+/* Device rasteriser ("next" row 4): builds the occupancy grid of `slot` on the device instead of the
+ * reference's Python loops and emits the packed layout the kernels read directly (no fp32 grid round trip).
+ *   MPPI_RASTER_OBSTACLE  ObstacleMap.add_circle_obstacle / add_rectangle_obstacle
+ *                         (src/envs/obstacle_map_2d.py:103-123, :125-160): free background, shapes paint 1.
+ *                         h_discs [n_discs,3] = (centre cell x, centre cell y, radius_occ^2) - indices that fall
+ *                         outside the map are clipped onto its border like the reference's np.clip (:121-122);
+ *                         h_rects [n_rects,4] = (x_init, x_end, y_init, y_end), the already clipped half-open
+ *                         slice of :150-157.
+ *   MPPI_RASTER_LANE      LaneMap.populate_map (src/envs/lane_map_2d.py:68-88): occupied background, every
+ *                         disc (centre-line cell inside the map, r2 = largest integer squared cell distance with
+ *                         sqrt(r2) <= (lane_width / 2) / cell_size in fp64) paints 0 - the thresholded Euclidean
+ *                         distance transform of the centre line, exactly. No rectangles.
+ * The world -> cell conversions are the reference's fp64 numpy expressions and stay with the caller
+ * (mppi_playground_b200/maps.py). d_grid_out: optional [W,H] fp32 0/1 grid (the reference's _map_torch), or NULL.
+ * Re-rasterising a slot with unchanged geometry reuses its buffers and division proofs. Synchronous. */
+#define MPPI_RASTER_OBSTACLE 0
+#define MPPI_RASTER_LANE 1
+int mppi_raster_map(MppiHandle* h, int32_t slot, int32_t mode, int32_t width, int32_t height, float cell_size,
+                    float origin_x, float origin_y, const int32_t* h_discs, int32_t n_discs, const int32_t* h_rects,
+                    int32_t n_rects, float* d_grid_out);
 
 /* ---- one solve (MPPI.forward, mppi.py:223-460) ----------------------------------- */
 /* d_state [ds]; d_refpath [T+1,4] (RACING only, else NULL: example/racing.py:73-81);
@@ -193,8 +217,45 @@ int mppi_weights(MppiHandle* h, float* d_weights, void* stream);
 /* get_top_samples (mppi.py:462-487): the n highest-weight samples of the last
  * solve, weight-descending. Trajectories are not stored during the solve;
  * they are re-rolled from the sampler key (or from d_noise, which must still
- * be valid, in parity mode). d_traj [n,T+1,ds], d_w [n]. */
+ * be valid, in parity mode). d_traj [n,T+1,ds], d_w [n]. n <= 1024 runs the
+ * radix select of mppi_step_epilogue (one launch up to K = 65536); larger n
+ * falls back to a full radix sort of the costs. */
 int mppi_top_samples(MppiHandle* h, int32_t n, float* d_traj, float* d_w, void* stream);
+/* ---- control-step epilogue ("next" row 2) ---------------------------------------------------------------
+ * What the reference's control loops run between two solves (example/racing.py:233-237,
+ * example/navigation2d.py:39-44), as ONE launch (plus one select level per 65536 candidates when K > 65536):
+ *   env.step(action_seq[0])          src/envs/racing_env.py:142-163 / navigation_2d.py:97-117: clamp, one
+ *                                    dynamics step, goal test norm(next[:2] - goal) < threshold;
+ *   env.collision_check(state_seq)   racing_env.py:374-384 / navigation_2d.py:281-291: obstacle-map value of
+ *                                    every predicted position;
+ *   solver.get_top_samples(top_n)    mppi.py:462-487: radix SELECT of the top_n lowest costs (= highest weights;
+ *                                    ties by the lower sample id) instead of a sort of all K, winners re-rolled.
+ * Every group is optional (NULL outputs / top_n = 0). */
+typedef struct MppiStepEpilogue {
+  const float* d_state;      /* [ds] env state before the step; NULL: the state of the last solve */
+  const float* d_action_seq; /* [T,du] of the last solve (row 0 is executed) */
+  const float* d_state_seq;  /* [T+1,ds] of the last solve */
+  float goal_x, goal_y, goal_threshold; /* goal_threshold <= 0: no goal test (flag 0) */
+  int32_t top_n;             /* 0: no top samples; at most 1024 on this path */
+  /* sample-sharded solvers: the ranks' mppi_top_candidates outputs gathered by the caller ([n_cand] each);
+   * NULL / 0: select from this handle's own costs */
+  const float* d_cand_cost;
+  const int32_t* d_cand_id;
+  int32_t n_cand;
+  const float* d_noise_global; /* parity mode on a sharded solver: injected noise indexed by GLOBAL sample id, else NULL */
+  float* d_next_state;       /* out [ds], or NULL */
+  float* d_flags;            /* out [1 + T+1]: is_goal_reached, then is_collisions[0..T] (0/1 like compute_cost); needs d_next_state */
+  float* d_top_traj;         /* out [top_n, T+1, ds] */
+  float* d_top_w;            /* out [top_n], descending */
+  float* d_top_cost;         /* out [top_n] optional: the winners' costs (ascending) */
+  int32_t* d_top_id;         /* out [top_n] optional: the winners' global sample ids */
+} MppiStepEpilogue;
+int mppi_step_epilogue(MppiHandle* h, const MppiStepEpilogue* args, void* stream);
+/* This handle's n best (cost ascending, then id) samples of the last solve as (cost, GLOBAL sample id) pairs:
+ * the per-rank half of get_top_samples on a sharded solver. n <= 1024. */
+int mppi_top_candidates(MppiHandle* h, int32_t n, float* d_cand_cost, int32_t* d_cand_id, void* stream);
+/* Kernels the last mppi_step_epilogue / mppi_top_candidates / mppi_top_samples (select path) launched. */
+int32_t mppi_last_epilogue_launches(const MppiHandle* h);
 /* _states_prediction (mppi.py:508-524): roll n action sequences d_actions [n,T,du]
  * from d_state; d_traj [n,T+1,ds]. Used by get_samples_from_posterior (mppi.py:489-506). */
 int mppi_rollout_actions(MppiHandle* h, const float* d_state, const float* d_actions, int32_t n, float* d_traj,

@@ -48,9 +48,27 @@ class MppiFp32Report(C.Structure):
                                           "sm_clock_mhz")] + [("sms", C.c_int32), ("reserved", C.c_int32)]
 
 
-# name -> (restype, argtypes); every symbol include/mppi_b200.h declares
 _P = C.c_void_p
 _FP = C.c_void_p  # float* passed as raw address
+RASTER_OBSTACLE, RASTER_LANE = 0, 1
+TOP_MAX = 1024  # largest top_n of the select path (mppi_step_epilogue / mppi_top_candidates)
+
+
+class MppiStepEpilogue(C.Structure):
+    """struct MppiStepEpilogue of include/mppi_b200.h, field for field."""
+
+    _fields_ = [
+        ("d_state", _FP), ("d_action_seq", _FP), ("d_state_seq", _FP),
+        ("goal_x", C.c_float), ("goal_y", C.c_float), ("goal_threshold", C.c_float),
+        ("top_n", C.c_int32),
+        ("d_cand_cost", _FP), ("d_cand_id", _FP), ("n_cand", C.c_int32),
+        ("d_noise_global", _FP),
+        ("d_next_state", _FP), ("d_flags", _FP), ("d_top_traj", _FP), ("d_top_w", _FP), ("d_top_cost", _FP),
+        ("d_top_id", _FP),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/mppi_b200.h declares
 PROTOTYPES = {
     "mppi_create": (C.c_int, [C.POINTER(MppiConfig), C.POINTER(_P)]),
     "mppi_destroy": (None, [_P]),
@@ -60,6 +78,8 @@ PROTOTYPES = {
     "mppi_set_model_params": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int32]),
     "mppi_set_map": (C.c_int, [_P, C.c_int32, _FP, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float,
                                C.c_float]),
+    "mppi_raster_map": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float,
+                                  C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.c_int32, _FP]),
     "mppi_solve": (C.c_int, [_P, _FP, _FP, _FP, _FP, _FP, _P]),
     "mppi_solve_host": (C.c_int, [_P, _FP, _FP, _FP, _FP]),
     "mppi_shard_rollout": (C.c_int, [_P, _FP, _FP, _FP, _P]),
@@ -75,6 +95,9 @@ PROTOTYPES = {
     "mppi_partial_ptr": (C.c_int, [_P, C.POINTER(_P)]),
     "mppi_weights": (C.c_int, [_P, _FP, _P]),
     "mppi_top_samples": (C.c_int, [_P, C.c_int32, _FP, _FP, _P]),
+    "mppi_step_epilogue": (C.c_int, [_P, C.POINTER(MppiStepEpilogue), _P]),
+    "mppi_top_candidates": (C.c_int, [_P, C.c_int32, _FP, _FP, _P]),
+    "mppi_last_epilogue_launches": (C.c_int32, [_P]),
     "mppi_rollout_actions": (C.c_int, [_P, _FP, _FP, C.c_int32, _FP, _P]),
     "mppi_get_lambda": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), _P]),
     "mppi_get_carry": (C.c_int, [_P, _FP, _FP, _P]),

@@ -22,6 +22,7 @@
 
 #include "../../include/mppi_b200.h"
 #include "mppi_kernels.cuh"
+#include "mppi_epilogue.cuh"
 
 using namespace mppi;
 
@@ -159,6 +160,9 @@ struct MppiHandle {
   unsigned int* d_counter = nullptr;
   uint32_t* d_map[2] = {nullptr, nullptr};
   bool map_set[2] = {false, false};
+  bool maps_global = false;  // grids exceed shared memory: they stay in global memory (solve_kernel<.., kGlobalMaps>)
+  float proved_cell[2] = {0.0f, 0.0f}, proved_ox[2] = {0.0f, 0.0f}, proved_oy[2] = {0.0f, 0.0f};  // division proofs cached
+  bool proved[2] = {false, false};
   unsigned long long fastdiv_mismatches[2] = {0, 0};
   bool tiny_quotient_ok[2] = {false, false};  // check_tiny_quotient_kernel found no mismatch for this slot
   float proved_wheelbase = -1.0f, wheelbase_rcp = 1.0f;
@@ -167,7 +171,12 @@ struct MppiHandle {
   float* h_pinned = nullptr;  // state | refpath | action_seq | state_seq
   float* d_stage = nullptr;
   cudaStream_t own_stream = nullptr;
-  // top samples
+  // top samples: select tree candidates (ping-pong), then the full-sort fallback for n > kTopMax
+  float* d_cand_cost[2] = {nullptr, nullptr};
+  int* d_cand_id[2] = {nullptr, nullptr};
+  size_t cand_cap = 0;
+  RasterShape* d_shapes = nullptr;
+  size_t shapes_cap = 0;
   int* d_idx_in = nullptr;
   int* d_idx_out = nullptr;
   float* d_keys_out = nullptr;
@@ -178,6 +187,7 @@ struct MppiHandle {
   bool solved = false;
   const float* last_noise = nullptr;
   int last_launches = 0;
+  int last_epilogue_launches = 0;
   // fused peer exchange (mppi_p2p_*)
   float* d_mailbox = nullptr;
   float* d_gather_scratch = nullptr;
@@ -253,7 +263,12 @@ int launch_solve(MppiHandle* h, const SolveParams& p, int mode, bool inject, cud
   void (*k)(SolveParams) = nullptr;
 #define PICK(MODE)                                                                   \
   do {                                                                               \
-    if (inject) {                                                                    \
+    if (h->maps_global) {                                                            \
+      if constexpr (M::kMaps > 0) {                                                  \
+        k = inject ? (void (*)(SolveParams))solve_kernel<M, true, MODE, 1, true>     \
+                   : (void (*)(SolveParams))solve_kernel<M, false, MODE, 1, true>;   \
+      }                                                                              \
+    } else if (inject) {                                                             \
       k = (void (*)(SolveParams))solve_kernel<M, true, MODE, 1>;                     \
     } else if (g.spt == 2) {                                                         \
       if constexpr (M::kHasBounded) k = (void (*)(SolveParams))solve_kernel<M, false, MODE, 2>; \
@@ -495,6 +510,15 @@ void refresh_model_flags(MppiHandle* h) {
 
 void refresh_launch_geometry(MppiHandle* h) {
   unsigned mb[2] = {h->base.map_bytes[0], h->base.map_bytes[1]};
+  {  // grids that do not fit beside the smallest block's buffers stay in global memory (general loop only)
+    SmemLayout Lmin = make_layout(h->mi.maps, mb, h->cfg.horizon, h->E_pad, h->base.prev_action_bytes, h->mi.refpath, 2,
+                                  h->mi.tail_per_step, 1, 0);
+    h->maps_global = h->mi.maps > 0 && Lmin.total > kMaxSmem;
+    if (h->maps_global) {
+      mb[0] = mb[1] = 0;
+      h->base.mp.flags &= ~kFlagBounded;  // the bounded loops read the staged grids
+    }
+  }
   const bool pair_model = h->cfg.model == MPPI_MODEL_RACING || h->cfg.model == MPPI_MODEL_NAVIGATION2D;
   for (int v = 0; v < 2; ++v) {
     MppiHandle::Geometry& g = h->geo[v];
@@ -695,6 +719,11 @@ void mppi_destroy(MppiHandle* h) {
   cudaFree(h->d_map[0]);
   cudaFree(h->d_map[1]);
   cudaFree(h->d_stage);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(h->d_cand_cost[i]);
+    cudaFree(h->d_cand_id[i]);
+  }
+  cudaFree(h->d_shapes);
   cudaFree(h->d_idx_in);
   cudaFree(h->d_idx_out);
   cudaFree(h->d_keys_out);
@@ -728,36 +757,24 @@ int mppi_set_model_params(MppiHandle* h, const float* params, int32_t n) {
   return MPPI_OK;
 }
 
-int mppi_set_map(MppiHandle* h, int32_t slot, const float* grid, int32_t on_device, int32_t W, int32_t H,
-                 float cell, float ox, float oy) {
-  if (!h || !grid) return fail(MPPI_ERR_INVALID, "null argument");
-  if (slot < 0 || slot >= h->mi.maps) return fail(MPPI_ERR_INVALID, "model has %d map slots, got slot %d", h->mi.maps, slot);
-  if (W < 1 || H < 1 || !(cell > 0.0f)) return fail(MPPI_ERR_INVALID, "bad map geometry");
-  ON_DEVICE(h->device);
-  const int words = (H + 1 + 31) / 32;  // + the out-of-bounds border bit (see MapView)
-  const size_t bytes = pad16((size_t)(W + 1) * words * 4);
-  const float* d_grid = grid;
-  float* tmp = nullptr;
-  if (!on_device) {
-    CUDA_TRY(cudaMalloc((void**)&tmp, (size_t)W * H * 4));
-    cudaError_t e = cudaMemcpy(tmp, grid, (size_t)W * H * 4, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
-      cudaFree(tmp);
-      return fail(MPPI_ERR_CUDA, "map upload: %s", cudaGetErrorString(e));
-    }
-    d_grid = tmp;
-  }
+// (Re)allocate the packed grid of `slot` for a W x H map; *words / *bytes describe the bordered layout.
+static int alloc_map_bits(MppiHandle* h, int slot, int W, int H, int* words, size_t* bytes) {
+  *words = (H + 1 + 31) / 32;  // + the out-of-bounds border bit (see MapView)
+  *bytes = pad16((size_t)(W + 1) * *words * 4);
+  if (h->d_map[slot] && h->base.map_bytes[slot] == (unsigned)*bytes && h->base.map_W[slot] == W &&
+      h->base.map_H[slot] == H)
+    return MPPI_OK;  // same geometry as before (dynamic obstacles re-rasterised every control step): reuse
   cudaFree(h->d_map[slot]);
   h->d_map[slot] = nullptr;
-  cudaError_t e = cudaMalloc((void**)&h->d_map[slot], bytes);
-  if (e == cudaSuccess) e = cudaMemset(h->d_map[slot], 0, bytes);
-  if (e == cudaSuccess) {
-    int n = (W + 1) * words;
-    pack_map_kernel<<<(n + 255) / 256, 256>>>(d_grid, W, H, words, h->d_map[slot]);
-    e = cudaDeviceSynchronize();
-  }
-  cudaFree(tmp);
-  if (e != cudaSuccess) return fail(MPPI_ERR_CUDA, "map pack: %s", cudaGetErrorString(e));
+  cudaError_t e = cudaMalloc((void**)&h->d_map[slot], *bytes);
+  if (e == cudaSuccess) e = cudaMemset(h->d_map[slot], 0, *bytes);
+  if (e != cudaSuccess) return fail(MPPI_ERR_CUDA, "map alloc: %s", cudaGetErrorString(e));
+  return MPPI_OK;
+}
+
+// Everything after the packed bits of `slot` are in place: geometry, division proofs, flags, launch geometry.
+static int finish_map_setup(MppiHandle* h, int slot, int W, int H, int words, size_t bytes, float cell, float ox,
+                            float oy) {
   SolveParams& b = h->base;
   b.map_bits[slot] = h->d_map[slot];
   b.map_W[slot] = W;
@@ -765,7 +782,9 @@ int mppi_set_map(MppiHandle* h, int32_t slot, const float* grid, int32_t on_devi
   b.map_words[slot] = words;
   b.map_bytes[slot] = (unsigned)bytes;
   b.map_cell[slot] = cell;
-  {  // exact fast division by the cell size: prove it for this divisor, or keep the true division
+  // exact fast division by the cell size: prove it for this divisor, or keep the true division. The proofs
+  // depend on (cell, origin) only, so a re-rasterised map of the same geometry keeps them.
+  if (!(h->proved[slot] && h->proved_cell[slot] == cell && h->proved_ox[slot] == ox && h->proved_oy[slot] == oy)) {
     float rcp = 0.0f;
     const bool ok = prove_exact_division(cell, &rcp);
     b.map_rcp[slot] = rcp;
@@ -782,6 +801,10 @@ int mppi_set_map(MppiHandle* h, int32_t slot, const float* grid, int32_t on_devi
       cudaFree(d_bad);
       h->tiny_quotient_ok[slot] = bad == 0;
     }
+    h->proved[slot] = true;
+    h->proved_cell[slot] = cell;
+    h->proved_ox[slot] = ox;
+    h->proved_oy[slot] = oy;
   }
   b.map_ox[slot] = ox;
   b.map_oy[slot] = oy;
@@ -789,9 +812,82 @@ int mppi_set_map(MppiHandle* h, int32_t slot, const float* grid, int32_t on_devi
   refresh_model_flags(h);
   refresh_launch_geometry(h);
   if (std::max(h->geo[0].smem, h->geo[1].smem) > kMaxSmem)
-    return fail(MPPI_ERR_UNSUPPORTED, "occupancy maps need %u B of shared memory (> %u)",
+    return fail(MPPI_ERR_UNSUPPORTED, "shared memory budget exceeded (%u B > %u)",
                 std::max(h->geo[0].smem, h->geo[1].smem), kMaxSmem);
   return MPPI_OK;
+}
+
+int mppi_set_map(MppiHandle* h, int32_t slot, const float* grid, int32_t on_device, int32_t W, int32_t H,
+                 float cell, float ox, float oy) {
+  if (!h || !grid) return fail(MPPI_ERR_INVALID, "null argument");
+  if (slot < 0 || slot >= h->mi.maps) return fail(MPPI_ERR_INVALID, "model has %d map slots, got slot %d", h->mi.maps, slot);
+  if (W < 1 || H < 1 || !(cell > 0.0f)) return fail(MPPI_ERR_INVALID, "bad map geometry");
+  ON_DEVICE(h->device);
+  const float* d_grid = grid;
+  float* tmp = nullptr;
+  if (!on_device) {
+    CUDA_TRY(cudaMalloc((void**)&tmp, (size_t)W * H * 4));
+    cudaError_t e = cudaMemcpy(tmp, grid, (size_t)W * H * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      cudaFree(tmp);
+      return fail(MPPI_ERR_CUDA, "map upload: %s", cudaGetErrorString(e));
+    }
+    d_grid = tmp;
+  }
+  int words = 0;
+  size_t bytes = 0;
+  int rc = alloc_map_bits(h, slot, W, H, &words, &bytes);
+  if (rc) {
+    cudaFree(tmp);
+    return rc;
+  }
+  const long long n = (long long)(W + 1) * words;
+  pack_map_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_grid, W, H, words, h->d_map[slot]);
+  cudaError_t e = cudaDeviceSynchronize();
+  cudaFree(tmp);
+  if (e != cudaSuccess) return fail(MPPI_ERR_CUDA, "map pack: %s", cudaGetErrorString(e));
+  return finish_map_setup(h, slot, W, H, words, bytes, cell, ox, oy);
+}
+
+int mppi_raster_map(MppiHandle* h, int32_t slot, int32_t mode, int32_t W, int32_t H, float cell, float ox, float oy,
+                    const int32_t* h_discs, int32_t n_discs, const int32_t* h_rects, int32_t n_rects,
+                    float* d_grid_out) {
+  if (!h) return fail(MPPI_ERR_INVALID, "null handle");
+  if (slot < 0 || slot >= h->mi.maps) return fail(MPPI_ERR_INVALID, "model has %d map slots, got slot %d", h->mi.maps, slot);
+  if (W < 1 || H < 1 || !(cell > 0.0f)) return fail(MPPI_ERR_INVALID, "bad map geometry");
+  if (mode != MPPI_RASTER_OBSTACLE && mode != MPPI_RASTER_LANE) return fail(MPPI_ERR_INVALID, "unknown raster mode %d", mode);
+  if (n_discs < 0 || n_rects < 0 || (n_discs > 0 && !h_discs) || (n_rects > 0 && !h_rects))
+    return fail(MPPI_ERR_INVALID, "bad shape list");
+  if (mode == MPPI_RASTER_LANE && n_rects > 0) return fail(MPPI_ERR_INVALID, "lane maps are painted from discs only");
+  ON_DEVICE(h->device);
+  std::vector<RasterShape> shapes((size_t)n_discs + n_rects);
+  for (int i = 0; i < n_discs; ++i) {
+    if (h_discs[3 * i + 2] < 0) return fail(MPPI_ERR_INVALID, "disc %d has a negative squared radius", i);
+    shapes[i] = RasterShape{h_discs[3 * i], h_discs[3 * i + 1], h_discs[3 * i + 2], 0};
+  }
+  for (int i = 0; i < n_rects; ++i)
+    shapes[n_discs + i] = RasterShape{h_rects[4 * i], h_rects[4 * i + 1], h_rects[4 * i + 2], h_rects[4 * i + 3]};
+  if (shapes.size() > h->shapes_cap) {
+    cudaFree(h->d_shapes);
+    h->d_shapes = nullptr;
+    h->shapes_cap = 0;
+    CUDA_TRY(cudaMalloc((void**)&h->d_shapes, shapes.size() * sizeof(RasterShape)));
+    h->shapes_cap = shapes.size();
+  }
+  if (!shapes.empty())
+    CUDA_TRY(cudaMemcpy(h->d_shapes, shapes.data(), shapes.size() * sizeof(RasterShape), cudaMemcpyHostToDevice));
+  int words = 0;
+  size_t bytes = 0;
+  int rc = alloc_map_bits(h, slot, W, H, &words, &bytes);
+  if (rc) return rc;
+  const long long n = (long long)(W + 1) * words;
+  const int threads = 256;
+  raster_map_kernel<<<(unsigned)((n + threads - 1) / threads), threads, threads * sizeof(RasterShape)>>>(
+      h->d_shapes, n_discs, h->d_shapes + n_discs, n_rects, mode == MPPI_RASTER_LANE ? 1 : 0, W, H, words,
+      h->d_map[slot], d_grid_out);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return fail(MPPI_ERR_CUDA, "map raster: %s", cudaGetErrorString(e));
+  return finish_map_setup(h, slot, W, H, words, bytes, cell, ox, oy);
 }
 
 static int solve_impl(MppiHandle* h, const float* d_state, const float* d_refpath, const float* d_noise,
@@ -1043,11 +1139,166 @@ int mppi_weights(MppiHandle* h, float* d_weights, void* stream) {
   return MPPI_OK;
 }
 
+}  // extern "C"
+
+// Parameter block of the kernels that re-roll samples of the LAST solve (its state, warm start, sampler index).
+static SolveParams last_solve_params(MppiHandle* h) {
+  SolveParams p = h->base;
+  p.state = h->d_state_snapshot;
+  p.prev_action = h->d_nominal_snapshot;
+  p.noise = h->last_noise;
+  const uint64_t idx = h->solve_count - 1;
+  p.key.solve_lo = (uint32_t)idx;
+  p.key.solve_hi = (uint32_t)(idx >> 32);
+  return p;
+}
+
+// Select tree: reduce `src` level by level (one CTA per kTopSlice candidates, n winners each) until a single
+// CTA can finish; on return *src is what the final CTA selects from.
+static int run_select_levels(MppiHandle* h, TopSource* src, int n, cudaStream_t st) {
+  int side = 0;
+  while (src->count > kTopSlice) {
+    const long long blocks = ((long long)src->count + kTopSlice - 1) / kTopSlice;
+    const size_t need = (size_t)blocks * n;
+    if (need > (size_t)0x7fffffff) return fail(MPPI_ERR_UNSUPPORTED, "too many candidates for the select tree");
+    if (need > h->cand_cap) {
+      if (side != 0) return fail(MPPI_ERR_STATE, "select tree grew");  // later levels only shrink
+      for (int i = 0; i < 2; ++i) {
+        cudaFree(h->d_cand_cost[i]);
+        cudaFree(h->d_cand_id[i]);
+        h->d_cand_cost[i] = nullptr;
+        h->d_cand_id[i] = nullptr;
+      }
+      h->cand_cap = 0;
+      for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaMalloc((void**)&h->d_cand_cost[i], need * 4));
+        CUDA_TRY(cudaMalloc((void**)&h->d_cand_id[i], need * 4));
+      }
+      h->cand_cap = need;
+    }
+    const int dst = side & 1;
+    topn_select_kernel<<<(unsigned)blocks, kTopThreads, 0, st>>>(*src, n, h->d_cand_cost[dst], h->d_cand_id[dst]);
+    CUDA_TRY(cudaGetLastError());
+    h->last_epilogue_launches++;
+    src->costs = h->d_cand_cost[dst];
+    src->ids = h->d_cand_id[dst];
+    src->id_offset = 0;
+    src->count = (int)need;
+    ++side;
+  }
+  return MPPI_OK;
+}
+
+template <class M>
+static int launch_epilogue(MppiHandle* h, const SolveParams& p, const EpilogueParams& e, cudaStream_t st) {
+  if (p.noise)
+    control_epilogue_kernel<M, true><<<1, kTopThreads, 0, st>>>(p, e);
+  else
+    control_epilogue_kernel<M, false><<<1, kTopThreads, 0, st>>>(p, e);
+  CUDA_TRY(cudaGetLastError());
+  h->last_epilogue_launches++;
+  return MPPI_OK;
+}
+
+static int dispatch_epilogue(MppiHandle* h, const SolveParams& p, const EpilogueParams& e, cudaStream_t st) {
+  switch (h->cfg.model) {
+    case MPPI_MODEL_PENDULUM: return launch_epilogue<Pendulum>(h, p, e, st);
+    case MPPI_MODEL_CARTPOLE: return launch_epilogue<Cartpole>(h, p, e, st);
+    case MPPI_MODEL_MOUNTAINCAR: return launch_epilogue<MountainCar>(h, p, e, st);
+    case MPPI_MODEL_NAVIGATION2D: return launch_epilogue<Navigation2D>(h, p, e, st);
+    case MPPI_MODEL_RACING: return launch_epilogue<Racing>(h, p, e, st);
+    case MPPI_MODEL_CARTPOLE_CONTINUOUS: return launch_epilogue<CartpoleContinuous>(h, p, e, st);
+    case MPPI_MODEL_GOAL_IN_DANGER_ZONE: return launch_epilogue<GoalInDangerZone>(h, p, e, st);
+  }
+  return fail(MPPI_ERR_INVALID, "unknown model");
+}
+
+extern "C" {
+
+int mppi_top_candidates(MppiHandle* h, int32_t n, float* d_cand_cost, int32_t* d_cand_id, void* stream) {
+  if (!h || !d_cand_cost || !d_cand_id) return fail(MPPI_ERR_INVALID, "null argument");
+  if (n < 1 || n > kTopMax) return fail(MPPI_ERR_INVALID, "n must be in [1, %d]", kTopMax);
+  if (!h->solved) return fail(MPPI_ERR_STATE, "no solve has run yet");
+  if (h->cfg.sample_offset + (long long)h->cfg.num_samples > 0x7fffffffLL)
+    return fail(MPPI_ERR_UNSUPPORTED, "global sample ids beyond 2^31");
+  ON_DEVICE(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  h->last_epilogue_launches = 0;
+  TopSource src{h->d_costs, nullptr, h->cfg.sample_offset, h->cfg.num_samples};
+  int rc = run_select_levels(h, &src, n, st);
+  if (rc) return rc;
+  topn_select_kernel<<<1, kTopThreads, 0, st>>>(src, n, d_cand_cost, d_cand_id);
+  CUDA_TRY(cudaGetLastError());
+  h->last_epilogue_launches++;
+  return MPPI_OK;
+}
+
+int mppi_step_epilogue(MppiHandle* h, const MppiStepEpilogue* a, void* stream) {
+  if (!h || !a) return fail(MPPI_ERR_INVALID, "null argument");
+  if (!h->solved) return fail(MPPI_ERR_STATE, "no solve has run yet");
+  const int K = h->cfg.num_samples;
+  const bool want_step = a->d_next_state != nullptr, want_flags = a->d_flags != nullptr, want_top = a->top_n > 0;
+  if (want_step && !a->d_action_seq) return fail(MPPI_ERR_INVALID, "env step needs d_action_seq");
+  if (want_flags && !a->d_state_seq) return fail(MPPI_ERR_INVALID, "collision flags need d_state_seq");
+  if (want_flags && !want_step) return fail(MPPI_ERR_INVALID, "d_flags[0] is the goal test of d_next_state: pass both");
+  if (want_top) {
+    if (!a->d_top_traj || !a->d_top_w) return fail(MPPI_ERR_INVALID, "top samples need d_top_traj and d_top_w");
+    if (a->top_n > kTopMax) return fail(MPPI_ERR_UNSUPPORTED, "top_n > %d: use mppi_top_samples", kTopMax);
+    if (a->top_n > h->cfg.total_samples) return fail(MPPI_ERR_INVALID, "num_samples must be in [1, %lld]", (long long)h->cfg.total_samples);
+    if ((a->d_cand_cost == nullptr) != (a->d_cand_id == nullptr) || (a->d_cand_cost && a->n_cand < a->top_n))
+      return fail(MPPI_ERR_INVALID, "candidate list must hold costs, ids and at least top_n entries");
+    if (!a->d_cand_cost && a->top_n > K) return fail(MPPI_ERR_INVALID, "num_samples must be in [1, %d]", K);
+    if (h->cfg.sample_offset + (long long)K > 0x7fffffffLL) return fail(MPPI_ERR_UNSUPPORTED, "global sample ids beyond 2^31");
+  }
+  ON_DEVICE(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  h->last_epilogue_launches = 0;
+  SolveParams p = last_solve_params(h);
+  EpilogueParams e{};
+  e.state = a->d_state ? a->d_state : h->d_state_snapshot;
+  e.action_seq = a->d_action_seq;
+  e.state_seq = a->d_state_seq;
+  e.goal_x = a->goal_x;
+  e.goal_y = a->goal_y;
+  e.goal_threshold = a->goal_threshold;
+  e.next_state = a->d_next_state;
+  e.flags = a->d_flags;
+  e.top_n = want_top ? a->top_n : 0;
+  e.top_traj = a->d_top_traj;
+  e.top_w = a->d_top_w;
+  e.top_cost = a->d_top_cost;
+  e.top_id = a->d_top_id;
+  e.noise_id_base = h->cfg.sample_offset;
+  if (want_top) {
+    if (a->d_noise_global) {  // injected noise indexed by GLOBAL sample id (winners of other ranks included)
+      p.noise = a->d_noise_global;
+      e.noise_id_base = 0;
+    } else if (p.noise && a->d_cand_cost && h->cfg.total_samples != K) {
+      return fail(MPPI_ERR_INVALID, "merged top samples of an injected-noise solve need d_noise_global");
+    }
+    e.src = a->d_cand_cost ? TopSource{a->d_cand_cost, a->d_cand_id, 0, a->n_cand}
+                           : TopSource{h->d_costs, nullptr, h->cfg.sample_offset, K};
+    int rc = run_select_levels(h, &e.src, e.top_n, st);
+    if (rc) return rc;
+  }
+  return dispatch_epilogue(h, p, e, st);
+}
+
+int32_t mppi_last_epilogue_launches(const MppiHandle* h) { return h ? h->last_epilogue_launches : 0; }
+
 int mppi_top_samples(MppiHandle* h, int32_t n, float* d_traj, float* d_w, void* stream) {
   if (!h || !d_traj || !d_w) return fail(MPPI_ERR_INVALID, "null argument");
   const int K = h->cfg.num_samples;
   if (n < 1 || n > K) return fail(MPPI_ERR_INVALID, "num_samples must be in [1, %d]", K);  // mppi.py:476
   if (!h->solved) return fail(MPPI_ERR_STATE, "no solve has run yet");
+  if (n <= kTopMax && h->cfg.sample_offset + (long long)K <= 0x7fffffffLL) {
+    // the usual case (the examples ask for 300): radix select + re-roll, no sort of all K costs
+    MppiStepEpilogue a{};
+    a.top_n = n;
+    a.d_top_traj = d_traj;
+    a.d_top_w = d_w;
+    return mppi_step_epilogue(h, &a, stream);
+  }
   ON_DEVICE(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   if (!h->d_idx_in) {
@@ -1059,16 +1310,10 @@ int mppi_top_samples(MppiHandle* h, int32_t n, float* d_traj, float* d_w, void* 
                                              h->d_idx_out, K, 0, 32, st));
     CUDA_TRY(cudaMalloc(&h->d_sort_tmp, h->sort_tmp_bytes));
   }
-  // highest weight == lowest cost (mppi.py:479-485); ascending radix sort on the fp32 costs
+  // highest weight == lowest cost (mppi.py:479-485); ascending (stable) radix sort on the fp32 costs
   CUDA_TRY(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp, h->sort_tmp_bytes, h->d_costs, h->d_keys_out, h->d_idx_in,
                                            h->d_idx_out, K, 0, 32, st));
-  SolveParams p = h->base;
-  p.state = h->d_state_snapshot;
-  p.prev_action = h->d_nominal_snapshot;
-  p.noise = h->last_noise;
-  const uint64_t idx = h->solve_count - 1;
-  p.key.solve_lo = (uint32_t)idx;
-  p.key.solve_hi = (uint32_t)(idx >> 32);
+  SolveParams p = last_solve_params(h);
   switch (h->cfg.model) {
     case MPPI_MODEL_PENDULUM: return launch_reroll<Pendulum>(h, p, n, d_traj, d_w, st);
     case MPPI_MODEL_CARTPOLE: return launch_reroll<Cartpole>(h, p, n, d_traj, d_w, st);

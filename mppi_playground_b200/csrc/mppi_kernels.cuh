@@ -1153,14 +1153,20 @@ __device__ __noinline__ void finisher_block(const SolveParams& p, const SmemLayo
 // flags allow it and no noise is injected); thread `tid` of block `b` owns local samples
 // b * 2 * blockDim + {tid, blockDim + tid}. If the solve's initial state fails the kernel-side range check the
 // same launch runs the general loop once per sample (same results, slower).
-template <class M, bool kInject, int kMode, int SPT>
+//
+// kGlobalMaps: occupancy grids too large for shared memory (the reference's lookup has no size limit,
+// src/envs/obstacle_map_2d.py:168-200) stay in global memory (bit-packed, L2 resident) and are read by the general
+// loop; a separate instantiation, so the staged kernels' shared-memory loads are untouched.
+template <class M, bool kInject, int kMode, int SPT, bool kGlobalMaps = false>
 __global__ void __launch_bounds__(SPT == 2 ? 256 : 512, 1) solve_kernel(const __grid_constant__ SolveParams p) {
   constexpr int DU = M::DU;
   static_assert(SPT == 1 || (M::kHasBounded && !kInject), "two samples per thread is the bounded sampler loop");
+  static_assert(!kGlobalMaps || (M::kMaps > 0 && SPT == 1), "global-memory grids: map models, one sample per thread");
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
-  const SmemLayout L = make_layout(M::kMaps, p.map_bytes, p.T, p.E_pad, p.prev_action_bytes, M::kRefPath, n_warps,
-                                   tail_per_step<M>(), SPT, p.stage_bytes);
+  const unsigned no_map_bytes[2] = {0u, 0u};
+  const SmemLayout L = make_layout(M::kMaps, kGlobalMaps ? no_map_bytes : p.map_bytes, p.T, p.E_pad,
+                                   p.prev_action_bytes, M::kRefPath, n_warps, tail_per_step<M>(), SPT, p.stage_bytes);
   // Block 0 is the FINISHER (kFused / kReduce): it never rolls samples. While the workers (blocks 1..) roll, it
   // runs the whole epilogue once on dummy data - which pulls the epilogue's code and tables into its SM's
   // caches - then waits for the workers' tickets and combines / finishes for real. kCosts has no epilogue.
@@ -1187,13 +1193,15 @@ __global__ void __launch_bounds__(SPT == 2 ? 256 : 512, 1) solve_kernel(const __
   if (tid == 0) {
     unsigned bytes = p.prev_action_bytes;
     if (kMode != kReduce) {
-      for (int i = 0; i < M::kMaps; ++i) bytes += p.map_bytes[i];
+      if (!kGlobalMaps)
+        for (int i = 0; i < M::kMaps; ++i) bytes += p.map_bytes[i];
       if (M::kRefPath && p.ref_bulk_ok && !p.inline_inputs) bytes += (unsigned)(p.T + 1) * 16;
     }
     mbar_expect_tx(bar, bytes);
     bulk_g2s(nominal, p.prev_action, p.prev_action_bytes, bar);
     if (kMode != kReduce) {
-      for (int i = 0; i < M::kMaps; ++i) bulk_g2s(smem + L.map_off[i], p.map_bits[i], p.map_bytes[i], bar);
+      if (!kGlobalMaps)
+        for (int i = 0; i < M::kMaps; ++i) bulk_g2s(smem + L.map_off[i], p.map_bits[i], p.map_bytes[i], bar);
       if (M::kRefPath && p.ref_bulk_ok && !p.inline_inputs)
         bulk_g2s(smem + L.refraw_off, p.refpath, (unsigned)(p.T + 1) * 16, bar);
     }
@@ -1211,8 +1219,9 @@ __global__ void __launch_bounds__(SPT == 2 ? 256 : 512, 1) solve_kernel(const __
   if constexpr (M::kMaps >= 1) {
     MapView mv[2];
     for (int i = 0; i < M::kMaps; ++i)
-      mv[i] = MapView{reinterpret_cast<const uint32_t*>(smem + L.map_off[i]), p.map_W[i], p.map_H[i], p.map_words[i],
-                      ExactDiv{p.map_cell[i], p.map_rcp[i], p.map_fastdiv[i]}, p.map_ox[i], p.map_oy[i]};
+      mv[i] = MapView{kGlobalMaps ? p.map_bits[i] : reinterpret_cast<const uint32_t*>(smem + L.map_off[i]), p.map_W[i],
+                      p.map_H[i], p.map_words[i], ExactDiv{p.map_cell[i], p.map_rcp[i], p.map_fastdiv[i]}, p.map_ox[i],
+                      p.map_oy[i]};
     if constexpr (M::kMaps == 1) {
       ctx.map = mv[0];
     } else {
@@ -1280,7 +1289,7 @@ __global__ void __launch_bounds__(SPT == 2 ? 256 : 512, 1) solve_kernel(const __
         }
       }
     }
-    if constexpr (SPT == 1 && !kInject && M::kHasBounded) {
+    if constexpr (SPT == 1 && !kInject && M::kHasBounded && !kGlobalMaps) {
       // (uniform over the block) the bounded single-sample loop: same flag, the single loop's range check
       paired = (p.mp.flags & kFlagBounded) && M::state_in_bounds(ctx, state_of(p));
       if (paired) {

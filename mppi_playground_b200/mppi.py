@@ -199,6 +199,26 @@ class MPPI(nn.Module):
                                                    float(cell), float(ox), float(oy)))
         self._map_identity = ident
 
+    def rasterise_map(self, slot: int, raster, want_grid: bool = False) -> Optional[torch.Tensor]:
+        """Build the occupancy grid of map ``slot`` on the device from a shape list (``maps.ObstacleRaster`` /
+        ``maps.LaneRaster``) - the device twin of ObstacleMap.add_*_obstacle / LaneMap.populate_map
+        (obstacle_map_2d.py:103-160, lane_map_2d.py:68-88) - and bind it to the solver without an fp32 grid
+        round trip. ``want_grid`` also returns the reference's ``_map_torch`` ([W,H] fp32 0/1)."""
+        from .maps import flatten_shapes
+
+        discs, rects = flatten_shapes(raster)
+        grid = torch.empty(raster.width, raster.height, device=self._device) if want_grid else None
+        i32p = C.POINTER(C.c_int32)
+        with torch.cuda.device(self._device):
+            _capi.check(self._lib.mppi_raster_map(
+                self._h, slot, raster.mode, raster.width, raster.height, float(raster.cell_size),
+                float(raster.origin[0]), float(raster.origin[1]), discs.ctypes.data_as(i32p), len(discs),
+                rects.ctypes.data_as(i32p), len(rects), _ptr(grid)))
+        # the grids now live in the engine: stop mirroring the binding's map objects for this solver
+        ident_fn = getattr(self._binding, "map_identity", None)
+        self._map_identity = ident_fn() if ident_fn else "static"
+        return grid
+
     def _refresh_params(self) -> None:
         p = self._binding.params(strict=True)
         if p != self._params_cache:
@@ -239,9 +259,13 @@ class MPPI(nn.Module):
         if noise is not None:
             noise = torch.as_tensor(noise).detach().to(self._device, torch.float32).contiguous()
             lo = self._shard_lo
+            self.__dict__["_noise_full"] = None
             if tuple(noise.shape) == (self._num_samples, T, du) and self._world > 1:
+                self.__dict__["_noise_full"] = noise  # get_top_samples re-rolls other ranks' winners from it
                 noise = noise[lo:lo + self._local_samples].contiguous()
             assert tuple(noise.shape) == (self._local_samples, T, du)
+        else:
+            self.__dict__["_noise_full"] = None
         self.__dict__["_noise_keepalive"] = (noise, st, ref)  # plain dict write: nn.Module.__setattr__ is slow
         action = torch.empty(T, du, device=self._device, dtype=torch.float32)
         states = torch.empty(T + 1, ds, device=self._device, dtype=torch.float32)
@@ -347,12 +371,100 @@ class MPPI(nn.Module):
         ``([n, T+1, ds], [n])``. Re-rolled on demand instead of stored."""
         assert num_samples <= self._num_samples
         if self._world > 1:
-            raise NotImplementedError("get_top_samples on a sharded solver returns are not merged across ranks yet")
+            _, _, _, top = self.step_epilogue(top_n=num_samples)
+            return top
         traj = torch.empty(num_samples, self._horizon + 1, self._dim_state, device=self._device)
         w = torch.empty(num_samples, device=self._device)
         _capi.check(self._lib.mppi_top_samples(self._h, num_samples, traj.data_ptr(), w.data_ptr(),
                                                _stream_ptr(self._device)))
         return traj, w
+
+    def top_candidates(self, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """This rank's ``n`` best samples of the last solve as (cost [n] ascending, GLOBAL sample id [n] int32):
+        the per-rank half of ``get_top_samples`` on a sharded solver (padding: cost inf, id -1)."""
+        cost = torch.empty(n, device=self._device, dtype=torch.float32)
+        ids = torch.empty(n, device=self._device, dtype=torch.int32)
+        _capi.check(self._lib.mppi_top_candidates(self._h, n, cost.data_ptr(), ids.data_ptr(),
+                                                  _stream_ptr(self._device)))
+        return cost, ids
+
+    def _gather_candidates(self, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """One all-gather of every rank's n best (cost, id) pairs (2n words per rank)."""
+        import torch.distributed as dist
+
+        cost, ids = self.top_candidates(n)
+        mine = torch.cat([cost, ids.view(torch.float32)])  # ids travel as raw 32-bit words
+        buf = torch.empty(self._world * 2 * n, device=self._device, dtype=torch.float32)
+        dist.all_gather_into_tensor(buf, mine, group=self._pg)
+        buf = buf.view(self._world, 2, n)
+        return buf[:, 0].reshape(-1).contiguous(), buf[:, 1].reshape(-1).contiguous().view(torch.int32)
+
+    def step_epilogue(self, action_seq: Optional[torch.Tensor] = None, state_seq: Optional[torch.Tensor] = None,
+                      state=None, goal=None, goal_threshold: float = 0.0, top_n: int = 0, candidates=None):
+        """The control-step epilogue of the reference's loops (example/racing.py:233-237,
+        example/navigation2d.py:39-44) in one launch: ``env.step(action_seq[0])`` (racing_env.py:142-163),
+        ``env.collision_check(state_seq)`` (:374-384) and ``solver.get_top_samples(top_n)`` (mppi.py:462-487).
+
+        Returns ``(next_state [ds], is_goal_reached (0-dim bool), is_collisions [1, T+1], (top_traj, top_w))``;
+        groups that were not asked for are ``None``. ``state`` defaults to the state of the last solve;
+        ``goal`` = (x, y) with ``goal_threshold`` as in the env's ``step``. On a sharded solver the top samples
+        are merged across ranks (one all-gather of each rank's ``top_n`` best); ``candidates`` = (costs, ids)
+        replaces that gather (shards driven by one process)."""
+        T, ds = self._horizon, self._dim_state
+        a = _capi.MppiStepEpilogue()
+        keep = []
+        want_step = action_seq is not None
+        if want_step:
+            act = action_seq.detach().to(self._device, torch.float32).contiguous()
+            assert tuple(act.shape) == (T, self._dim_control)
+            nxt = torch.empty(ds, device=self._device)
+            a.d_action_seq, a.d_next_state = act.data_ptr(), nxt.data_ptr()
+            keep += [act]
+            if state is not None:
+                st = self._device_state(state)
+                a.d_state = st.data_ptr()
+                keep += [st]
+            flags = torch.empty(T + 2, device=self._device)
+            if state_seq is not None:
+                seq = state_seq.detach().to(self._device, torch.float32).reshape(T + 1, ds).contiguous()
+                a.d_state_seq, a.d_flags = seq.data_ptr(), flags.data_ptr()
+                keep += [seq]
+            elif goal is not None:
+                seq = torch.zeros(T + 1, ds, device=self._device)
+                a.d_state_seq, a.d_flags = seq.data_ptr(), flags.data_ptr()
+                keep += [seq]
+            if goal is not None:
+                a.goal_x, a.goal_y, a.goal_threshold = float(goal[0]), float(goal[1]), float(goal_threshold)
+        else:
+            assert state_seq is None and goal is None, "collision flags / goal test come with the env step"
+        top = None
+        if top_n:
+            assert top_n <= self._num_samples  # mppi.py:476
+            if top_n > _capi.TOP_MAX:
+                raise ValueError(f"step_epilogue selects at most {_capi.TOP_MAX} top samples; use get_top_samples")
+            traj = torch.empty(top_n, T + 1, ds, device=self._device)
+            w = torch.empty(top_n, device=self._device)
+            a.top_n, a.d_top_traj, a.d_top_w = top_n, traj.data_ptr(), w.data_ptr()
+            if candidates is None and self._world > 1:
+                if self._pg is None:
+                    raise ValueError("a sharded solver without a process group needs candidates=(costs, ids)")
+                candidates = self._gather_candidates(top_n)
+            if candidates is not None:
+                cc = candidates[0].detach().to(self._device, torch.float32).contiguous()
+                ci = candidates[1].detach().to(self._device, torch.int32).contiguous()
+                assert cc.numel() == ci.numel()
+                a.d_cand_cost, a.d_cand_id, a.n_cand = cc.data_ptr(), ci.data_ptr(), cc.numel()
+                keep += [cc, ci]
+                full = self.__dict__.get("_noise_full")
+                if full is not None:
+                    a.d_noise_global = full.data_ptr()
+            top = (traj, w)
+        _capi.check(self._lib.mppi_step_epilogue(self._h, C.byref(a), _stream_ptr(self._device)))
+        self.__dict__["_epilogue_keepalive"] = keep
+        nxt_out = nxt if want_step else None
+        reached = flags[0] > 0.5 if (want_step and a.d_flags) else None
+        coll = flags[1:].view(1, T + 1) if (want_step and state_seq is not None) else None
+        return nxt_out, reached, coll, top
 
     def get_samples_from_posterior(self, optimal_solution: torch.Tensor, state: torch.Tensor, num_samples: int):
         """mppi.py:489-506: sample action sequences from N(optimal_solution, diag sigma^2)
@@ -567,9 +679,11 @@ def solve_shards_inprocess(solvers, state, noise: Optional[torch.Tensor] = None)
         sv._refresh_params()
         ref = sv._device_refpath()
         nz = None
+        sv.__dict__["_noise_full"] = None
         if noise is not None:
-            nz = torch.as_tensor(noise)[sv._shard_lo: sv._shard_lo + sv._local_samples]
-            nz = nz.detach().to(sv._device, torch.float32).contiguous()
+            full = torch.as_tensor(noise).detach().to(sv._device, torch.float32).contiguous()
+            sv.__dict__["_noise_full"] = full
+            nz = full[sv._shard_lo: sv._shard_lo + sv._local_samples].contiguous()
         sv._noise_keepalive = (nz, st, ref)
         s = _stream_ptr(sv._device)
         sv._shard_stage_rollout(st, ref, nz, s)
@@ -589,6 +703,21 @@ def solve_shards_inprocess(solvers, state, noise: Optional[torch.Tensor] = None)
         states = torch.empty(sv._horizon + 1, sv._dim_state, device=sv._device)
         sv._shard_stage_finish(gathered, st, action, states, s)
         out.append((action, states.view(1, sv._horizon + 1, sv._dim_state)))
+    return out
+
+
+def top_samples_inprocess(solvers, n: int):
+    """``get_top_samples(n)`` for shard solvers that live in ONE process: every shard's n best candidates are
+    concatenated (device copies instead of the all-gather) and each shard merges and re-rolls the global winners.
+    Returns the per-shard ``(top_traj, top_w)`` list; all entries agree."""
+    cands = [sv.top_candidates(n) for sv in solvers]
+    for sv in solvers:
+        torch.cuda.current_stream(sv._device).synchronize()
+    out = []
+    for sv in solvers:
+        cost = torch.cat([c.to(sv._device) for c, _ in cands])
+        ids = torch.cat([i.to(sv._device) for _, i in cands])
+        out.append(sv.step_epilogue(top_n=n, candidates=(cost, ids))[3])
     return out
 
 

@@ -204,6 +204,107 @@ def env_fixtures():
     print("env fixtures written")
 
 
+def epilogue_cases():
+    """Control-step epilogue: closed loops driven exactly like example/racing.py:229-237 and
+    example/navigation2d.py:36-44 - forward, env.step(action_seq[0]), env.collision_check(state_seq),
+    get_top_samples - recorded per step, plus probes that reach what the short loops do not: goal flags on both
+    sides of the threshold and occupancy flags over obstacles and beyond the map border."""
+    rng = np.random.default_rng(7)
+
+    def drive(env, solver, n_solves, pre_solve=None, top_n=64):
+        rec = {k: [] for k in ("state", "noise", "refpath", "action_seq", "state_seq", "next_state", "is_goal",
+                               "collisions", "top_traj", "top_w", "costs")}
+        state = env._robot_state.clone()
+        for _ in range(n_solves):
+            if pre_solve is not None:
+                rec["refpath"].append(pre_solve(state).numpy().copy())
+            a, ss = solver.forward(state=state.clone())
+            rec["state"].append(state.numpy().copy())
+            rec["noise"].append(solver._action_noises.numpy().copy())
+            rec["action_seq"].append(a.numpy().copy())
+            rec["state_seq"].append(ss.numpy().copy())
+            state, goal = env.step(a[0, :])
+            rec["next_state"].append(state.numpy().copy())
+            rec["is_goal"].append(bool(goal))
+            rec["collisions"].append(env.collision_check(state=ss).numpy().copy())
+            tt, tw = solver.get_top_samples(top_n)
+            rec["top_traj"].append(tt.numpy().copy())
+            rec["top_w"].append(tw.numpy().copy())
+        return {k: np.stack(v) for k, v in rec.items() if len(v)}
+
+    def probes(env, ds, du, lim):
+        goal = env._goal_pos.numpy()
+        thr = 1.0 if ds == 4 else 0.5  # racing_env.py:158 / navigation_2d.py:112
+        st = np.zeros((24, ds), dtype=np.float32)
+        st[:, :2] = goal + rng.uniform(-1.6 * thr, 1.6 * thr, size=(24, 2))
+        st[:, 2] = rng.uniform(-3.0, 3.0, size=24)
+        act = rng.uniform(-1.0, 1.0, size=(24, du)).astype(np.float32) * 3.0  # beyond the env bounds: step clamps
+        nxt, reached = [], []
+        for s_, a_ in zip(st, act):
+            env._robot_state = torch.tensor(s_)
+            n_, g_ = env.step(torch.tensor(a_))
+            nxt.append(n_.numpy().copy()), reached.append(bool(g_))
+        traj = np.zeros((1, 600, ds), dtype=np.float32)
+        traj[0, :, :2] = rng.uniform(-1.15 * lim, 1.15 * lim, size=(600, 2))  # some positions beyond the border
+        coll = env.collision_check(state=torch.tensor(traj)).numpy().copy()
+        return dict(probe_state=st, probe_action=act, probe_next=np.stack(nxt), probe_goal=np.array(reached),
+                    coll_probe_in=traj, coll_probe_out=coll, goal=goal, goal_threshold=np.float32(thr))
+
+    env, ctl, ns = rh.make_racing()
+    cfg = dict(horizon=25, num_samples=1024, sigmas=[0.5, 0.1], lambda_=1.0)
+    kw = dict(cfg)
+    ctl.solver = ns.MPPI(dim_state=4, dim_control=2, dynamics=env.dynamics, cost_func=ctl.cost_function,
+                         u_min=env.u_min, u_max=env.u_max, sigmas=torch.tensor(kw.pop("sigmas")), **kw)
+
+    def pre_solve(state):
+        ctl.reference_path, ctl.current_path_index = ctl.calc_ref_trajectory(
+            state, env.racing_center_path, ctl.current_path_index, ctl.solver._horizon, DL=0.1,
+            lookahead_distance=3, reference_path_interval=0.85)
+        return ctl.reference_path
+
+    out = drive(env, ctl.solver, 4, pre_solve)
+    out.update(probes(env, 4, 2, 40.0))
+    out["cfg"] = np.array(json.dumps(dict(cfg, model="racing")))
+    out["versions"] = np.array(VERSIONS)
+    np.savez_compressed(os.path.join(OUT, "epilogue_racing.npz"), **out)
+    print("epilogue_racing: goal flags", out["probe_goal"].sum(), "/ 24, occupied probes", int(out["coll_probe_out"].sum()))
+
+    env2, ns = rh.make_navigation2d()
+    cfg2 = dict(horizon=30, num_samples=768, sigmas=[0.5, 0.5], lambda_=0.5)
+    kw = dict(cfg2)
+    solver2 = ns.MPPI(dim_state=3, dim_control=2, dynamics=env2.dynamics, cost_func=env2.cost_function,
+                      u_min=env2.u_min, u_max=env2.u_max, sigmas=torch.tensor(kw.pop("sigmas")), **kw)
+    out = drive(env2, solver2, 4)
+    out.update(probes(env2, 3, 2, 10.0))
+    out["cfg"] = np.array(json.dumps(dict(cfg2, model="navigation2d")))
+    out["versions"] = np.array(VERSIONS)
+    np.savez_compressed(os.path.join(OUT, "epilogue_navigation2d.npz"), **out)
+    print("epilogue_navigation2d: goal flags", out["probe_goal"].sum(), "/ 24, occupied probes",
+          int(out["coll_probe_out"].sum()))
+
+
+def shape_fixtures():
+    """Map construction inputs: the shapes the reference envs paint their grids from
+    (obstacle_map_2d.py:235-345 with default_rng(seed), racing_env.py:59-92, navigation_2d.py:34-51); the grids
+    themselves are already in env_racing.npz / env_navigation2d.npz."""
+    env, _, _ = rh.make_racing()
+    om = env._obstacle_map
+    env2, _ = rh.make_navigation2d()
+    om2 = env2._obstacle_map
+    np.savez_compressed(
+        os.path.join(OUT, "env_shapes.npz"),
+        racing_circle_centers=np.stack([c.center for c in om.circle_obs_list]),
+        racing_circle_radii=np.array([c.radius for c in om.circle_obs_list]),
+        racing_map_size=np.array(env.map_size), racing_cell=np.array(env.cell_size),
+        racing_lane_width=np.array(env.line_width * 0.8),
+        nav_circle_centers=np.stack([c.center for c in om2.circle_obs_list]),
+        nav_circle_radii=np.array([c.radius for c in om2.circle_obs_list]),
+        nav_rect_centers=np.stack([r.center for r in om2.rectangle_obs_list]),
+        nav_rect_wh=np.array([[r.width, r.height] for r in om2.rectangle_obs_list]),
+        nav_map_size=np.array([20, 20]), nav_cell=np.array(om2._cell_size), versions=np.array(VERSIONS))
+    print("shape fixtures written")
+
+
 def full_size_cases():
     """One recorded case per BASELINE.json size (configs[1], [2], [3]) from the live reference: native noise
     draws, the noise kept as a digest (see noise_digest), every one of the K costs kept."""
@@ -221,6 +322,10 @@ def main(only=None):
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     if only == "full":
         full_size_cases()
+        return
+    if only == "epilogue":
+        epilogue_cases()
+        shape_fixtures()
         return
     if only is None:
         env_fixtures()
@@ -258,4 +363,5 @@ def main(only=None):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else None)  # `extra`: only the later-added models; `full`: BASELINE sizes
+    # `extra`: only the later-added models; `full`: BASELINE sizes; `epilogue`: control-step epilogue + map shapes
+    main(sys.argv[1] if len(sys.argv) > 1 else None)

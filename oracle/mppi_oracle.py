@@ -742,3 +742,70 @@ class OracleMPPI:
         w = self.weights[idx]
         order = torch.argsort(w, descending=True)
         return self.state_seq_batch[idx][order], w[order]
+
+
+# ----------------------------------------------------------------------------
+# control-step epilogue (SURVEY 8f "next" row 2): what the reference's loops run between two solves
+# ----------------------------------------------------------------------------
+
+
+def env_step(model, state: torch.Tensor, action: torch.Tensor, goal, goal_threshold: float):
+    """``RacingEnv.step`` src/envs/racing_env.py:142-163 (== ``Navigation2DEnv.step`` navigation_2d.py:97-117):
+    clamp the executed action to the env bounds, one batch-1 dynamics step, goal test. ``model`` is one of the
+    oracle models above (its ``dynamics`` is the env's); returns ``(next_state [ds], is_goal_reached bool)``."""
+    u = action
+    if hasattr(model, "u_min"):
+        u = torch.clamp(action, model.u_min, model.u_max)  # :151 / :105
+    nxt = model.dynamics(state.view(1, -1), u.view(1, -1)).squeeze(0)  # :153-155
+    goal_t = torch.as_tensor(goal, dtype=torch.float32)
+    reached = bool(torch.norm(nxt[:2] - goal_t) < goal_threshold)  # :158-161
+    return nxt, reached
+
+
+def collision_check(obstacle: GridMap, state_seq: torch.Tensor) -> torch.Tensor:
+    """``RacingEnv.collision_check`` src/envs/racing_env.py:374-384 (== navigation_2d.py:281-291): obstacle-map
+    value of every predicted position. ``state_seq`` [B, L, ds] -> [B, L] (the reference's ``squeeze(1)`` is a
+    no-op for L > 1)."""
+    return obstacle.lookup(state_seq[:, :, :2])
+
+
+# ----------------------------------------------------------------------------
+# map construction (SURVEY 8f "next" row 4), numpy restatements of the reference's painters
+# ----------------------------------------------------------------------------
+
+
+def paint_obstacle_map(width: int, height: int, discs, rects) -> np.ndarray:
+    """``ObstacleMap.add_circle_obstacle`` / ``add_rectangle_obstacle`` src/envs/obstacle_map_2d.py:103-160 on a
+    zero [width, height] grid. ``discs`` = (centre cell x, y, radius_occ**2) per circle, ``rects`` = the clipped
+    (x_init, x_end, y_init, y_end) per rectangle - the host conversions of mppi_playground_b200/maps.py (the
+    reference's fp64 expressions, checked against the live reference in tests/test_reference_live.py)."""
+    grid = np.zeros((width, height))
+    for cx, cy, r2 in discs:
+        r = int(math.isqrt(int(r2)))
+        i = np.arange(-r, r + 1)
+        ii, jj = np.meshgrid(i, i, indexing="ij")
+        hit = ii**2 + jj**2 <= r2  # :120
+        xs = np.clip(cx + ii[hit], 0, width - 1)  # :121-122 (indices are clipped, not dropped)
+        ys = np.clip(cy + jj[hit], 0, height - 1)
+        grid[xs, ys] = 1  # :123
+    for x0, x1, y0, y1 in rects:
+        grid[x0:x1, y0:y1] = 1  # :156
+    return grid
+
+
+def paint_lane_map(width: int, height: int, cells, r2: int) -> np.ndarray:
+    """``LaneMap.populate_map`` src/envs/lane_map_2d.py:68-88: ones, the in-map centre-line ``cells`` zeroed, then
+    ``distance_transform_edt(map) <= max_distance`` -> 0 else 1, with the threshold expressed as the largest
+    accepted integer squared cell distance ``r2`` (maps.LaneRaster). Brute-force nearest-cell distance in exact
+    integer arithmetic (the EDT's value is sqrt of exactly this integer)."""
+    cells = np.asarray(cells, dtype=np.int64).reshape(-1, 2)
+    best = np.full((width, height), np.iinfo(np.int64).max, dtype=np.int64)
+    xs = np.arange(width, dtype=np.int64)[:, None]
+    ys = np.arange(height, dtype=np.int64)[None, :]
+    r = int(math.isqrt(max(int(r2), 0)))
+    for cx, cy in cells:  # only the (2r+1)^2 window around a centre cell can pass the threshold
+        x0, x1 = max(cx - r, 0), min(cx + r + 1, width)
+        y0, y1 = max(cy - r, 0), min(cy + r + 1, height)
+        d2 = (xs[x0:x1] - cx) ** 2 + (ys[:, y0:y1] - cy) ** 2
+        np.minimum(best[x0:x1, y0:y1], d2, out=best[x0:x1, y0:y1])
+    return np.where(best <= r2, 0, 1).astype(np.float64)

@@ -14,7 +14,7 @@ import re
 import subprocess
 import sys
 
-SYMBOL = "_ZN4mppi12solve_kernelINS_6RacingELb0ELi0ELi2EEEvNS_11SolveParamsE"  # <Racing, inject=false, kFused, SPT=2>
+SYMBOL = "_ZN4mppi12solve_kernelINS_6RacingELb0ELi0ELi2ELb0EEEvNS_11SolveParamsE"  # <Racing, inject=false, kFused, SPT=2, staged maps>
 SAMPLE_STEPS_PER_ITER = 4  # one Philox chunk per sample = 2 time steps, two samples per thread
 GROUPS = [
     ("fp32 arithmetic (FADD/FMUL/FFMA/FMNMX/FSEL/FSETP)", ("FADD", "FMUL", "FFMA", "FMNMX", "FSEL", "FSETP", "HFMA2")),

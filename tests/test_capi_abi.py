@@ -33,20 +33,22 @@ def test_library_exports_every_declared_symbol():
     assert lib.mppi_abi_version() == _capi.ABI_VERSION
 
 
-def test_config_struct_layout_matches_header(tmp_path):
-    fields = [f[0] for f in _capi.MppiConfig._fields_]
+@pytest.mark.parametrize("name", ["MppiConfig", "MppiStepEpilogue", "MppiFp32Report"])
+def test_struct_layouts_match_header(tmp_path, name):
+    mirror = getattr(_capi, name)
+    fields = [f[0] for f in mirror._fields_]
     prog = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){",
-            'printf("%zu\\n", sizeof(MppiConfig));']
-    prog += [f'printf("%zu\\n", offsetof(MppiConfig, {f}));' for f in fields]
+            f'printf("%zu\\n", sizeof({name}));']
+    prog += [f'printf("%zu\\n", offsetof({name}, {f}));' for f in fields]
     prog += ["return 0;}"]
     c = tmp_path / "layout.c"
     c.write_text("\n".join(prog))
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-std=c99", "-o", str(exe), str(c)])
     out = [int(x) for x in subprocess.check_output([str(exe)]).split()]
-    assert out[0] == C.sizeof(_capi.MppiConfig)
+    assert out[0] == C.sizeof(mirror)
     for f, off in zip(fields, out[1:]):
-        assert getattr(_capi.MppiConfig, f).offset == off, f
+        assert getattr(mirror, f).offset == off, f
 
 
 def test_philox_known_answers():

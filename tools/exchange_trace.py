@@ -25,6 +25,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="c4", choices=sorted(bench.WORKLOADS))
 ap.add_argument("--solves", type=int, default=40)
 a = ap.parse_args()
+real_stdout = os.dup(1)  # keep stdout for the JSON (NCCL prints its version banner there)
+os.dup2(2, 1)
 rank, local_rank, world = bench.dist_env()
 device = torch.device("cuda", local_rank)
 torch.cuda.set_device(device)
@@ -65,5 +67,5 @@ if rank == 0:
            "exchange_total_us": {"min": min(ex), "median": float(np.median(ex)), "max": max(ex)},
            "note": "wait_for_peers includes the skew between the ranks' kernels (they are launched by independent "
                    "processes); send + gather_copy is the data path itself (P floats to / from every peer over NVLink)"}
-    print(json.dumps(out, indent=1))
+    os.write(real_stdout, (json.dumps(out, indent=1) + "\n").encode())
 dist.destroy_process_group()
