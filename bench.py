@@ -307,7 +307,14 @@ def run_b200(args, rank, local_rank, world):
     solver.kernel_timing(True)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    gate = torch.zeros(1, device=device)
     for i in range(args.steps):
+        if world > 1:
+            # align the ranks before every timed step (outside the per-step events): the ranks are independent
+            # processes whose L2-flush memsets drift apart by tens of us, and a rank that starts early would
+            # charge the wait for the late ones to the in-kernel exchange. In a control loop the ranks are
+            # aligned anyway: every solve starts from the broadcast of the new state.
+            dist.all_reduce(gate)
         ev[i][0].record(stream)
         solve(args.warmup + i)
         ev[i][1].record(stream)
@@ -420,6 +427,8 @@ def run_b200(args, rank, local_rank, world):
             "details": {"inputs": f"closed loop of {n_rec} recorded states"
                                   + (" + reference paths" if use_ref else "") + ", device resident",
                         "l2": "flushed between timed steps (192 MiB memset outside the per-step CUDA events)",
+                        "rank_alignment": ("4-byte NCCL all-reduce before every timed step, outside the per-step "
+                                           "events (see run_b200)") if world > 1 else None,
                         "warmup_solves_run": n_warm_run,
                         "ms_per_step_back_to_back_no_flush": b2b_ms,
                         "parallelism": (f"K sharded over {world} GPUs, one fused kernel per GPU, shard partials "

@@ -195,8 +195,9 @@ int32_t mppi_partial_floats(const MppiHandle* h);
 /* Fused peer exchange (one process per GPU on one NVLink/NVSwitch node): every rank exports a CUDA IPC
  * handle of its mailbox (64 bytes), the caller all-gathers the handles ([world][64]) and connects. From
  * then on mppi_solve / mppi_solve_host on these shard handles (fixed lambda / MPO) is ONE kernel launch
- * per GPU: the finishing block stores the shard partial into every peer's mailbox over NVLink, waits for
- * the peers' sequence flags and finishes the solve - no collective call, no second launch.
+ * per GPU: the finishing block stores the shard partial into every peer's mailbox over NVLink as 8-byte
+ * (payload, sequence number) words, polls its own mailbox until every rank's words carry this solve's number
+ * and finishes the solve - no collective call, no second launch.
  * LBPS / ESSPS handles keep using the staged mppi_shard_* path. mppi_p2p_status reports a timed-out
  * exchange (a peer that never launched its solve). */
 int mppi_p2p_export(MppiHandle* h, uint8_t handle_out[64]);
@@ -218,18 +219,20 @@ int mppi_weights(MppiHandle* h, float* d_weights, void* stream);
  * solve, weight-descending. Trajectories are not stored during the solve;
  * they are re-rolled from the sampler key (or from d_noise, which must still
  * be valid, in parity mode). d_traj [n,T+1,ds], d_w [n]. n <= 1024 runs the
- * radix select of mppi_step_epilogue (one launch up to K = 65536); larger n
- * falls back to a full radix sort of the costs. */
+ * radix select + multi-block re-roll of mppi_step_epilogue; larger n falls
+ * back to a full radix sort of the costs. */
 int mppi_top_samples(MppiHandle* h, int32_t n, float* d_traj, float* d_w, void* stream);
 /* ---- control-step epilogue ("next" row 2) ---------------------------------------------------------------
  * What the reference's control loops run between two solves (example/racing.py:233-237,
- * example/navigation2d.py:39-44), as ONE launch (plus one select level per 65536 candidates when K > 65536):
+ * example/navigation2d.py:39-44) in 1-3 small launches (step + flags + final select | winners' re-roll on one
+ * block each | one select level per 8192 candidates above 8192):
  *   env.step(action_seq[0])          src/envs/racing_env.py:142-163 / navigation_2d.py:97-117: clamp, one
  *                                    dynamics step, goal test norm(next[:2] - goal) < threshold;
  *   env.collision_check(state_seq)   racing_env.py:374-384 / navigation_2d.py:281-291: obstacle-map value of
  *                                    every predicted position;
  *   solver.get_top_samples(top_n)    mppi.py:462-487: radix SELECT of the top_n lowest costs (= highest weights;
- *                                    ties by the lower sample id) instead of a sort of all K, winners re-rolled.
+ *                                    ties by the lower sample id) instead of a sort of all K, winners re-rolled
+ *                                    (racing / navigation2d: block-parallel rollout, one block per winner).
  * Every group is optional (NULL outputs / top_n = 0). */
 typedef struct MppiStepEpilogue {
   const float* d_state;      /* [ds] env state before the step; NULL: the state of the last solve */
@@ -283,8 +286,8 @@ int mppi_map_info(const MppiHandle* h, int32_t slot, int32_t* fast_division, uin
  * slots; h_out (may be NULL) receives [min(max_blocks, grid), 24] stamps of the last solve. Row 0 is the
  * finisher block (0 start, 1 warm-up pass over, 2 all workers' tickets seen, 3 partials in shared memory,
  * 8-9 inside the combine, 5 combined, 7 SG / carry done, 10-13 inside the optimal-trajectory rollout,
- * 6 finished; sharded fused solves: 16 exchange entered, 17 partial sent to the peers, 18 all peers' flags seen,
- * 19 gathered); rows 1.. are the worker blocks (0 start, 1 inputs staged, 2 costs done, 3 weights done,
+ * 6 finished; sharded fused solves: 16 exchange entered, 17 partial sent to the peers, 18 all peers' words seen and
+ * gathered (19 = 18)); rows 1.. are the worker blocks (0 start, 1 inputs staged, 2 costs done, 3 weights done,
  * 4 partial written). Unused slots keep 0. */
 int mppi_block_trace(MppiHandle* h, int32_t enable, uint64_t* h_out, int32_t max_blocks);
 /* Exhaustive device self-test of the bounded arithmetic helpers against the general ones, over every

@@ -175,6 +175,8 @@ struct MppiHandle {
   float* d_cand_cost[2] = {nullptr, nullptr};
   int* d_cand_id[2] = {nullptr, nullptr};
   size_t cand_cap = 0;
+  float* d_win_cost = nullptr;
+  int* d_win_id = nullptr;
   RasterShape* d_shapes = nullptr;
   size_t shapes_cap = 0;
   int* d_idx_in = nullptr;
@@ -723,6 +725,8 @@ void mppi_destroy(MppiHandle* h) {
     cudaFree(h->d_cand_cost[i]);
     cudaFree(h->d_cand_id[i]);
   }
+  cudaFree(h->d_win_cost);
+  cudaFree(h->d_win_id);
   cudaFree(h->d_shapes);
   cudaFree(h->d_idx_in);
   cudaFree(h->d_idx_out);
@@ -1177,7 +1181,7 @@ static int run_select_levels(MppiHandle* h, TopSource* src, int n, cudaStream_t 
       h->cand_cap = need;
     }
     const int dst = side & 1;
-    topn_select_kernel<<<(unsigned)blocks, kTopThreads, 0, st>>>(*src, n, h->d_cand_cost[dst], h->d_cand_id[dst]);
+    topn_select_kernel<<<(unsigned)blocks, kTopThreads, 0, st>>>(*src, n, 0, h->d_cand_cost[dst], h->d_cand_id[dst]);
     CUDA_TRY(cudaGetLastError());
     h->last_epilogue_launches++;
     src->costs = h->d_cand_cost[dst];
@@ -1189,26 +1193,45 @@ static int run_select_levels(MppiHandle* h, TopSource* src, int n, cudaStream_t 
   return MPPI_OK;
 }
 
+struct RerollArgs {
+  long long noise_id_base;
+  float* traj;
+  float* w;
+};
+
 template <class M>
-static int launch_epilogue(MppiHandle* h, const SolveParams& p, const EpilogueParams& e, cudaStream_t st) {
+static int launch_epilogue(MppiHandle* h, const SolveParams& p, const EpilogueParams& e, const RerollArgs& r,
+                           cudaStream_t st) {
+  control_epilogue_kernel<M><<<1, kTopThreads, 0, st>>>(p, e);
+  CUDA_TRY(cudaGetLastError());
+  h->last_epilogue_launches++;
+  if (e.top_n <= 0) return MPPI_OK;
+  const int n = e.top_n;
+  unsigned grid = (unsigned)((n + 31) / 32), block = 32, smem = 0;
+  if constexpr (M::kParallelTail) {
+    grid = (unsigned)n;
+    block = 128;
+    smem = ((unsigned)h->E_pad + (unsigned)tail_per_step<M>() * (unsigned)(h->cfg.horizon + 9) + 16u) * 4u;
+  }
   if (p.noise)
-    control_epilogue_kernel<M, true><<<1, kTopThreads, 0, st>>>(p, e);
+    reroll_winners_kernel<M, true><<<grid, block, smem, st>>>(p, e.top_cost, e.top_id, r.noise_id_base, n, r.traj, r.w);
   else
-    control_epilogue_kernel<M, false><<<1, kTopThreads, 0, st>>>(p, e);
+    reroll_winners_kernel<M, false><<<grid, block, smem, st>>>(p, e.top_cost, e.top_id, r.noise_id_base, n, r.traj, r.w);
   CUDA_TRY(cudaGetLastError());
   h->last_epilogue_launches++;
   return MPPI_OK;
 }
 
-static int dispatch_epilogue(MppiHandle* h, const SolveParams& p, const EpilogueParams& e, cudaStream_t st) {
+static int dispatch_epilogue(MppiHandle* h, const SolveParams& p, const EpilogueParams& e, const RerollArgs& r,
+                             cudaStream_t st) {
   switch (h->cfg.model) {
-    case MPPI_MODEL_PENDULUM: return launch_epilogue<Pendulum>(h, p, e, st);
-    case MPPI_MODEL_CARTPOLE: return launch_epilogue<Cartpole>(h, p, e, st);
-    case MPPI_MODEL_MOUNTAINCAR: return launch_epilogue<MountainCar>(h, p, e, st);
-    case MPPI_MODEL_NAVIGATION2D: return launch_epilogue<Navigation2D>(h, p, e, st);
-    case MPPI_MODEL_RACING: return launch_epilogue<Racing>(h, p, e, st);
-    case MPPI_MODEL_CARTPOLE_CONTINUOUS: return launch_epilogue<CartpoleContinuous>(h, p, e, st);
-    case MPPI_MODEL_GOAL_IN_DANGER_ZONE: return launch_epilogue<GoalInDangerZone>(h, p, e, st);
+    case MPPI_MODEL_PENDULUM: return launch_epilogue<Pendulum>(h, p, e, r, st);
+    case MPPI_MODEL_CARTPOLE: return launch_epilogue<Cartpole>(h, p, e, r, st);
+    case MPPI_MODEL_MOUNTAINCAR: return launch_epilogue<MountainCar>(h, p, e, r, st);
+    case MPPI_MODEL_NAVIGATION2D: return launch_epilogue<Navigation2D>(h, p, e, r, st);
+    case MPPI_MODEL_RACING: return launch_epilogue<Racing>(h, p, e, r, st);
+    case MPPI_MODEL_CARTPOLE_CONTINUOUS: return launch_epilogue<CartpoleContinuous>(h, p, e, r, st);
+    case MPPI_MODEL_GOAL_IN_DANGER_ZONE: return launch_epilogue<GoalInDangerZone>(h, p, e, r, st);
   }
   return fail(MPPI_ERR_INVALID, "unknown model");
 }
@@ -1227,7 +1250,7 @@ int mppi_top_candidates(MppiHandle* h, int32_t n, float* d_cand_cost, int32_t* d
   TopSource src{h->d_costs, nullptr, h->cfg.sample_offset, h->cfg.num_samples};
   int rc = run_select_levels(h, &src, n, st);
   if (rc) return rc;
-  topn_select_kernel<<<1, kTopThreads, 0, st>>>(src, n, d_cand_cost, d_cand_id);
+  topn_select_kernel<<<1, kTopThreads, 0, st>>>(src, n, 1, d_cand_cost, d_cand_id);
   CUDA_TRY(cudaGetLastError());
   h->last_epilogue_launches++;
   return MPPI_OK;
@@ -1264,15 +1287,17 @@ int mppi_step_epilogue(MppiHandle* h, const MppiStepEpilogue* a, void* stream) {
   e.next_state = a->d_next_state;
   e.flags = a->d_flags;
   e.top_n = want_top ? a->top_n : 0;
-  e.top_traj = a->d_top_traj;
-  e.top_w = a->d_top_w;
-  e.top_cost = a->d_top_cost;
-  e.top_id = a->d_top_id;
-  e.noise_id_base = h->cfg.sample_offset;
+  RerollArgs r{h->cfg.sample_offset, a->d_top_traj, a->d_top_w};
   if (want_top) {
+    if (!h->d_win_cost) {  // winners between the select and the re-roll launch (when the caller does not want them)
+      CUDA_TRY(cudaMalloc((void**)&h->d_win_cost, kTopMax * 4));
+      CUDA_TRY(cudaMalloc((void**)&h->d_win_id, kTopMax * 4));
+    }
+    e.top_cost = a->d_top_cost ? a->d_top_cost : h->d_win_cost;
+    e.top_id = a->d_top_id ? a->d_top_id : h->d_win_id;
     if (a->d_noise_global) {  // injected noise indexed by GLOBAL sample id (winners of other ranks included)
       p.noise = a->d_noise_global;
-      e.noise_id_base = 0;
+      r.noise_id_base = 0;
     } else if (p.noise && a->d_cand_cost && h->cfg.total_samples != K) {
       return fail(MPPI_ERR_INVALID, "merged top samples of an injected-noise solve need d_noise_global");
     }
@@ -1281,7 +1306,7 @@ int mppi_step_epilogue(MppiHandle* h, const MppiStepEpilogue* a, void* stream) {
     int rc = run_select_levels(h, &e.src, e.top_n, st);
     if (rc) return rc;
   }
-  return dispatch_epilogue(h, p, e, st);
+  return dispatch_epilogue(h, p, e, r, st);
 }
 
 int32_t mppi_last_epilogue_launches(const MppiHandle* h) { return h ? h->last_epilogue_launches : 0; }

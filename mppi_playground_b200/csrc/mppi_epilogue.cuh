@@ -7,7 +7,7 @@
 //
 // (same three calls in example/navigation2d.py:39-44 against src/envs/navigation_2d.py:97-117,281-291). In the
 // reference these are ~100 tiny ATen launches per control step plus a topk over the K weights; here they are
-// one launch (two when K > 65536): a radix SELECT of the n lowest costs (the n highest weights: the softmax is
+// a few small launches: a radix SELECT of the n lowest costs (the n highest weights: the softmax is
 // monotone) instead of a sort of all K, the winners' trajectories re-rolled from the sampler key, the executed
 // action's dynamics step, the goal test and the occupancy flags of the predicted trajectory.
 //
@@ -20,7 +20,8 @@ namespace mppi {
 
 constexpr int kTopMax = 1024;      // largest n of the select path: one CTA sorts its winners in shared memory
 constexpr int kTopThreads = 1024;  // threads of a select CTA
-constexpr int kTopSlice = 65536;   // elements one CTA selects from (64 per thread and pass, L2 resident)
+constexpr int kTopSlice = 8192;    // elements one CTA selects from: one batch of 8 per thread and pass. A single SM
+                                   // needs ~50 us for four passes over 65536 candidates (issue bound), eight SMs ~6
 constexpr int kTopBins = 2048;     // 11 bits per radix pass: 11 + 11 + 10
 
 // fp32 -> u32 whose unsigned order is the float order (negative: flip all bits, else set the sign bit)
@@ -50,9 +51,36 @@ struct TopSource {
   __device__ __forceinline__ uint32_t id(int i) const { return ids ? (uint32_t)ids[i] : (uint32_t)(id_offset + i); }
 };
 
+// Visit every element of src[lo, hi) with f(valid, key, id), the WHOLE warp in lock step (f may use warp
+// collectives; `valid` is false on the lanes that ran off the end). Loads are issued in batches of kTopBatch
+// before any is consumed: the candidates sit in L2, and one exposed ~600-cycle load per element and pass was
+// the whole cost of the first version of this kernel.
+constexpr int kTopBatch = 8;
+template <class F>
+__device__ __forceinline__ void for_each_candidate(const TopSource& src, int lo, int hi, F f) {
+  const int tid = threadIdx.x;
+  for (int b0 = lo; b0 < hi; b0 += kTopBatch * kTopThreads) {
+    float c[kTopBatch];
+    int id[kTopBatch];
+#pragma unroll
+    for (int j = 0; j < kTopBatch; ++j) {
+      const int i = b0 + j * kTopThreads + tid;
+      c[j] = (i < hi) ? __ldg(src.costs + i) : 0.0f;
+      id[j] = (i < hi && src.ids) ? __ldg(src.ids + i) : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < kTopBatch; ++j) {
+      const int i = b0 + j * kTopThreads + tid;
+      f(i < hi, ordered_key(c[j]), src.ids ? (uint32_t)id[j] : (uint32_t)(src.id_offset + i));
+    }
+  }
+}
+
 // One radix-select pass over the elements of [lo, hi) whose `value` matches (value & pmask) == pval: histogram
 // of the `bits` bits at `shift`, then the bin that holds the need-th smallest (1-based) of the matching elements.
 // kOnIds: the value is the id of the elements whose KEY equals tie_key (tie break among equal costs), else the key.
+// The histogram adds are aggregated per warp (one shared atomic per distinct bin and warp): MPPI costs crowd
+// into a handful of bins.
 template <bool kOnIds>
 __device__ __forceinline__ void radix_pass(TopShared& sh, const TopSource& src, int lo, int hi, uint32_t tie_key,
                                            uint32_t pmask, uint32_t pval, int shift, int bits, unsigned need,
@@ -61,15 +89,13 @@ __device__ __forceinline__ void radix_pass(TopShared& sh, const TopSource& src, 
   const uint32_t bmask = (1u << bits) - 1u;
   for (int b = tid; b < kTopBins; b += kTopThreads) sh.hist[b] = 0u;
   __syncthreads();
-  for (int i = lo + tid; i < hi; i += kTopThreads) {
-    const uint32_t k = src.key(i);
-    uint32_t v = k;
-    if (kOnIds) {
-      if (k != tie_key) continue;
-      v = src.id(i);
-    }
-    if ((v & pmask) == pval) atomicAdd(&sh.hist[(v >> shift) & bmask], 1u);
-  }
+  for_each_candidate(src, lo, hi, [&](bool valid, uint32_t k, uint32_t id) {
+    const uint32_t v = kOnIds ? id : k;
+    const bool counted = valid && (!kOnIds || k == tie_key) && ((v & pmask) == pval);
+    const uint32_t b = counted ? ((v >> shift) & bmask) : 0xffffffffu;
+    const unsigned same = __match_any_sync(kFullMask, b);
+    if (counted && lane == __ffs(same) - 1) atomicAdd(&sh.hist[b], (unsigned)__popc(same));
+  });
   __syncthreads();
   // exclusive scan over the 2048 bins, two bins per thread
   const unsigned a = sh.hist[2 * tid], b = sh.hist[2 * tid + 1], s = a + b;
@@ -81,8 +107,9 @@ __device__ __forceinline__ void radix_pass(TopShared& sh, const TopSource& src, 
   }
   if (lane == 31) sh.warp_tot[warp] = incl;
   __syncthreads();
-  unsigned base = 0;
-  for (int w = 0; w < warp; ++w) base += sh.warp_tot[w];
+  unsigned base = (lane < warp) ? sh.warp_tot[lane] : 0u;  // sum of the lower warps' totals (kTopThreads / 32 = 32 warps)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) base += __shfl_xor_sync(kFullMask, base, o);
   const unsigned excl = base + incl - s;
   if (need > excl && need <= excl + a) {
     sh.sel_bin = 2u * tid;
@@ -102,7 +129,8 @@ __device__ __forceinline__ void radix_pass(TopShared& sh, const TopSource& src, 
 
 // The n smallest (key, id) pairs of src[lo, hi), ascending, into sh.win[0 .. n) (entries beyond the number of
 // elements stay ~0). Whole CTA of kTopThreads threads; 1 <= n <= kTopMax.
-__device__ __forceinline__ void block_select_topn(TopShared& sh, const TopSource& src, int lo, int hi, int n) {
+__device__ __forceinline__ void block_select_topn(TopShared& sh, const TopSource& src, int lo, int hi, int n,
+                                                  bool sorted = true) {
   const int tid = threadIdx.x;
   const int count = hi - lo;
   uint32_t kth = 0xffffffffu, id_th = 0xffffffffu;  // select key < kth, or key == kth and id <= id_th
@@ -131,14 +159,14 @@ __device__ __forceinline__ void block_select_topn(TopShared& sh, const TopSource
   for (int i = tid; i < kTopMax; i += kTopThreads) sh.win[i] = ~0ull;
   if (tid == 0) sh.count = 0u;
   __syncthreads();
-  for (int i = lo + tid; i < hi; i += kTopThreads) {
-    const uint32_t k = src.key(i), id = src.id(i);
-    if (k < kth || (k == kth && id <= id_th)) {
+  for_each_candidate(src, lo, hi, [&](bool valid, uint32_t k, uint32_t id) {
+    if (valid && (k < kth || (k == kth && id <= id_th))) {
       const unsigned pos = atomicAdd(&sh.count, 1u);
       if (pos < (unsigned)kTopMax) sh.win[pos] = ((unsigned long long)k << 32) | id;
     }
-  }
+  });
   __syncthreads();
+  if (!sorted) return;  // an inner level of the select tree: the next level only needs the SET of winners
   // bitonic sort of the next power of two >= n entries (the pairs are unique: ids differ)
   int N = 2;
   while (N < n) N <<= 1;
@@ -159,12 +187,13 @@ __device__ __forceinline__ void block_select_topn(TopShared& sh, const TopSource
 
 // Level of the select tree: CTA b reduces slice b of the candidates to its n best, [gridDim.x, n] pairs out
 // (cost +inf / id -1 where a slice holds fewer than n elements).
-__global__ void __launch_bounds__(kTopThreads, 1) topn_select_kernel(TopSource src, int n, float* __restrict__ out_cost,
+__global__ void __launch_bounds__(kTopThreads, 1) topn_select_kernel(const __grid_constant__ TopSource src, int n,
+                                                                     int sorted, float* __restrict__ out_cost,
                                                                      int* __restrict__ out_id) {
   __shared__ TopShared sh;
   const int lo = (int)min((long long)blockIdx.x * kTopSlice, (long long)src.count);
   const int hi = (int)min((long long)lo + kTopSlice, (long long)src.count);
-  block_select_topn(sh, src, lo, hi, n);
+  block_select_topn(sh, src, lo, hi, n, sorted != 0);
   for (int i = threadIdx.x; i < n; i += kTopThreads) {
     const unsigned long long e = sh.win[i];
     const uint32_t id = (uint32_t)e;
@@ -217,16 +246,15 @@ struct EpilogueParams {
   // get_top_samples
   TopSource src;
   int top_n;                // 0: none
-  long long noise_id_base;  // kInject: noise row of global id g is g - noise_id_base
-  float* top_traj;          // [top_n, T+1, ds]
-  float* top_w;             // [top_n]
-  float* top_cost;          // optional [top_n] winners' costs / global ids (tests, cross-rank merge)
-  int* top_id;
+  float* top_cost;          // [top_n] winners' costs (ascending) / global sample ids, re-rolled by
+  int* top_id;              // reroll_winners_kernel
 };
 
-// One CTA: the control-step epilogue. Launched alone (K <= kTopSlice) or after topn_select_kernel levels.
-template <class M, bool kInject>
-__global__ void __launch_bounds__(kTopThreads, 1) control_epilogue_kernel(SolveParams p, EpilogueParams e) {
+// One CTA: env step, goal test, collision flags and the top-n select (alone for K <= kTopSlice, else after
+// topn_select_kernel levels); reroll_winners_kernel follows when top samples were asked for.
+template <class M>
+__global__ void __launch_bounds__(kTopThreads, 1) control_epilogue_kernel(const __grid_constant__ SolveParams p,
+                                                                          const __grid_constant__ EpilogueParams e) {
   constexpr int DS = M::DS, DU = M::DU;
   __shared__ TopShared sh;
   const int tid = threadIdx.x;
@@ -263,18 +291,63 @@ __global__ void __launch_bounds__(kTopThreads, 1) control_epilogue_kernel(SolveP
     }
   }
   if (e.top_n <= 0) return;
-  // ---- get_top_samples (mppi.py:462-487)
+  // ---- get_top_samples (mppi.py:462-487), first half: WHICH samples. Their trajectories are re-rolled by
+  //      reroll_winners_kernel on as many SMs as there are winners (one SM would spend ~100 us on 300 of them).
   block_select_topn(sh, e.src, 0, e.src.count, e.top_n);
   if (tid < e.top_n) {
     const unsigned long long w = sh.win[tid];
-    const uint32_t id = (uint32_t)w;
-    const float cost = key_to_float((uint32_t)(w >> 32));
-    const long long kg = (long long)id;
-    reroll_sample<M, kInject>(p, kg, kg - e.noise_id_base, e.top_traj + (size_t)tid * (p.T + 1) * DS);
-    const float lam = (float)p.sc->lambda_used;
-    e.top_w[tid] = expf((-cost) / lam - p.sc->xmax) / (float)p.sc->S;
-    if (e.top_cost) e.top_cost[tid] = cost;
-    if (e.top_id) e.top_id[tid] = (int)id;
+    e.top_cost[tid] = key_to_float((uint32_t)(w >> 32));
+    e.top_id[tid] = (int)(uint32_t)w;
+  }
+}
+
+// get_top_samples, second half: winner i (cost[i], global sample id[i]) rolled again from its sampler key (or the
+// injected noise) - what the reference keeps as _state_seq_batch[k] (mppi.py:280-286) - and its weight.
+// Models with a block-parallel rollout (racing, navigation2d: M::rollout_block, bit-identical to T serial step()
+// calls, see finish_solve) get one block per winner: the controls of all stages are regenerated in parallel, then
+// only the short recurrences run serially. The other models roll one winner per thread, 32 winners per block.
+template <class M, bool kInject>
+__global__ void __launch_bounds__(128, 1) reroll_winners_kernel(const __grid_constant__ SolveParams p,
+                                                                const float* __restrict__ cost,
+                                                                const int* __restrict__ id, long long noise_id_base,
+                                                                int n, float* __restrict__ traj,
+                                                                float* __restrict__ wout) {
+  constexpr int DS = M::DS, DU = M::DU;
+  const int tid = threadIdx.x;
+  const float lam = (float)p.sc->lambda_used;
+  if constexpr (M::kParallelTail) {
+    extern __shared__ __align__(16) float rr_smem[];
+    float* opt = rr_smem;                 // [E_pad] the winner's clamped controls
+    float* scratch = rr_smem + p.E_pad;   // rollout_block scratch
+    const int i = blockIdx.x;
+    const long long kg = (long long)(uint32_t)id[i];
+    const uint32_t k_lo = (uint32_t)kg, k_hi = (uint32_t)((unsigned long long)kg >> 32);
+    const bool zero_mean = kg >= p.explore_threshold;
+    const float* nz = kInject ? (p.noise + (size_t)(kg - noise_id_base) * p.T * DU) : nullptr;
+    for (int c = tid; c * 4 < p.E; c += blockDim.x) {  // one sampler chunk = 4 consecutive entries of [T*DU]
+      float z[4];
+      if (!kInject) normal4(p.key, k_lo, k_hi, (uint32_t)c, z);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = c * 4 + j;
+        if (e < p.E) {
+          const int t = e / DU, d = e - t * DU;
+          const float eps = kInject ? nz[e] : p.sigma[d] * z[j];
+          opt[e] = perturbed_entry<DU>(p, p.prev_action, zero_mean, t, d, eps);
+        }
+      }
+    }
+    __syncthreads();
+    typename M::Ctx ctx{};
+    ctx.p = &p.mp;
+    M::rollout_block(ctx, p.state, opt, p.T, traj + (size_t)i * (p.T + 1) * DS, scratch, nullptr, [](int, int) {});
+    if (tid == 0) wout[i] = expf((-cost[i]) / lam - p.sc->xmax) / (float)p.sc->S;
+  } else {
+    const int i = blockIdx.x * blockDim.x + tid;
+    if (i >= n) return;
+    const long long kg = (long long)(uint32_t)id[i];
+    reroll_sample<M, kInject>(p, kg, kg - noise_id_base, traj + (size_t)i * (p.T + 1) * DS);
+    wout[i] = expf((-cost[i]) / lam - p.sc->xmax) / (float)p.sc->S;
   }
 }
 

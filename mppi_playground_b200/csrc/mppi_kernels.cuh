@@ -87,7 +87,7 @@ struct SolveParams {
   unsigned long long* trace;  // optional [grid, kTraceSlots] %globaltimer stamps per block (profiling aid), else null
   int n_shards;  // 1: finish inside the kernel
   // fused peer exchange (NVLink P2P, one launch per solve on every GPU): each rank owns a mailbox
-  // [2 parities][kMaxPeers][P] floats followed by [2][kMaxPeers] sequence flags; peer_mailbox[r] is rank
+  // [2 parities][kMaxPeers][P] of 8-byte (payload, sequence number) words; peer_mailbox[r] is rank
   // r's mailbox mapped into this process (CUDA IPC). 0 ranks = staged path (rank_partial + finish_kernel).
   int p2p_world, p2p_rank;
   unsigned p2p_seq;  // sequence number of this solve (>= 1)
@@ -672,64 +672,66 @@ __device__ __noinline__ void finish_solve(const SolveParams& p, const FinishOut&
 // ---------------------------------------------------------------------------
 // fused shard exchange over peer memory
 // ---------------------------------------------------------------------------
-__host__ __device__ inline size_t mailbox_floats(int P) { return (size_t)2 * kMaxPeers * P + 2 * kMaxPeers; }
+// Mailbox of one rank: [2 parities][kMaxPeers][P] 8-byte words (payload bits, sequence flag).
+__host__ __device__ inline size_t mailbox_floats(int P) { return (size_t)2 * kMaxPeers * P * 2; }
 
-__device__ __forceinline__ void st_release_sys(unsigned* ptr, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
+// One 8-byte store / load that cannot tear (the LL scheme NCCL's low-latency protocol is built on): the payload
+// word and the sequence number it belongs to travel together, so the receiver needs no separate flag, the sender
+// no system-scope fence between data and flag.
+__device__ __forceinline__ void st_ll(uint2* ptr, unsigned data, unsigned flag) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(ptr), "r"(data), "r"(flag) : "memory");
 }
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* ptr) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+__device__ __forceinline__ uint2 ld_ll(const uint2* ptr) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(ptr) : "memory");
   return v;
 }
-__device__ __forceinline__ float ld_volatile(const float* ptr) {
-  float v;
-  asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(ptr) : "memory");
-  return v;
-}
 
-// Last block of every rank: push this shard's partial into every rank's mailbox (peer stores over
-// NVLink), publish a sequence flag, wait for all ranks' flags in the own mailbox, and leave the gathered
-// partials in gather_scratch. Double-buffered by the parity of the sequence number: a rank can only
-// reach solve s+2 after every rank published s+1, i.e. after every rank finished reading solve s.
+// Finisher block of every rank: push this shard's partial into every rank's mailbox (peer stores over NVLink /
+// NVSwitch), every word tagged with the solve's sequence number, then poll the own mailbox until every rank's
+// words carry that number and leave the gathered partials in gather_scratch. No fence, no flag round trip: one
+// NVLink one-way latency. Double-buffered by the parity of the sequence number: a rank can only reach solve s+2
+// after every rank's words of s+1 arrived, i.e. after every rank finished reading solve s.
 __device__ inline bool exchange_partials(const SolveParams& p, const Combined& c, const double* N) {
   const int tid = threadIdx.x, nt = blockDim.x, G = p.p2p_world, P = p.P;
   stamp(p, 16);
   const unsigned seq = p.p2p_seq, parity = seq & 1u;
   const size_t slot = ((size_t)parity * kMaxPeers + p.p2p_rank) * P;
-  for (int r = 0; r < G; ++r) {
-    float* dst = p.peer_mailbox[r] + slot;
-    for (int e = tid; e < p.E_pad; e += nt) dst[kPartialHeader + e] = (e < p.E) ? (float)N[e] : 0.0f;
-    if (tid == 0) {
-      dst[0] = c.xmax;
-      dst[1] = (float)c.S;
-      dst[2] = c.xmax_tau;
-      dst[3] = (float)c.S_tau;
-      dst[4] = (float)c.Sc_tau;
-      dst[5] = c.cmin;
-      dst[6] = c.cmax;
-      dst[7] = 0.0f;
+  for (int e = tid; e < P; e += nt) {
+    float v;
+    switch (e) {
+      case 0: v = c.xmax; break;
+      case 1: v = (float)c.S; break;
+      case 2: v = c.xmax_tau; break;
+      case 3: v = (float)c.S_tau; break;
+      case 4: v = (float)c.Sc_tau; break;
+      case 5: v = c.cmin; break;
+      case 6: v = c.cmax; break;
+      case 7: v = 0.0f; break;
+      default: v = (e - kPartialHeader < p.E) ? (float)N[e - kPartialHeader] : 0.0f;
     }
+    const unsigned bits = __float_as_uint(v);
+    for (int r = 0; r < G; ++r) st_ll(reinterpret_cast<uint2*>(p.peer_mailbox[r]) + slot + e, bits, seq);
   }
-  __threadfence_system();
-  __syncthreads();
   __shared__ int timed_out;
   if (tid == 0) timed_out = 0;
   __syncthreads();
   stamp(p, 17);  // this rank's partial is on its way to every peer
-  if (tid < G) {
-    unsigned* peer_flags = reinterpret_cast<unsigned*>(p.peer_mailbox[tid] + (size_t)2 * kMaxPeers * P);
-    st_release_sys(peer_flags + parity * kMaxPeers + p.p2p_rank, seq);
-    const unsigned* my_flags = reinterpret_cast<const unsigned*>(p.peer_mailbox[p.p2p_rank] + (size_t)2 * kMaxPeers * P);
-    const long long t0 = clock64();
-    while (ld_acquire_sys(my_flags + parity * kMaxPeers + tid) != seq) {
+  const uint2* mine = reinterpret_cast<const uint2*>(p.peer_mailbox[p.p2p_rank]) + (size_t)parity * kMaxPeers * P;
+  const long long t0 = clock64();
+  for (int i = tid; i < G * P; i += nt) {
+    uint2 w = ld_ll(mine + i);
+    while (w.y != seq) {
       if (clock64() - t0 > 4000000000LL) {  // ~2 s: a peer never arrived - do not hang the GPU
         timed_out = 1;
         break;
       }
-      __nanosleep(100);
+      __nanosleep(40);
+      w = ld_ll(mine + i);
     }
+    p.gather_scratch[i] = __uint_as_float(w.x);
   }
+  __threadfence();
   __syncthreads();
   if (timed_out) {
     if (tid == 0 && p.error_flag) {
@@ -738,11 +740,7 @@ __device__ inline bool exchange_partials(const SolveParams& p, const Combined& c
     }
     return false;
   }
-  stamp(p, 18);  // every peer's flag has arrived
-  const float* mine = p.peer_mailbox[p.p2p_rank] + (size_t)parity * kMaxPeers * P;
-  for (int i = tid; i < G * P; i += nt) p.gather_scratch[i] = ld_volatile(mine + i);
-  __threadfence();
-  __syncthreads();
+  stamp(p, 18);  // every peer's words have arrived (and are gathered)
   stamp(p, 19);
   return true;
 }
@@ -1978,7 +1976,7 @@ __global__ void pack_map_kernel(const float* __restrict__ grid, int W, int H, in
 // sigma * eps of the in-kernel sampler in the reference's [K,T,du] layout
 // (what MultivariateNormal.rsample returns, mppi.py:261-263) - tests only.
 template <int DU>
-__global__ void sample_noise_kernel(SolveParams p, float* __restrict__ out) {
+__global__ void sample_noise_kernel(const __grid_constant__ SolveParams p, float* __restrict__ out) {
   long long k_local = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k_local >= p.K) return;
   long long kg = p.k_offset + k_local;
@@ -1995,7 +1993,7 @@ __global__ void sample_noise_kernel(SolveParams p, float* __restrict__ out) {
 
 // get_top_samples (mppi.py:462-487): re-roll the selected samples, storing states.
 template <class M, bool kInject>
-__global__ void reroll_kernel(SolveParams p, const int* __restrict__ order, int n, float* __restrict__ traj,
+__global__ void reroll_kernel(const __grid_constant__ SolveParams p, const int* __restrict__ order, int n, float* __restrict__ traj,
                               float* __restrict__ wout) {
   constexpr int DS = M::DS, DU = M::DU, SPC = Chunking<DU>::kStepsPerChunk;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2033,7 +2031,7 @@ __global__ void reroll_kernel(SolveParams p, const int* __restrict__ order, int 
 
 // _states_prediction (mppi.py:508-524): roll n given action sequences [n,T,du].
 template <class M>
-__global__ void rollout_actions_kernel(SolveParams p, const float* __restrict__ actions, int n,
+__global__ void rollout_actions_kernel(const __grid_constant__ SolveParams p, const float* __restrict__ actions, int n,
                                        float* __restrict__ traj) {
   constexpr int DS = M::DS, DU = M::DU;
   int i = blockIdx.x * blockDim.x + threadIdx.x;

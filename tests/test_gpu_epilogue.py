@@ -45,7 +45,7 @@ def test_step_epilogue_matches_reference_control_loop(name):
         action, states = solver.forward(state, noise=torch.from_numpy(z["noise"][s]))
         nxt, reached, coll, (traj, w) = solver.step_epilogue(action, states, state=state, goal=goal,
                                                              goal_threshold=thr, top_n=n_top)
-        assert solver._lib.mppi_last_epilogue_launches(solver._h) == 1  # K <= 65536: ONE launch for all of it
+        assert solver._lib.mppi_last_epilogue_launches(solver._h) == 2  # K <= 8192: step + flags + select | re-roll
         # the engine's action_seq differs from the reference's by the parity tolerance; the step itself is exact
         onxt, oreached = mo.env_step(omodel, state, action[0].cpu(), goal, thr)
         np.testing.assert_allclose(nxt.cpu().numpy(), onxt.numpy(), rtol=0, atol=2e-6)
@@ -101,15 +101,15 @@ def test_step_epilogue_probes_goal_flags_clamps_and_border(name):
 
 
 TOP_CASES = [
-    (dict(model="racing", horizon=80, num_samples=65536, sigmas=[0.5, 0.1], lambda_=1.0, use_sg_filter=True), 300, 1),
-    (dict(model="racing", horizon=25, num_samples=4000, sigmas=[0.5, 0.1], lambda_=1.0), 1024, 1),
-    (dict(model="navigation2d", horizon=30, num_samples=70001, sigmas=[0.5, 0.5], lambda_="ESSPS"), 300, 2),
+    (dict(model="racing", horizon=80, num_samples=65536, sigmas=[0.5, 0.1], lambda_=1.0, use_sg_filter=True), 300, 3),
+    (dict(model="racing", horizon=25, num_samples=4000, sigmas=[0.5, 0.1], lambda_=1.0), 1024, 2),
+    (dict(model="navigation2d", horizon=30, num_samples=70001, sigmas=[0.5, 0.5], lambda_="ESSPS"), 300, 3),
     (dict(model="cartpole", horizon=50, num_samples=1048576, u_min=[-3.0], u_max=[3.0], sigmas=[1.0], lambda_=0.001,
-          state0=[0.0, 0.0, 0.05, 0.0]), 300, 2),
+          state0=[0.0, 0.0, 0.05, 0.0]), 300, 4),
     (dict(model="pendulum", horizon=20, num_samples=200, u_min=[-2.0], u_max=[2.0], sigmas=[1.0], lambda_=1.0,
-          state0=[3.0, 0.0]), 200, 1),
+          state0=[3.0, 0.0]), 200, 2),
     (dict(model="mountaincar", horizon=40, num_samples=300, u_min=[-1.0], u_max=[1.0], sigmas=[1.0], lambda_=0.1,
-          state0=[-0.5, 0.0]), 1, 1),
+          state0=[-0.5, 0.0]), 1, 2),
 ]
 
 
@@ -117,7 +117,7 @@ TOP_CASES = [
 def test_top_select_equals_stable_sort_of_all_costs(cfg, n, launches):
     """The radix select returns exactly the first n entries of a stable ascending sort of the K costs (ids and
     costs bit for bit - ties by the lower sample id), the winners' weights are softmax(-c / lambda) and their
-    trajectories are what rolling their controls gives; one launch per 65536-candidate level."""
+    trajectories are what rolling their controls gives; launches = select levels + select/step + re-roll."""
     import ctypes as C
 
     from mppi_playground_b200 import _capi

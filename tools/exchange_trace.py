@@ -46,17 +46,18 @@ else:
     state = torch.tensor(wl["state0"])
 state = state.to(device)
 lib, h = solver._lib, solver._h
+gate = torch.zeros(1, device=device)
 for s in range(a.solves):
     if s == a.solves - 1:
         _capi.check(lib.mppi_block_trace(h, 1, None, 0))
-        dist.barrier()
+    dist.all_reduce(gate)  # ranks aligned on the device before every solve, like bench.py's timed steps
     solver.forward(state)
 solver.check_exchange()
 buf = (C.c_uint64 * 24)()
 _capi.check(lib.mppi_block_trace(h, 1, buf, 1))
 t = np.array(buf, dtype=np.int64)
 mine = {"rank": rank, "workers_done_to_exchange_us": (t[16] - t[2]) / 1e3, "send_us": (t[17] - t[16]) / 1e3,
-        "wait_for_peers_us": (t[18] - t[17]) / 1e3, "gather_copy_us": (t[19] - t[18]) / 1e3,
+        "poll_and_gather_us": (t[18] - t[17]) / 1e3,
         "exchange_total_us": (t[19] - t[16]) / 1e3, "kernel_us": (t[6] - t[0]) / 1e3,
         "tail_after_exchange_us": (t[6] - t[19]) / 1e3}
 allr = [None] * world
@@ -65,7 +66,8 @@ if rank == 0:
     ex = [r["exchange_total_us"] for r in allr]
     out = {"config": a.config, "n_gpus": world, "ranks": allr,
            "exchange_total_us": {"min": min(ex), "median": float(np.median(ex)), "max": max(ex)},
-           "note": "wait_for_peers includes the skew between the ranks' kernels (they are launched by independent "
-                   "processes); send + gather_copy is the data path itself (P floats to / from every peer over NVLink)"}
+           "note": "send = P tagged 8-byte words stored to every peer over NVLink (no fence); poll_and_gather = "
+                   "waiting until every rank's words carry this solve's sequence number (includes the residual skew "
+                   "between the ranks' kernels) while copying them out"}
     os.write(real_stdout, (json.dumps(out, indent=1) + "\n").encode())
 dist.destroy_process_group()
