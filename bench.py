@@ -315,7 +315,10 @@ def run_b200(args, rank, local_rank, world):
                 # processes whose L2-flush memsets drift apart by tens of us, and a rank that starts early would
                 # charge the wait for the late ones to the in-kernel exchange. In a control loop the ranks are
                 # aligned anyway: every solve starts from the broadcast of the new state.
-                dist.all_reduce(gate)
+                if fused:
+                    _capi.check(lib.mppi_p2p_barrier(h, sp))  # all ranks leave within one NVLink latency
+                else:
+                    dist.all_reduce(gate)
             ev[i][0].record(stream)
             solve(args.warmup + i)
             ev[i][1].record(stream)
@@ -465,8 +468,9 @@ def run_b200(args, rank, local_rank, world):
             "details": {"inputs": f"closed loop of {n_rec} recorded states"
                                   + (" + reference paths" if use_ref else "") + ", device resident",
                         "l2": "flushed between timed steps (192 MiB memset outside the per-step CUDA events)",
-                        "rank_alignment": ("4-byte NCCL all-reduce before every timed step, outside the per-step "
-                                           "events (see run_b200)") if world > 1 else None,
+                        "rank_alignment": (("device-side peer barrier (mppi_p2p_barrier)" if fused else
+                                            "4-byte NCCL all-reduce") + " before every timed step, outside the "
+                                           "per-step events (see run_b200)") if world > 1 else None,
                         "warmup_solves_run": n_warm_run,
                         "ms_per_step_back_to_back_no_flush": b2b_ms,
                         "ms_per_step_kernel_timing_pass": sum(per_step_instrumented_ms) / args.steps,

@@ -203,6 +203,11 @@ int32_t mppi_partial_floats(const MppiHandle* h);
 int mppi_p2p_export(MppiHandle* h, uint8_t handle_out[64]);
 int mppi_p2p_connect(MppiHandle* h, const uint8_t* handles, int32_t world, int32_t rank);
 int mppi_p2p_status(MppiHandle* h, int32_t* timed_out);
+/* Device-side barrier across the connected ranks on `stream` (one tiny kernel: every rank flags every peer's
+ * mailbox over NVLink and waits for all flags in its own). All ranks leave within one NVLink latency of each
+ * other; bench.py uses it to start every timed step on all GPUs together. Every rank must call it the same
+ * number of times; a missing rank times out like the exchange (mppi_p2p_status reports a negative number). */
+int mppi_p2p_barrier(MppiHandle* h, void* stream);
 /* Same wiring for shard handles that live in ONE process (one process driving several GPUs with peer
  * access enabled, or several shards on one GPU): the mailboxes are plain device pointers. The shard
  * solves must then run concurrently (one stream per handle). */

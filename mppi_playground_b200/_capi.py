@@ -89,6 +89,7 @@ PROTOTYPES = {
     "mppi_p2p_export": (C.c_int, [_P, C.POINTER(C.c_uint8)]),
     "mppi_p2p_connect": (C.c_int, [_P, C.POINTER(C.c_uint8), C.c_int32, C.c_int32]),
     "mppi_p2p_status": (C.c_int, [_P, C.POINTER(C.c_int32)]),
+    "mppi_p2p_barrier": (C.c_int, [_P, _P]),
     "mppi_p2p_mailbox_ptr": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "mppi_p2p_connect_local": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_int32, C.c_int32]),
     "mppi_costs_ptr": (C.c_int, [_P, C.POINTER(_P)]),

@@ -195,6 +195,7 @@ struct MppiHandle {
   float* d_gather_scratch = nullptr;
   int* d_error_flag = nullptr;
   int p2p_world = 0, p2p_rank = 0;
+  unsigned barrier_seq = 0;
   float* peer_mailbox[kMaxPeers] = {};
   bool peer_opened[kMaxPeers] = {};
   const float* inline_state = nullptr;  // set for the duration of a host-call solve
@@ -1100,6 +1101,22 @@ int mppi_p2p_connect_local(MppiHandle* h, const uint64_t* mailbox_ptrs, int32_t 
 int mppi_p2p_mailbox_ptr(MppiHandle* h, uint64_t* ptr) {
   if (!h || !ptr) return fail(MPPI_ERR_INVALID, "null argument");
   *ptr = (uint64_t)(uintptr_t)h->d_mailbox;
+  return MPPI_OK;
+}
+
+int mppi_p2p_barrier(MppiHandle* h, void* stream) {
+  if (!h) return fail(MPPI_ERR_INVALID, "null handle");
+  if (h->p2p_world < 2) return fail(MPPI_ERR_STATE, "no peers connected (mppi_p2p_connect first)");
+  ON_DEVICE(h->device);
+  BarrierParams b{};
+  for (int r = 0; r < h->p2p_world; ++r)
+    b.peer_slots[r] = reinterpret_cast<unsigned*>(h->peer_mailbox[r] + mailbox_barrier_offset(h->P));
+  b.world = h->p2p_world;
+  b.rank = h->p2p_rank;
+  b.seq = ++h->barrier_seq;
+  b.error_flag = h->d_error_flag;
+  p2p_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(b);
+  CUDA_TRY(cudaGetLastError());
   return MPPI_OK;
 }
 

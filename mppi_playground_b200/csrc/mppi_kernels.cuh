@@ -672,8 +672,10 @@ __device__ __noinline__ void finish_solve(const SolveParams& p, const FinishOut&
 // ---------------------------------------------------------------------------
 // fused shard exchange over peer memory
 // ---------------------------------------------------------------------------
-// Mailbox of one rank: [2 parities][kMaxPeers][P] 8-byte words (payload bits, sequence flag).
-__host__ __device__ inline size_t mailbox_floats(int P) { return (size_t)2 * kMaxPeers * P * 2; }
+// Mailbox of one rank: [2 parities][kMaxPeers][P] 8-byte words (payload bits, sequence flag), then the
+// [2 parities][kMaxPeers] arrival words of the device-side rank barrier (mppi_p2p_barrier).
+__host__ __device__ inline size_t mailbox_barrier_offset(int P) { return (size_t)2 * kMaxPeers * P * 2; }
+__host__ __device__ inline size_t mailbox_floats(int P) { return mailbox_barrier_offset(P) + 2 * kMaxPeers; }
 
 // One 8-byte store / load that cannot tear (the LL scheme NCCL's low-latency protocol is built on): the payload
 // word and the sequence number it belongs to travel together, so the receiver needs no separate flag, the sender
@@ -743,6 +745,34 @@ __device__ inline bool exchange_partials(const SolveParams& p, const Combined& c
   stamp(p, 18);  // every peer's words have arrived (and are gathered)
   stamp(p, 19);
   return true;
+}
+
+// Device-side barrier across the ranks of a fused sharded solver: rank i stores the barrier's sequence number into
+// slot [parity][i] of EVERY rank's mailbox and waits until all slots of its own mailbox carry it. All ranks leave
+// within one NVLink latency of each other (a collective's completion times differ by several hops), which is
+// what a benchmark needs to start a timed step on every GPU together. Bounded wait like the exchange.
+struct BarrierParams {
+  unsigned* peer_slots[kMaxPeers];  // rank r's [2][kMaxPeers] arrival words
+  int world, rank;
+  unsigned seq;
+  int* error_flag;
+};
+__global__ void p2p_barrier_kernel(const __grid_constant__ BarrierParams b) {
+  const int r = threadIdx.x;
+  if (r >= b.world) return;
+  const unsigned parity = b.seq & 1u;
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(b.peer_slots[r] + parity * kMaxPeers + b.rank), "r"(b.seq)
+               : "memory");
+  const unsigned* mine = b.peer_slots[b.rank] + parity * kMaxPeers + r;
+  const long long t0 = clock64();
+  unsigned v;
+  do {
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if (v != b.seq && clock64() - t0 > 4000000000LL) {
+      if (b.error_flag) *reinterpret_cast<volatile int*>(b.error_flag) = -(int)(b.seq & 0x7fffffffu) - 1;
+      break;
+    }
+  } while (v != b.seq);
 }
 
 // ---------------------------------------------------------------------------

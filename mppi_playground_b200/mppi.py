@@ -281,6 +281,11 @@ class MPPI(nn.Module):
             self._sharded_solve(st, ref, noise, action, states, s)
         return action, states.view(1, T + 1, ds)
 
+    def peer_barrier(self) -> None:
+        """Device-side barrier across the ranks of a fused sharded solver on the current stream (``mppi_p2p_barrier``):
+        all GPUs pass it within one NVLink latency of each other."""
+        _capi.check(self._lib.mppi_p2p_barrier(self._h, _stream_ptr(self._device)))
+
     def check_exchange(self, synchronize: bool = True) -> None:
         """Raise if the fused peer exchange of a sharded solve timed out (a rank's kernel was not running within
         ~2 s of the others: the outputs of that solve are NaN on this rank and the carried state was not updated).

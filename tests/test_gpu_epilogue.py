@@ -332,3 +332,31 @@ def test_maps_larger_than_shared_memory_use_the_global_path():
     # a normal solver keeps the staged, paired geometry
     _, normal = build_engine(dict(model="racing", horizon=80, num_samples=65536, sigmas=[0.5, 0.1], lambda_=1.0))
     assert normal.launch_info()["smem_bytes"] > 150000
+
+
+def test_peer_barrier_between_inprocess_shards():
+    """mppi_p2p_barrier: every shard flags every peer's mailbox and waits for all flags in its own; shards driven
+    by one process on separate streams pass it together, repeatedly (double-buffered by the sequence parity), and
+    the fused solves keep working afterwards."""
+    from mppi_playground_b200.mppi import connect_shards_inprocess, solve_fused_shards_inprocess
+
+    cfg = dict(model="cartpole", horizon=20, num_samples=4096, u_min=[-3.0], u_max=[3.0], sigmas=[1.0], lambda_=0.001)
+    world = 3
+    shards = [build_engine(cfg, shard=(r, world))[1] for r in range(world)]
+    connect_shards_inprocess(shards)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    state = torch.tensor([0.0, 0.0, 0.05, 0.0])
+    for _ in range(5):
+        for sv, st in zip(shards, streams):
+            with torch.cuda.stream(st):
+                sv.peer_barrier()
+        outs = solve_fused_shards_inprocess(shards, state, streams)
+    for st in streams:
+        st.synchronize()
+    for sv in shards:
+        sv.check_exchange()
+    assert all(torch.equal(o[0], outs[0][0]) for o in outs)
+    _, single = build_engine(cfg)
+    for _ in range(5):
+        a1, _ = single.forward(state)
+    np.testing.assert_allclose(outs[0][0].cpu().numpy(), a1.cpu().numpy(), rtol=2e-5, atol=2e-6)

@@ -50,7 +50,7 @@ gate = torch.zeros(1, device=device)
 for s in range(a.solves):
     if s == a.solves - 1:
         _capi.check(lib.mppi_block_trace(h, 1, None, 0))
-    dist.all_reduce(gate)  # ranks aligned on the device before every solve, like bench.py's timed steps
+    solver.peer_barrier()  # ranks aligned on the device before every solve, like bench.py's timed steps
     solver.forward(state)
 solver.check_exchange()
 buf = (C.c_uint64 * 24)()

@@ -38,7 +38,7 @@ for cfg in CASES:
         state = fx.load_env_navigation2d().start_state.clone()
     else:
         state = torch.tensor([0.0, 0.0, 0.05, 0.0])
-    worst = 0.0
+    worst, top_diff = 0.0, None
     for s in range(3):
         if cfg["model"] == "racing":
             ref, cind = eng.racing_reference_path(state, env.center_path, cind, cfg["horizon"], v_max=env.v_max)
@@ -49,8 +49,20 @@ for cfg in CASES:
         gathered = [torch.empty_like(a) for _ in range(world)]
         dist.all_gather(gathered, a)
         assert all(torch.equal(g, gathered[0]) for g in gathered), "ranks disagree"
+        if s == 0:
+            # get_top_samples across the ranks (each rank's 300 best, one NCCL all-gather, merge, re-roll by global
+            # sample id): after the first solve the shards' costs are bit-equal to the unsharded solve's, so the
+            # winners' trajectories must be identical
+            tt, tw = sharded.get_top_samples(300)
+            both = [torch.empty_like(tt) for _ in range(world)]
+            dist.all_gather(both, tt)
+            assert all(torch.equal(g, both[0]) for g in both), "ranks disagree on the top samples"
         if rank == 0:
             a1, s1 = single.forward(state)
+            if s == 0:
+                t1, w1 = single.get_top_samples(300)
+                top_diff = float((tt - t1).abs().max())
+                assert float(((tw - w1).abs() / (w1.abs() + 1e-30)).max()) < 1e-3
             worst = max(worst, float((a - a1).abs().max()), float((st - s1).abs().max()))
             nxt = s1[0, 1].clone()
         else:
@@ -59,8 +71,8 @@ for cfg in CASES:
         state = nxt.cpu()
     if rank == 0:
         report.append({"case": f"{cfg['model']}-{cfg['lambda_']}-K{cfg['num_samples']}", "world": world,
-                       "max_abs_diff_vs_single_gpu": worst})
-        assert worst < 2e-3, report[-1]
+                       "max_abs_diff_vs_single_gpu": worst, "top_samples_300_max_abs_diff_vs_single_gpu": top_diff})
+        assert worst < 2e-3 and top_diff == 0.0, report[-1]
 if rank == 0:
     print(json.dumps(report))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
