@@ -2,7 +2,7 @@
 """Turn gpurun_out/prof_<tag>.ncu-rep + launches_<tag>.csv into the committed summaries
    profiles/r01_solve_kernel_ncu.md, profiles/r01_launches_ncu.md and profiles/ncu_traffic.json (the
    DRAM bytes and pipe figures bench.py reports as roofline.traffic / ncu_pipes). Run in the build container:
-   python profiles/summarize_ncu.py <tag>"""
+   python profiles/summarize_ncu.py <tag> [<round prefix, e.g. r02>]"""
 import collections
 import csv
 import io
@@ -11,6 +11,7 @@ import subprocess
 import sys
 
 tag = sys.argv[1]
+rnd = sys.argv[2] if len(sys.argv) > 2 else "r01"  # prefix of the committed summaries
 rep, launches = f"gpurun_out/prof_{tag}.ncu-rep", f"gpurun_out/launches_{tag}.csv"
 
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -75,7 +76,7 @@ out += ["", "## SASS evidence", "",
         f"`UBLKCP` (cp.async.bulk, TMA engine) occurrences in libmppi_b200.so: {sass.count('UBLKCP')}; "
         f"`SYNCS` (mbarrier): {sass.count('SYNCS')}; tensor-core mnemonics (`UTC*MMA`, `HMMA`): "
         f"{sass.count('UTCHMMA') + sass.count('HMMA')} (none by design: the path has no contraction)."]
-open("profiles/r01_solve_kernel_ncu.md", "w").write("\n".join(out) + "\n")
+open(f"profiles/{rnd}_solve_kernel_ncu.md", "w").write("\n".join(out) + "\n")
 
 
 def _num(name, row=rows[2]):
@@ -86,7 +87,7 @@ def _num(name, row=rows[2]):
 
 rd, wr = _num("dram__bytes_read.sum"), _num("dram__bytes_write.sum")
 json.dump({"dram_bytes_per_launch": int(rd + wr), "dram_read": int(rd), "dram_write": int(wr),
-           "source": f"profiles/r01_solve_kernel_ncu.md (ncu --set full capture {tag}, dram__bytes_read.sum + "
+           "source": f"profiles/{rnd}_solve_kernel_ncu.md (ncu --set full capture {tag}, dram__bytes_read.sum + "
                      "dram__bytes_write.sum, launch 0)",
            "pipes": {"issue_active_pct": _num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                      "fma_pipe_pct": _num("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
@@ -111,6 +112,8 @@ lo = [f"# ncu launch list, {tag}: `python bench.py --steps 6 --warmup 3 --no-cpu
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
     lo.append(f"| `{k[:100]}` | {len(v)} | {sum(v) / len(v) / 1e3:.1f} | {sum(v) / 1e3:.1f} | {100 * sum(v) / tot_t:.1f}% |")
 lo += ["", "The memset (`FillFunctor`) launches are bench.py's L2 flush between timed steps, the `pack_map` / "
-       "`check_fastdiv` launches are one-time set-up (`mppi_set_map`). Within a solve the only kernel is `solve_kernel` (100%)."]
-open("profiles/r01_launches_ncu.md", "w").write("\n".join(lo) + "\n")
+       "`check_fastdiv` launches are one-time set-up (`mppi_set_map`). Within a solve the only kernel is `solve_kernel` (100%); "
+       "`control_epilogue_kernel` / `topn_select_kernel` / `reroll_winners_kernel` are bench.py's control-step epilogue timing "
+       "(details.control_step_epilogue_us), outside the solve metric."]
+open(f"profiles/{rnd}_launches_ncu.md", "w").write("\n".join(lo) + "\n")
 print("ok")

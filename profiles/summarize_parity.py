@@ -2,6 +2,9 @@
 """gpurun_out/parity_report.jsonl (written by tests/test_gpu_parity.py on the GPU box) -> profiles/parity_r01.md."""
 import collections
 import json
+import sys
+
+rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
 
 rows = [json.loads(l) for l in open("gpurun_out/parity_report.jsonl")]
 agg = collections.OrderedDict()
@@ -11,7 +14,7 @@ for r in rows:
     for k, src in (("cost", "cost_rel_max"), ("flip", "cost_flip_frac"), ("act", "action_err"), ("st", "state_err"),
                    ("lam", "lam_rel")):
         a[k] = max(a[k], float(r[src]))
-out = ["# Parity measured on B200 (round 1)", "",
+out = [f"# Parity measured on B200 ({rnd})", "",
        "Source: `gpurun_out/parity_report.jsonl`, written by `tests/test_gpu_parity.py` on the GPU box (the last run of",
        "every test; regenerate with `python profiles/summarize_parity.py`). `golden/*`: engine fed the reference's recorded",
        "noise vs the reference's recorded outputs (`tests/golden/*.npz`, from the live reference). `native/*`: in-kernel",
@@ -30,5 +33,5 @@ out += ["", "Other GPU checks in the same suite (62 tests): exhaustive self-test
         "reference path == host twin bit for bit, full-size properties at BASELINE configs 3/4/5 (oracle on a 4096-sample",
         "subset, fp64 recomputation of the weighted mean to 2e-6, `state_seq` == rollout of `action_seq`, determinism), sampler",
         "statistics (moments, KS, independence), Philox4x32-10 known answers. Multi-GPU: `profiles/mgpu_check_r01_n{2,8}.json`."]
-open("profiles/parity_r01.md", "w").write("\n".join(out) + "\n")
+open(f"profiles/parity_{rnd}.md", "w").write("\n".join(out) + "\n")
 print(len(agg), "cases")
