@@ -25,13 +25,16 @@ out = [f"# Parity measured on B200 ({rnd})", "",
 for name in sorted(agg):
     a = agg[name]
     out.append(f"| {name} | {a['n']} | {a['cost']:.1e} | {a['flip']:.1e} | {a['act']:.1e} | {a['st']:.1e} | {a['lam']:.1e} |")
-out += ["", "Other GPU checks in the same suite (62 tests): exhaustive self-tests (`tan_quarter == tanf` on |x|<=0.78,",
-        "`sincos_bounded == sincosf` on |x|<=4, `wrap_angle_bounded` / `wrap_angle_nonneg == wrap_angle`, exact cell / wheelbase",
-        "division: 0 mismatches over all fp32 inputs of each range), bounded loop == general loop bit for bit, block-parallel",
-        "tail rollout == serial `step()` bit for bit, host-buffer solve == device-buffer solve bit for bit, sharded (2 and 3",
-        "shards, staged and fused peer exchange) == unsharded (costs bit-equal on the first solve, sequences to 2e-6), device",
-        "reference path == host twin bit for bit, full-size properties at BASELINE configs 3/4/5 (oracle on a 4096-sample",
-        "subset, fp64 recomputation of the weighted mean to 2e-6, `state_seq` == rollout of `action_seq`, determinism), sampler",
-        "statistics (moments, KS, independence), Philox4x32-10 known answers. Multi-GPU: `profiles/mgpu_check_r01_n{2,8}.json`."]
+out += ["", "Other GPU checks in the same suite (98 tests in round 2, `profiles/r02_pytest_gpu.log`): exhaustive self-tests",
+        "(`tan_quarter == tanf` on |x|<=0.78, `sincos_bounded == sincosf` on |x|<=4, the `wrap_angle_*` family == `wrap_angle`, packed",
+        "f32x2 forms == scalar forms, exact cell / wheelbase division: 0 mismatches over all fp32 inputs of each range), bounded and",
+        "paired loops == general loop bit for bit, block-parallel tail rollout == serial `step()` bit for bit, host-buffer solve ==",
+        "device-buffer solve bit for bit, sharded (2 and 3 shards, staged and fused peer exchange, peer barrier) == unsharded, fused",
+        "exchange timeout -> exception, device reference path == host twin bit for bit, drop-in objects shaped like the reference's",
+        "(`tests/test_gpu_dropin.py`), full-size golden cases recorded from the live reference (`golden-full/*`), all-K oracle",
+        "comparison at every BASELINE size (`fullsize/*`), control-step epilogue vs the reference's recorded loop and probes, top-n",
+        "select == stable sort (ids and costs bit for bit, K up to 1 048 576), sharded top samples == unsharded, device rasteriser ==",
+        "the reference's grids bit for bit, 2000 x 2000 grids through the global-memory path vs the oracle, sampler statistics,",
+        "Philox4x32-10 known answers. Multi-GPU: `profiles/mgpu_check_r02_n{2,8}.json`."]
 open(f"profiles/parity_{rnd}.md", "w").write("\n".join(out) + "\n")
 print(len(agg), "cases")
