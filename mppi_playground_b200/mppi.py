@@ -395,14 +395,8 @@ class MPPI(nn.Module):
 
     def _gather_candidates(self, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """One all-gather of every rank's n best (cost, id) pairs (2n words per rank)."""
-        import torch.distributed as dist
-
         cost, ids = self.top_candidates(n)
-        mine = torch.cat([cost, ids.view(torch.float32)])  # ids travel as raw 32-bit words
-        buf = torch.empty(self._world * 2 * n, device=self._device, dtype=torch.float32)
-        dist.all_gather_into_tensor(buf, mine, group=self._pg)
-        buf = buf.view(self._world, 2, n)
-        return buf[:, 0].reshape(-1).contiguous(), buf[:, 1].reshape(-1).contiguous().view(torch.int32)
+        return gather_candidates(cost, ids, self._world, self._pg)
 
     def step_epilogue(self, action_seq: Optional[torch.Tensor] = None, state_seq: Optional[torch.Tensor] = None,
                       state=None, goal=None, goal_threshold: float = 0.0, top_n: int = 0, candidates=None):
@@ -754,6 +748,26 @@ def gather_shards(local: torch.Tensor, total: int, world: int, group=None) -> to
         dist.all_gather(chunks, padded, group=group)
         buf = torch.cat(chunks)
     return torch.cat([buf[r * width: r * width + sizes[r]] for r in range(world)]).contiguous()
+
+
+def gather_candidates(cost: torch.Tensor, ids: torch.Tensor, world: int, group=None):
+    """All-gather of per-rank top-n candidate lists: ``cost`` [n] fp32 and ``ids`` [n] int32 (global sample ids,
+    -1 = padding) travel as ONE buffer of 2n 32-bit words per rank (the ids bit-reinterpreted, never converted).
+    Returns ``(costs [world*n], ids [world*n])`` in rank order."""
+    import torch.distributed as dist
+
+    n = cost.numel()
+    assert ids.numel() == n and cost.dtype == torch.float32 and ids.dtype == torch.int32
+    mine = torch.cat([cost.view(torch.int32), ids])  # integer words: no NaN canonicalisation anywhere on the way
+    buf = torch.empty(world * 2 * n, device=cost.device, dtype=torch.int32)
+    if hasattr(dist, "all_gather_into_tensor") and cost.is_cuda:
+        dist.all_gather_into_tensor(buf, mine, group=group)
+    else:
+        chunks = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(chunks, mine, group=group)
+        buf = torch.cat(chunks)
+    buf = buf.view(world, 2, n)
+    return buf[:, 0].reshape(-1).contiguous().view(torch.float32), buf[:, 1].reshape(-1).contiguous()
 
 
 class _CudaArrayView:

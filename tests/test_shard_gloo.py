@@ -47,6 +47,24 @@ def _worker(rank, world, port, case_name, out_dir):
         dist.all_gather(bufs, part)
         opt = sm.combine_partials(torch.stack(bufs).numpy()).reshape(case.cfg["horizon"], -1)
         np.save(os.path.join(out_dir, f"opt_{rank}.npy"), opt)
+        # (c) get_top_samples across ranks: every rank's n best (cost, GLOBAL id) pairs - the contract of
+        #     mppi_top_candidates: stable ascending order, padding (+inf, -1) when the shard is smaller than n -
+        #     travel as one buffer (ids bit-reinterpreted), and the merge of the gathered lists by (cost, id) is the
+        #     top-n of all K samples
+        from mppi_playground_b200.mppi import gather_candidates
+
+        n = 40
+        order = torch.sort(tr.costs, stable=True).indices[:n]
+        cost_l = torch.full((n,), float("inf"))
+        ids_l = torch.full((n,), -1, dtype=torch.int32)
+        cost_l[: len(order)], ids_l[: len(order)] = tr.costs[order], (order + lo).to(torch.int32)
+        cc, ci = gather_candidates(cost_l, ids_l, world)
+        assert cc.shape == (world * n,) and ci.dtype == torch.int32
+        assert torch.equal(cc[rank * n:(rank + 1) * n], cost_l) and torch.equal(ci[rank * n:(rank + 1) * n], ids_l)
+        key = np.lexsort((ci.numpy().astype(np.uint32), cc.numpy()))[:n]  # by cost, ties by (unsigned) id
+        full = torch.sort(torch.from_numpy(case.costs[0]), stable=True)
+        np.testing.assert_array_equal(ci.numpy()[key], full.indices[:n].numpy())
+        np.testing.assert_array_equal(cc.numpy()[key], full.values[:n].numpy())
     finally:
         dist.destroy_process_group()
 
