@@ -231,3 +231,69 @@ def test_live_reference_mpo_lambda_moves_under_one_ulp_of_cost_noise():
     l, a = mpo_trajectory_under_ulp_noise(make, case, "up")
     assert float(np.max(np.abs(l - base_l) / np.abs(base_l))) > 1e-3
     assert float(np.max(np.abs(a - base_a))) > 3e-4
+
+
+def test_map_rasters_from_live_map_objects_equal_the_live_grids():
+    """§8f row 4 on the live objects: the host shape conversions of mppi_playground_b200/maps.py (the product
+    half) fed from the reference's own map objects, painted by the oracle's restatement, equal the grids the
+    reference's loops / distance transform produced - including a fresh map the fixtures never saw (another seed,
+    shapes that leave the map)."""
+    import sys
+
+    from mppi_playground_b200 import maps
+    from oracle import mppi_oracle as mo
+
+    env, _, _ = rh.make_racing()
+    om, lm = env._obstacle_map, env._lane_map
+    r = maps.ObstacleRaster.from_obstacle_map(om, env.map_size)
+    assert (r.width, r.height) == om._map.shape and list(r.origin) == list(om._cell_map_origin)
+    assert r.x_lim == om.x_lim and r.y_lim == om.y_lim
+    np.testing.assert_array_equal(mo.paint_obstacle_map(r.width, r.height, r.discs, r.rects), om._map)
+    lane = maps.LaneRaster(env.racing_center_path.numpy(), env.line_width * 0.8, env.map_size, env.cell_size)
+    assert list(lane.origin) == list(lm._cell_map_origin) and lane.x_lim == lm.x_lim
+    np.testing.assert_array_equal(mo.paint_lane_map(lane.width, lane.height, [(x, y) for x, y, _ in lane.discs], lane.r2),
+                                  lm._map)
+    # a fresh reference map: circles and rectangles partly outside, odd cell size
+    ObstacleMap = sys.modules["envs.obstacle_map_2d"].ObstacleMap
+    rng = np.random.default_rng(11)
+    live = ObstacleMap(map_size=(12, 8), cell_size=0.07, device=torch.device("cpu"))
+    mine = maps.ObstacleRaster(map_size=(12, 8), cell_size=0.07)
+    for _ in range(12):
+        c, rad = rng.uniform(-7, 7, size=2), float(rng.uniform(0.2, 1.5))
+        live.add_circle_obstacle(c, rad)
+        mine.add_circle_obstacle(c, rad)
+    for _ in range(8):
+        c, w, h = rng.uniform(-7, 7, size=2), float(rng.uniform(0.3, 3.0)), float(rng.uniform(0.3, 3.0))
+        live.add_rectangle_obstacle(c, w, h)
+        mine.add_rectangle_obstacle(c, w, h)
+    assert (mine.width, mine.height) == live._map.shape
+    np.testing.assert_array_equal(mo.paint_obstacle_map(mine.width, mine.height, mine.discs, mine.rects), live._map)
+    assert live._map[0].sum() + live._map[-1].sum() > 0  # something did smear onto a border row
+
+
+def test_oracle_epilogue_matches_live_env_on_fresh_states():
+    """§8f row 2 beyond the recorded vectors: env.step / collision_check of the live envs against the oracle's
+    restatement on random states, actions beyond the bounds and positions beyond the map."""
+    from oracle import fixtures as fx
+    from oracle import mppi_oracle as mo
+
+    rng = np.random.default_rng(5)
+    for make, model, lim, thr in ((lambda: rh.make_racing()[0], fx.oracle_racing_model(), 40.0, 1.0),
+                                  (lambda: rh.make_navigation2d()[0], fx.oracle_navigation2d_model(), 10.0, 0.5)):
+        env = make()
+        ds = model.dim_state
+        goal = env._goal_pos.numpy()
+        for _ in range(40):
+            st = np.zeros(ds, dtype=np.float32)
+            st[:2] = rng.uniform(-1.1 * lim, 1.1 * lim, size=2) if rng.random() < 0.5 else goal + rng.uniform(-1.5, 1.5, 2) * thr
+            st[2:] = rng.uniform(-4.0, 4.0, size=ds - 2)
+            act = (rng.uniform(-1, 1, size=2) * 4.0).astype(np.float32)
+            env._robot_state = torch.tensor(st)
+            want_next, want_goal = env.step(torch.tensor(act))
+            nxt, reached = mo.env_step(model, torch.tensor(st), torch.tensor(act), goal, thr)
+            np.testing.assert_array_equal(nxt.numpy(), want_next.numpy())
+            assert reached == bool(want_goal)
+        traj = torch.tensor(rng.uniform(-1.2 * lim, 1.2 * lim, size=(2, 300, ds)).astype(np.float32))
+        obstacle = model.obstacle if ds == 4 else model.grid
+        np.testing.assert_array_equal(mo.collision_check(obstacle, traj).numpy(),
+                                      env.collision_check(state=traj).numpy())
