@@ -443,6 +443,13 @@ def run_b200(args, rank, local_rank, world):
         cpu_baseline = time_oracle(wl, n_timed=6 if args.config == "c4" else 2, n_warm=1, states=states_h,
                                    refs=refs_h)
 
+    aten_gpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == "c4":
+        try:
+            aten_gpu = time_oracle_on_gpu(wl, device, states_h, refs_h)
+        except Exception as e:  # context only: never lose the line over it
+            aten_gpu = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     if rank == 0:
         peaks, peak_src = measured_peaks()
         info = solver.launch_info()
@@ -478,7 +485,8 @@ def run_b200(args, rank, local_rank, world):
                                         "exchanged by peer stores over NVLink inside the kernel" if fused else
                                         f"K sharded over {world} GPUs, NCCL all-gather of the partials + finish "
                                         "kernel") if world > 1 else "single GPU, one fused kernel",
-                        "launch": info, "control_step_epilogue_us": epilogue_us},
+                        "launch": info, "control_step_epilogue_us": epilogue_us,
+                        "reference_port_on_same_gpu": aten_gpu},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": launches,
@@ -569,6 +577,42 @@ def time_oracle(wl, n_timed, n_warm, states, refs):
                       f"{n_warm} warm-up, torch CPU fp32 with {threads} threads of {os.cpu_count()} host cpus "
                       f"(thread count {how}, candidates <= 32)",
             "seconds_per_solve": med, "thread_probe_seconds_per_solve": probes}
+
+
+def time_oracle_on_gpu(wl, device, states, refs, n_timed=3, n_warm=1):
+    """Context only: the reference's algorithm as it runs with ``device='cuda'`` - the same oracle port,
+    i.e. the reference's stock ATen op sequence (~150 tiny launches per time step, every intermediate materialised),
+    with every tensor on the SAME B200. Not the product, not the CPU baseline; wall clock around synchronised solves.
+    Runs last and inside try/except: it can never cost the bench line."""
+    from engine_util import build_oracle
+
+    with torch.device(device):  # factory calls inside the oracle (zeros / tensor / empty) land on the GPU
+        omodel, oracle = build_oracle(wl["cfg"], emulate_dead_work=True)
+        for name in ("obstacle", "lane", "grid"):
+            g = getattr(omodel, name, None)
+            if g is not None and hasattr(g, "grid"):
+                g.grid, g.origin = g.grid.to(device), g.origin.to(device)
+        for k, v in list(vars(omodel).items()):
+            if torch.is_tensor(v):
+                setattr(omodel, k, v.to(device))
+        for k, v in list(vars(oracle).items()):
+            if torch.is_tensor(v):
+                setattr(oracle, k, v.to(device))
+        times = []
+        for i in range(n_warm + n_timed):
+            if wl["refpath"]:
+                omodel.reference_path = refs[i % len(refs)].to(device)
+            st = states[i % len(states)].to(device)
+            torch.cuda.synchronize(device)
+            c0 = time.perf_counter()
+            oracle.forward(st)
+            torch.cuda.synchronize(device)
+            if i >= n_warm:
+                times.append(time.perf_counter() - c0)
+    med = statistics.median(times)
+    return {"value": 1.0 / med, "unit": "solves/s", "seconds_per_solve": med,
+            "what": f"oracle port (the reference's ATen op sequence) with all tensors on the same GPU, {n_timed} "
+                    "synchronised full-K solves (median), wall clock"}
 
 
 def run_reference(args, rank, world):
