@@ -38,3 +38,24 @@ def test_gpu_arm_constants_and_fixture():
     # BASELINE.json configs[4]
     K, T, ds, du, flops, nbytes, h2d, d2h = bench.wl_numbers(bench.WORKLOADS["c5"])
     assert (K, T, ds, du) == (1048576, 50, 4, 1) and flops == K * T * 52 + K * 20 and (h2d, d2h) == (16, 200 + 816)
+
+
+def test_same_gpu_reference_leg_keeps_every_tensor_on_its_device(monkeypatch):
+    """bench.time_oracle_on_gpu (the oracle port with its tensors on the GPU, context for the CPU ratio): run on
+    the `meta` device, where any tensor the oracle would leave on the CPU raises on first use."""
+    import torch
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import bench
+    import mppi_playground_b200 as eng
+    from oracle import fixtures as fx
+
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda device=None: None)
+    wl = dict(bench.WORKLOADS["c4"])
+    wl["cfg"] = dict(wl["cfg"], num_samples=256, u_min=[-2.0, -0.25], u_max=[2.0, 0.25])
+    env = fx.load_env_racing()
+    ref, _ = eng.racing_reference_path(env.start_state, env.center_path, 0, 80, v_max=env.v_max)
+    out = bench.time_oracle_on_gpu(wl, torch.device("meta"), env.start_state.view(1, -1), ref.view(1, 81, 4),
+                                   n_timed=1, n_warm=0)
+    assert out["value"] > 0 and out["unit"] == "solves/s"
