@@ -361,35 +361,3 @@ def test_peer_barrier_between_inprocess_shards():
         a1, _ = single.forward(state)
     np.testing.assert_allclose(outs[0][0].cpu().numpy(), a1.cpu().numpy(), rtol=2e-5, atol=2e-6)
 
-
-# Written after this round's GPU budget was spent: the kernel branches below (index clipping at the map border,
-# lane discs cut by the border) were checked through a Python twin of the per-cell formula against the oracle
-# painter (300 random maps) and the painter against the LIVE reference (tests/test_reference_live.py), but this
-# test itself has not run on a GPU yet - hence non-strict xfail: a pass shows as XPASS, a failure cannot hide.
-@pytest.mark.xfail(strict=False, reason="first GPU run of this test is the round-end suite")
-def test_device_rasteriser_border_cases_match_the_oracle_painter():
-    from mppi_playground_b200 import maps
-
-    rng = np.random.default_rng(11)
-    _, solver = build_engine(dict(model="navigation2d", horizon=10, num_samples=256, sigmas=[0.5, 0.5], lambda_=1.0))
-    for trial in range(4):
-        size = [(12, 8), (4, 4), (20, 6), (8, 14)][trial]
-        cell = [0.07, 0.5, 0.11, 0.05][trial]
-        r = maps.ObstacleRaster(map_size=size, cell_size=cell)
-        for _ in range(10):
-            r.add_circle_obstacle(rng.uniform(-0.6, 0.6, size=2) * np.array(size), float(rng.uniform(0.2, 1.5)))
-        for _ in range(6):
-            r.add_rectangle_obstacle(rng.uniform(-0.6, 0.6, size=2) * np.array(size), float(rng.uniform(0.3, 3.0)),
-                                     float(rng.uniform(0.3, 3.0)))
-        grid = solver.rasterise_map(0, r, want_grid=True)
-        want = mo.paint_obstacle_map(r.width, r.height, r.discs, r.rects)
-        np.testing.assert_array_equal(grid.cpu().numpy(), want)
-        assert want[0].sum() + want[-1].sum() + want[:, 0].sum() + want[:, -1].sum() > 0  # the border is involved
-        # lane mode: a centre line that runs off the map, discs cut by the border
-        t = np.linspace(0.0, 1.0, 200)
-        lane = np.stack([(t - 0.3) * size[0] * 1.2, np.sin(6 * t) * size[1] * 0.55, np.zeros_like(t)], axis=1)
-        lr = maps.LaneRaster(lane, lane_width=float(rng.uniform(0.4, 2.0)), map_size=size, cell_size=cell)
-        lgrid = solver.rasterise_map(0, lr, want_grid=True)
-        lwant = mo.paint_lane_map(lr.width, lr.height, [(x, y) for x, y, _ in lr.discs], lr.r2)
-        np.testing.assert_array_equal(lgrid.cpu().numpy(), lwant)
-        assert 0 < lwant.sum() < lwant.size
