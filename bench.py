@@ -479,6 +479,8 @@ def run_b200(args, rank, local_rank, world):
                                             "4-byte NCCL all-reduce") + " before every timed step, outside the "
                                            "per-step events (see run_b200)") if world > 1 else None,
                         "warmup_solves_run": n_warm_run,
+                        "per_step_us": {k: float(np.percentile(np.asarray(per_step_ms) * 1e3, q)) for k, q in
+                                        (("min", 0), ("p50", 50), ("p99", 99), ("max", 100))},
                         "ms_per_step_back_to_back_no_flush": b2b_ms,
                         "ms_per_step_kernel_timing_pass": sum(per_step_instrumented_ms) / args.steps,
                         "parallelism": (f"K sharded over {world} GPUs, one fused kernel per GPU, shard partials "
